@@ -1,0 +1,921 @@
+// cuba_engine.cu -- the engine behind the C ABI of include/cuba_b200.h: device memory, the host LM
+// control loop (reference src/cuda_bundle_adjustment.cpp:793-857) and the kernel launches.
+//
+// No CPU fallback: every compute entry point needs a CUDA device and fails loudly without one.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/cuba_b200.h"
+#include "cuba_kernels.cuh"
+#include "cuba_structure.h"
+
+namespace cuba_b200 {
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CUDA_TRY(expr)                                                                                      \
+	do {                                                                                                    \
+		cudaError_t _e = (expr);                                                                            \
+		if (_e != cudaSuccess) {                                                                            \
+			char _b[512];                                                                                   \
+			snprintf(_b, sizeof(_b), "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+			return fail(CUBA_ERR_CUDA, _b);                                                                 \
+		}                                                                                                   \
+	} while (0)
+
+template <typename U>
+struct DBuf {
+	U* p = nullptr; size_t n = 0;
+	DBuf() {}
+	DBuf(const DBuf&) = delete;
+	DBuf& operator=(const DBuf&) = delete;
+	~DBuf() { release(); }
+	void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+	cudaError_t alloc(size_t count)
+	{
+		if (count == n && p) return cudaSuccess;
+		release();
+		n = count;
+		return cudaMalloc((void**)&p, sizeof(U) * (count ? count : 1));
+	}
+	cudaError_t upload(const U* h, size_t count, cudaStream_t s)
+	{
+		cudaError_t e = alloc(count);
+		if (e != cudaSuccess || !count) return e;
+		return cudaMemcpyAsync(p, h, sizeof(U) * count, cudaMemcpyHostToDevice, s);
+	}
+	cudaError_t upload(const std::vector<U>& h, cudaStream_t s) { return upload(h.data(), h.size(), s); }
+	operator U*() const { return p; }
+};
+
+// ---- NCCL through dlopen: single-GPU users never need the library ---------------------------------
+struct Nccl {
+	void* lib = nullptr;
+	typedef struct { char internal[128]; } UniqueId;
+	int (*GetUniqueId)(UniqueId*) = nullptr;
+	int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
+	int (*CommDestroy)(void*) = nullptr;
+	int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+	const char* (*GetErrorString)(int) = nullptr;
+	bool load(std::string& why)
+	{
+		if (lib) return true;
+		const char* names[] = { "libnccl.so.2", "libnccl.so" };
+		for (const char* nme : names) { lib = dlopen(nme, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+		if (!lib) { why = std::string("dlopen libnccl.so.2 failed: ") + dlerror(); return false; }
+		GetUniqueId = (int (*)(UniqueId*))dlsym(lib, "ncclGetUniqueId");
+		CommInitRank = (int (*)(void**, int, UniqueId, int))dlsym(lib, "ncclCommInitRank");
+		CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+		AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+		GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+		if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce) { why = "libnccl lacks expected symbols"; return false; }
+		return true;
+	}
+};
+static Nccl g_nccl;
+enum { NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+
+struct Scalars { double v[8]; unsigned long long maxdiag; PcgStatus pcg; };
+
+struct EngineBase {
+	virtual ~EngineBase() {}
+	cuba_config cfg{};
+	int rk_type[2] = { 0, 0 };
+	double rk_delta[2] = { 0, 0 };
+	int rank = 0, world = 1;
+	void* comm = nullptr;
+	bool haveProblem = false;
+	long long launches = 0;
+	double prof[CUBA_PROF_NUM] = { 0 };
+
+	virtual int set_problem(const cuba_problem* p) = 0;
+	virtual int set_state(const double* q, const double* t, const double* Xw) = 0;
+	virtual int get_sizes(cuba_sizes* out) const = 0;
+	virtual int optimize(int niter, cuba_iter_stat* stats, int* nstats) = 0;
+	virtual int get_state(double* q, double* t, double* Xw) = 0;
+	virtual int get_chi2(double* out) = 0;
+	virtual int get_profile(double* sec) = 0;
+	virtual int stage_linearize(double* chi) = 0;
+	virtual int stage_max_diagonal(double* md) = 0;
+	virtual int stage_solve(double lambda, int* iters, int* ok) = 0;
+	virtual int stage_update(double lambda, double* chi, double* scale) = 0;
+	virtual int stage_commit(int accept) = 0;
+	virtual int stage_chi2(double* chi) = 0;
+	virtual int dbg_hpl_structure(int32_t* colPtr, int32_t* rowInd, int32_t* e2h) = 0;
+	virtual int dbg_hsc_structure(int32_t* rowPtr, int32_t* colInd) = 0;
+	virtual int dbg_system(double* Hpp, double* bp, double* Hll, double* bl, double* Hpl) = 0;
+	virtual int dbg_schur(double* Hsc, double* bsc, double* invHll) = 0;
+	virtual int dbg_delta(double* xp, double* xl) = 0;
+	virtual int bench_stage(int stage, int reps, int flush, double lambda, double* ms) = 0;
+};
+
+template <typename T>
+struct Engine : EngineBase {
+	Structure S;
+	cudaStream_t stream = nullptr;
+	int numSMs = 0;
+	int ntiles = 0, nPoseBlocks = 0, nChiBlocks = 0;
+	int cur = 0;            // current state buffer
+	bool trialValid = false;
+	// state
+	DBuf<T> pose[2], Xw[2], cam;
+	// edge streams
+	DBuf<T> e_mx, e_my, e_mz, e_om, p_mx, p_my, p_mz, p_om;
+	DBuf<int> e_ip, e_il, e_hpl, e_user, lmPtr, tileLm, hplLm, posePtr, p_il;
+	// system
+	DBuf<T> Hpp, bp, Hll, bl, Hpl, invHll, fVal, bsc, xp, xl;
+	DBuf<int> prodPtr, prodI, prodJ, blkRow, blkCol, u2f, u2fT, fRowPtr, fColInd;
+	// pcg
+	DBuf<T> pr, pz, pq, pp0, pp1, Minv;
+	DBuf<double> pcgPartial;
+	int pcgGrid = 0;
+	// reductions
+	DBuf<double> chiPartial, scalePartialL, scalePartialP, chiSq;
+	DBuf<Scalars> dScal;
+	Scalars* hScal = nullptr;   // pinned
+	DBuf<double> flushBuf;
+	std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> profEvents;
+	std::vector<cudaEvent_t> eventPool;
+
+	~Engine() override
+	{
+		if (stream) cudaStreamSynchronize(stream);
+		for (auto& pe : profEvents) { cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second); }
+		for (auto ev : eventPool) cudaEventDestroy(ev);
+		if (hScal) cudaFreeHost(hScal);
+		if (stream) cudaStreamDestroy(stream);
+		if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+	}
+
+	int init()
+	{
+		int ndev = 0;
+		cudaError_t e = cudaGetDeviceCount(&ndev);
+		if (e != cudaSuccess || ndev <= 0)
+			return fail(CUBA_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+		if (cfg.device >= 0) CUDA_TRY(cudaSetDevice(cfg.device));
+		int dev = 0;
+		CUDA_TRY(cudaGetDevice(&dev));
+		CUDA_TRY(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev));
+		CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+		CUDA_TRY(cudaMallocHost((void**)&hScal, sizeof(Scalars)));
+		memset(hScal, 0, sizeof(Scalars));
+		CUDA_TRY(dScal.alloc(1));
+		CUDA_TRY(cudaMemsetAsync(dScal.p, 0, sizeof(Scalars), stream));
+		return CUBA_OK;
+	}
+
+	// ---- profile helpers: CUDA events on the launching stream, resolved lazily ----------------------
+	cudaEvent_t newEvent()
+	{
+		cudaEvent_t ev;
+		if (!eventPool.empty()) { ev = eventPool.back(); eventPool.pop_back(); return ev; }
+		cudaEventCreate(&ev);
+		return ev;
+	}
+	struct ProfScope {
+		Engine* e; int item; cudaEvent_t a, b;
+		ProfScope(Engine* e_, int item_) : e(e_), item(item_) { a = e->newEvent(); b = e->newEvent(); cudaEventRecord(a, e->stream); }
+		~ProfScope() { cudaEventRecord(b, e->stream); e->profEvents.push_back({ item, { a, b } }); }
+	};
+	void resolveProfile()
+	{
+		cudaStreamSynchronize(stream);
+		for (auto& pe : profEvents) {
+			float ms = 0;
+			if (cudaEventElapsedTime(&ms, pe.second.first, pe.second.second) == cudaSuccess) prof[pe.first] += 1e-3 * ms;
+			eventPool.push_back(pe.second.first); eventPool.push_back(pe.second.second);
+		}
+		profEvents.clear();
+	}
+
+	RobustParams rkParams() const
+	{
+		RobustParams r;
+		for (int i = 0; i < 2; i++) { r.type[i] = rk_type[i]; r.delta[i] = rk_delta[i]; }
+		return r;
+	}
+
+	// ---- collectives (landmark-sharded runs) ----------------------------------------------------------
+	int allreduce(void* buf, size_t count, bool isT)
+	{
+		if (world <= 1) return CUBA_OK;
+		const int dt = isT ? (sizeof(T) == 8 ? NCCL_FLOAT64 : NCCL_FLOAT32) : NCCL_FLOAT64;
+		const int rc = g_nccl.AllReduce(buf, buf, count, dt, NCCL_SUM, comm, stream);
+		if (rc != 0) return fail(CUBA_ERR_COMM, std::string("ncclAllReduce failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+		return CUBA_OK;
+	}
+
+	// ---- problem upload -------------------------------------------------------------------------------
+	int set_problem(const cuba_problem* p) override
+	{
+		if (!p) return fail(CUBA_ERR_INVALID, "set_problem: null problem");
+		const auto t0 = std::chrono::steady_clock::now();
+		const char* err = "";
+		if (!build_structure(p->Pall, p->numP, p->Lall, p->numL, p->E2, p->idx2, p->E3, p->idx3, rank, world, TILE, S, &err))
+			return fail(CUBA_ERR_INVALID, err);
+		haveProblem = false;
+		const int Pall = S.Pall, Lall = S.Lall, eL = S.eLocal;
+		// state + cameras (narrowed to T at this boundary like the reference's ScalarCast, cpp:54-69)
+		std::vector<T> hp((size_t)Pall * 8, T(0)), hc((size_t)Pall * 8, T(0)), hx((size_t)Lall * 4, T(0));
+		for (int i = 0; i < Pall; i++) {
+			for (int k = 0; k < 4; k++) hp[8 * (size_t)i + k] = (T)p->q[4 * (size_t)i + k];
+			for (int k = 0; k < 3; k++) hp[8 * (size_t)i + 4 + k] = (T)p->t[3 * (size_t)i + k];
+			for (int k = 0; k < 5; k++) hc[8 * (size_t)i + k] = (T)p->cam[5 * (size_t)i + k];
+		}
+		for (int i = 0; i < Lall; i++) for (int k = 0; k < 3; k++) hx[4 * (size_t)i + k] = (T)p->Xw[3 * (size_t)i + k];
+		for (int b = 0; b < 2; b++) { CUDA_TRY(pose[b].upload(hp, stream)); CUDA_TRY(Xw[b].upload(hx, stream)); }
+		CUDA_TRY(cam.upload(hc, stream));
+		// landmark-major edge stream
+		std::vector<T> mx(eL), my(eL), mz(eL), om(eL);
+		for (int e = 0; e < eL; e++) {
+			const int u = S.order[e];
+			if (u < S.E2) { mx[e] = (T)p->meas2[2 * (size_t)u]; my[e] = (T)p->meas2[2 * (size_t)u + 1]; mz[e] = T(0); om[e] = (T)p->omega2[u]; }
+			else { const size_t k = (size_t)(u - S.E2); mx[e] = (T)p->meas3[3 * k]; my[e] = (T)p->meas3[3 * k + 1]; mz[e] = (T)p->meas3[3 * k + 2]; om[e] = (T)p->omega3[k]; }
+		}
+		CUDA_TRY(e_mx.upload(mx, stream)); CUDA_TRY(e_my.upload(my, stream)); CUDA_TRY(e_mz.upload(mz, stream)); CUDA_TRY(e_om.upload(om, stream));
+		CUDA_TRY(e_ip.upload(S.e_ip, stream)); CUDA_TRY(e_il.upload(S.e_il, stream)); CUDA_TRY(e_hpl.upload(S.e_hpl, stream));
+		CUDA_TRY(e_user.upload(S.order, stream));
+		CUDA_TRY(lmPtr.upload(S.lmPtr, stream)); CUDA_TRY(tileLm.upload(S.tileLm, stream)); CUDA_TRY(hplLm.upload(S.hplLm, stream));
+		// pose-major stream
+		const size_t nPe = S.p_src.size();
+		std::vector<T> qx(nPe), qy(nPe), qz(nPe), qo(nPe);
+		for (size_t k = 0; k < nPe; k++) { const int e = S.p_src[k]; qx[k] = mx[e]; qy[k] = my[e]; qz[k] = mz[e]; qo[k] = om[e]; }
+		CUDA_TRY(p_mx.upload(qx, stream)); CUDA_TRY(p_my.upload(qy, stream)); CUDA_TRY(p_mz.upload(qz, stream)); CUDA_TRY(p_om.upload(qo, stream));
+		CUDA_TRY(p_il.upload(S.p_il, stream)); CUDA_TRY(posePtr.upload(S.posePtr, stream));
+		// Schur structures
+		CUDA_TRY(prodPtr.upload(S.prodPtr, stream)); CUDA_TRY(prodI.upload(S.prodI, stream)); CUDA_TRY(prodJ.upload(S.prodJ, stream));
+		CUDA_TRY(blkRow.upload(S.blkRow, stream)); CUDA_TRY(blkCol.upload(S.blkCol, stream));
+		CUDA_TRY(u2f.upload(S.u2f, stream)); CUDA_TRY(u2fT.upload(S.u2fT, stream));
+		CUDA_TRY(fRowPtr.upload(S.fRowPtr, stream)); CUDA_TRY(fColInd.upload(S.fColInd, stream));
+		// system buffers
+		const size_t nP = S.numP, nL = S.numL;
+		CUDA_TRY(Hpp.alloc(36 * nP)); CUDA_TRY(bp.alloc(6 * nP)); CUDA_TRY(Hll.alloc(9 * nL)); CUDA_TRY(bl.alloc(3 * nL));
+		CUDA_TRY(Hpl.alloc(18 * (size_t)S.nhplLocal)); CUDA_TRY(invHll.alloc(9 * nL));
+		CUDA_TRY(fVal.alloc(36 * (size_t)S.nfull)); CUDA_TRY(bsc.alloc(6 * nP)); CUDA_TRY(xp.alloc(6 * nP)); CUDA_TRY(xl.alloc(3 * nL));
+		CUDA_TRY(pr.alloc(6 * nP)); CUDA_TRY(pz.alloc(6 * nP)); CUDA_TRY(pq.alloc(6 * nP)); CUDA_TRY(pp0.alloc(6 * nP)); CUDA_TRY(pp1.alloc(6 * nP));
+		CUDA_TRY(Minv.alloc(36 * nP));
+		// landmarks outside this rank's shard keep zero Hll/bl/xl (they are never touched locally)
+		CUDA_TRY(cudaMemsetAsync(Hll.p, 0, sizeof(T) * 9 * (nL ? nL : 1), stream));
+		CUDA_TRY(cudaMemsetAsync(bl.p, 0, sizeof(T) * 3 * (nL ? nL : 1), stream));
+		CUDA_TRY(cudaMemsetAsync(xl.p, 0, sizeof(T) * 3 * (nL ? nL : 1), stream));
+		CUDA_TRY(cudaMemsetAsync(xp.p, 0, sizeof(T) * 6 * (nP ? nP : 1), stream));
+		CUDA_TRY(cudaMemsetAsync(Hpp.p, 0, sizeof(T) * 36 * (nP ? nP : 1), stream));
+		CUDA_TRY(cudaMemsetAsync(bp.p, 0, sizeof(T) * 6 * (nP ? nP : 1), stream));
+		ntiles = (int)S.tileLm.size() - 1;
+		nPoseBlocks = (S.numP + RED_BLOCK - 1) / RED_BLOCK;
+		nChiBlocks = std::max(1, std::min((eL + RED_BLOCK - 1) / RED_BLOCK, numSMs * 8));
+		CUDA_TRY(chiPartial.alloc((size_t)std::max(ntiles, nChiBlocks) + 1));
+		CUDA_TRY(scalePartialL.alloc((size_t)std::max(ntiles, (S.numL + RED_BLOCK - 1) / RED_BLOCK) + 1));
+		CUDA_TRY(scalePartialP.alloc((size_t)nPoseBlocks + 1));
+		CUDA_TRY(chiSq.alloc((size_t)S.E));
+		// cooperative grid of the PCG kernel
+		{
+			int perSM = 0;
+			CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_pcg<T>, PCG_BLOCK, 0));
+			if (perSM < 1) return fail(CUBA_ERR_CUDA, "k_pcg cannot be resident");
+			const int wantWarps = std::max(1, S.numP);
+			const int wantBlocks = (wantWarps + PCG_BLOCK / 32 - 1) / (PCG_BLOCK / 32);
+			pcgGrid = std::max(1, std::min(wantBlocks, numSMs * std::min(perSM, 2)));
+			CUDA_TRY(pcgPartial.alloc(2 * (size_t)pcgGrid));
+		}
+		CUDA_TRY(cudaStreamSynchronize(stream));
+		cur = 0; trialValid = false;
+		for (int i = 0; i < CUBA_PROF_NUM; i++) prof[i] = 0;
+		const auto t1 = std::chrono::steady_clock::now();
+		prof[CUBA_PROF_BUILD_STRUCTURE] += std::chrono::duration<double>(t1 - t0).count();
+		haveProblem = true;
+		return CUBA_OK;
+	}
+
+	int set_state(const double* q, const double* t, const double* X) override
+	{
+		if (!haveProblem) return fail(CUBA_ERR_STATE, "set_state before set_problem");
+		std::vector<T> hp((size_t)S.Pall * 8, T(0)), hx((size_t)S.Lall * 4, T(0));
+		for (int i = 0; i < S.Pall; i++) {
+			for (int k = 0; k < 4; k++) hp[8 * (size_t)i + k] = (T)q[4 * (size_t)i + k];
+			for (int k = 0; k < 3; k++) hp[8 * (size_t)i + 4 + k] = (T)t[3 * (size_t)i + k];
+		}
+		for (int i = 0; i < S.Lall; i++) for (int k = 0; k < 3; k++) hx[4 * (size_t)i + k] = (T)X[3 * (size_t)i + k];
+		for (int b = 0; b < 2; b++) { CUDA_TRY(pose[b].upload(hp, stream)); CUDA_TRY(Xw[b].upload(hx, stream)); }
+		CUDA_TRY(cudaStreamSynchronize(stream));
+		trialValid = false;
+		return CUBA_OK;
+	}
+
+	int get_sizes(cuba_sizes* o) const override
+	{
+		if (!haveProblem) return fail(CUBA_ERR_STATE, "get_sizes before set_problem");
+		o->Pall = S.Pall; o->numP = S.numP; o->Lall = S.Lall; o->numL = S.numL; o->E2 = S.E2; o->E3 = S.E3;
+		o->nhpl = S.nhpl; o->nblk = S.nblk; o->nmul = (int32_t)S.nmul; o->nblk_full = S.nfull;
+		return CUBA_OK;
+	}
+
+	// ---- launches --------------------------------------------------------------------------------------
+	ChiArgs<T> chiArgs(int buf)
+	{
+		ChiArgs<T> a;
+		a.pose = pose[buf]; a.cam = cam; a.Xw = Xw[buf];
+		a.mx = e_mx; a.my = e_my; a.mz = e_mz; a.om = e_om; a.ip = e_ip; a.il = e_il;
+		a.E = S.eLocal; a.rk = rkParams(); a.chiPartial = chiPartial;
+		return a;
+	}
+
+	int launch_linearize_landmark()
+	{
+		if (ntiles <= 0) return CUBA_OK;
+		LinLmArgs<T> a;
+		a.pose = pose[cur]; a.cam = cam; a.Xw = Xw[cur];
+		a.mx = e_mx; a.my = e_my; a.mz = e_mz; a.om = e_om; a.ip = e_ip; a.il = e_il; a.hpl = e_hpl;
+		a.lmPtr = lmPtr; a.tileLm = tileLm; a.numP = S.numP; a.numL = S.numL;
+		a.Hpl = Hpl; a.Hll = Hll; a.bl = bl; a.chiPartial = chiPartial; a.rk = rkParams();
+		k_linearize_landmark<T><<<ntiles, TILE, 0, stream>>>(a);
+		launches++;
+		CUDA_TRY(cudaGetLastError());
+		return CUBA_OK;
+	}
+	int launch_linearize_pose()
+	{
+		if (S.numP <= 0) return CUBA_OK;
+		LinPoseArgs<T> a;
+		a.pose = pose[cur]; a.cam = cam; a.Xw = Xw[cur];
+		a.mx = p_mx; a.my = p_my; a.mz = p_mz; a.om = p_om; a.il = p_il; a.posePtr = posePtr;
+		a.Hpp = Hpp; a.bp = bp; a.rk = rkParams();
+		k_linearize_pose<T><<<S.numP, POSE_BLOCK, 0, stream>>>(a);
+		launches++;
+		CUDA_TRY(cudaGetLastError());
+		return CUBA_OK;
+	}
+	// sums chiPartial[0..n) (+ optional two more arrays) into dScal->v[slot..slot+2]
+	int launch_sum(const double* p0, int n0, const double* p1, int n1, const double* p2, int n2, int slot)
+	{
+		k_sum_partials<<<1, RED_BLOCK, 0, stream>>>(p0, n0, p1, n1, p2, n2, &dScal.p->v[slot]);
+		launches++;
+		CUDA_TRY(cudaGetLastError());
+		return CUBA_OK;
+	}
+	int fetchScalars()
+	{
+		CUDA_TRY(cudaMemcpyAsync(hScal, dScal.p, sizeof(Scalars), cudaMemcpyDeviceToHost, stream));
+		CUDA_TRY(cudaStreamSynchronize(stream));
+		return CUBA_OK;
+	}
+
+	int stage_linearize(double* chi) override
+	{
+		if (!haveProblem) return fail(CUBA_ERR_STATE, "linearize before set_problem");
+		{
+			ProfScope ps(this, CUBA_PROF_BUILD_SYSTEM);
+			int rc = launch_linearize_landmark(); if (rc) return rc;
+			rc = launch_linearize_pose(); if (rc) return rc;
+			if (world > 1 && S.numP > 0) {
+				// Hpp and bp are separate buffers: two reductions (42*numP scalars in total)
+				rc = allreduce(Hpp.p, 36 * (size_t)S.numP, true); if (rc) return rc;
+				rc = allreduce(bp.p, 6 * (size_t)S.numP, true); if (rc) return rc;
+			}
+			rc = launch_sum(chiPartial, ntiles, nullptr, 0, nullptr, 0, 0); if (rc) return rc;
+			if (world > 1) { rc = allreduce(&dScal.p->v[0], 1, false); if (rc) return rc; }
+		}
+		int rc = fetchScalars(); if (rc) return rc;
+		if (chi) *chi = hScal->v[0];
+		return CUBA_OK;
+	}
+
+	int stage_chi2(double* chi) override
+	{
+		if (!haveProblem) return fail(CUBA_ERR_STATE, "chi2 before set_problem");
+		int rc = launch_chi2(cur, 0); if (rc) return rc;
+		rc = fetchScalars(); if (rc) return rc;
+		if (chi) *chi = hScal->v[0];
+		return CUBA_OK;
+	}
+
+	int launch_chi2(int buf, int slot)
+	{
+		ProfScope ps(this, CUBA_PROF_COMPUTE_ERROR);
+		if (S.eLocal > 0) {
+			k_chi2<T><<<nChiBlocks, RED_BLOCK, 0, stream>>>(chiArgs(buf));
+			launches++;
+			CUDA_TRY(cudaGetLastError());
+		}
+		int rc = launch_sum(chiPartial, S.eLocal > 0 ? nChiBlocks : 0, nullptr, 0, nullptr, 0, slot); if (rc) return rc;
+		if (world > 1) { rc = allreduce(&dScal.p->v[slot], 1, false); if (rc) return rc; }
+		return CUBA_OK;
+	}
+
+	int stage_max_diagonal(double* md) override
+	{
+		if (!haveProblem) return fail(CUBA_ERR_STATE, "max_diagonal before set_problem");
+		CUDA_TRY(cudaMemsetAsync(&dScal.p->maxdiag, 0, sizeof(unsigned long long), stream));
+		const int n = S.numP * 6 + S.numL * 3;
+		if (n > 0) {
+			const int grid = std::max(1, std::min((n + 255) / 256, numSMs * 4));
+			k_max_diagonal<T><<<grid, 256, 0, stream>>>(Hpp, S.numP, Hll, S.numL, &dScal.p->maxdiag);
+			launches++;
+			CUDA_TRY(cudaGetLastError());
+		}
+		int rc = fetchScalars(); if (rc) return rc;
+		double m;
+		memcpy(&m, &hScal->maxdiag, sizeof(double));
+		if (world > 1) {
+			// max over ranks: Hll is sharded.  One tiny host-side exchange is avoided by reducing on device:
+			// ncclMax is not loaded; use the sum trick on a one-hot buffer instead -> do a plain allreduce of
+			// the per-rank value into slot arrays.
+			std::vector<double> slots(world, 0.0);
+			slots[rank] = m;
+			DBuf<double> tmp;
+			CUDA_TRY(tmp.upload(slots, stream));
+			rc = allreduce(tmp.p, (size_t)world, false); if (rc) return rc;
+			CUDA_TRY(cudaMemcpyAsync(slots.data(), tmp.p, sizeof(double) * world, cudaMemcpyDeviceToHost, stream));
+			CUDA_TRY(cudaStreamSynchronize(stream));
+			for (double s : slots) m = std::max(m, s);
+		}
+		if (md) *md = m;
+		return CUBA_OK;
+	}
+
+	int launch_schur(T lambda)
+	{
+		ProfScope ps(this, CUBA_PROF_SCHUR_COMPLEMENT);
+		if (S.numL > 0) {
+			k_inv_hll<T><<<(S.numL + 255) / 256, 256, 0, stream>>>(Hll, S.numL, lambda, invHll);
+			launches++;
+			CUDA_TRY(cudaGetLastError());
+		}
+		if (S.numP > 0 && S.numL > 0) {
+			SchurArgs<T> a;
+			a.Hpl = Hpl; a.invHll = invHll; a.bl = bl; a.Hpp = Hpp; a.bp = bp;
+			a.prodPtr = prodPtr; a.prodI = prodI; a.prodJ = prodJ; a.hplLm = hplLm;
+			a.blkRow = blkRow; a.blkCol = blkCol; a.u2f = u2f; a.u2fT = u2fT; a.nblk = S.nblk;
+			a.lambda = lambda; a.addDiag = rank == 0 ? 1 : 0; a.fVal = fVal; a.bsc = bsc;
+			const int wpb = SCHUR_BLOCK / 32;
+			k_schur<T><<<(S.nblk + wpb - 1) / wpb, SCHUR_BLOCK, 0, stream>>>(a);
+			launches++;
+			CUDA_TRY(cudaGetLastError());
+			if (world > 1) {
+				int rc = allreduce(fVal.p, 36 * (size_t)S.nfull, true); if (rc) return rc;
+				rc = allreduce(bsc.p, 6 * (size_t)S.numP, true); if (rc) return rc;
+			}
+		}
+		return CUBA_OK;
+	}
+
+	int launch_pcg()
+	{
+		ProfScope ps(this, CUBA_PROF_DECOMP_NUMERICAL);
+		PcgArgs<T> a;
+		a.fRowPtr = fRowPtr; a.fColInd = fColInd; a.fVal = fVal; a.b = bsc; a.numP = S.numP;
+		a.x = xp; a.r = pr; a.z = pz; a.q = pq; a.p0 = pp0; a.p1 = pp1; a.Minv = Minv; a.partial = pcgPartial;
+		a.maxIters = cfg.pcg_max_iters > 0 ? cfg.pcg_max_iters : std::max(200, 40 * S.numP);
+		const double tol = cfg.pcg_tol > 0 ? cfg.pcg_tol : (sizeof(T) == 8 ? 1e-13 : 1e-6);
+		a.tol2 = tol * tol;
+		a.status = &dScal.p->pcg;
+		void* args[] = { (void*)&a };
+		CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_pcg<T>, dim3(pcgGrid), dim3(PCG_BLOCK), args, 0, stream));
+		launches++;
+		return CUBA_OK;
+	}
+
+	int launch_backsub(T lambda)
+	{
+		ProfScope ps(this, CUBA_PROF_SCHUR_COMPLEMENT);
+		if (ntiles > 0 && S.numL > 0) {
+			BacksubArgs<T> a;
+			a.Hpl = Hpl; a.invHll = invHll; a.bl = bl; a.xp = xp; a.ip = e_ip; a.hpl = e_hpl; a.lmPtr = lmPtr; a.tileLm = tileLm;
+			a.numL = S.numL; a.lambda = lambda; a.XwCur = Xw[cur]; a.XwTrial = Xw[cur ^ 1]; a.xl = xl; a.scalePartial = scalePartialL;
+			k_backsub<T><<<ntiles, TILE, 0, stream>>>(a);
+			launches++;
+			CUDA_TRY(cudaGetLastError());
+		}
+		return CUBA_OK;
+	}
+
+	// Schur + PCG + back-substitution.  Leaves xp/xl, the trial landmarks and the landmark scale partials.
+	int stage_solve(double lambda, int* iters, int* ok) override
+	{
+		if (!haveProblem) return fail(CUBA_ERR_STATE, "solve before set_problem");
+		const T lam = (T)lambda;
+		int rc = launch_schur(lam); if (rc) return rc;
+		int nScaleL = 0;
+		if (S.numP > 0 && S.numL > 0) {
+			rc = launch_pcg(); if (rc) return rc;
+			rc = launch_backsub(lam); if (rc) return rc;
+			nScaleL = ntiles;
+		} else if (S.numP > 0) {
+			k_solve_poses_only<T><<<(S.numP + 127) / 128, 128, 0, stream>>>(Hpp, bp, S.numP, lam, xp);
+			launches++;
+			CUDA_TRY(cudaGetLastError());
+			hScal->pcg.iters = 0; hScal->pcg.status = 0;
+		} else if (S.numL > 0) {
+			nScaleL = (S.numL + RED_BLOCK - 1) / RED_BLOCK;
+			k_solve_landmarks_only<T><<<nScaleL, RED_BLOCK, 0, stream>>>(invHll, bl, S.numL, lam, Xw[cur], Xw[cur ^ 1], xl, scalePartialL);
+			launches++;
+			CUDA_TRY(cudaGetLastError());
+		}
+		nScaleLandmark = nScaleL;
+		solvedLambda = lambda;
+		if (iters || ok) {
+			rc = fetchScalars(); if (rc) return rc;
+			const bool usedPcg = S.numP > 0 && S.numL > 0;
+			if (iters) *iters = usedPcg ? hScal->pcg.iters : 0;
+			if (ok) *ok = usedPcg ? (hScal->pcg.status == 0) : 1;
+		}
+		return CUBA_OK;
+	}
+	int nScaleLandmark = 0;
+	double solvedLambda = 0;
+
+	// pose update + trial chi2 + scale; results in dScal->v[1] (chi2), v[2..3] (scale parts)
+	int stage_update(double lambda, double* chi, double* scale) override
+	{
+		if (!haveProblem) return fail(CUBA_ERR_STATE, "update before set_problem");
+		const T lam = (T)lambda;
+		{
+			ProfScope ps(this, CUBA_PROF_UPDATE);
+			if (S.numP > 0) {
+				k_update_poses<T><<<nPoseBlocks, RED_BLOCK, 0, stream>>>(xp, bp, S.numP, lam, pose[cur], pose[cur ^ 1], scalePartialP);
+				launches++;
+				CUDA_TRY(cudaGetLastError());
+			}
+		}
+		int rc = launch_chi2(cur ^ 1, 1); if (rc) return rc;
+		// scale = sum over [xp;xl] of x (lambda x + b): pose part is replicated, landmark part is sharded
+		rc = launch_sum(scalePartialL, nScaleLandmark, scalePartialP, S.numP > 0 ? nPoseBlocks : 0, nullptr, 0, 2); if (rc) return rc;
+		if (world > 1) { rc = allreduce(&dScal.p->v[2], 1, false); if (rc) return rc; }
+		rc = fetchScalars(); if (rc) return rc;
+		trialValid = true;
+		if (chi) *chi = hScal->v[1];
+		if (scale) *scale = hScal->v[2] + hScal->v[3];
+		return CUBA_OK;
+	}
+
+	int stage_commit(int accept) override
+	{
+		if (!trialValid) return fail(CUBA_ERR_STATE, "commit without a trial state");
+		if (accept) cur ^= 1;
+		trialValid = false;
+		return CUBA_OK;
+	}
+
+	// ---- the LM loop: reference src/cuda_bundle_adjustment.cpp:793-857 ---------------------------------
+	int optimize(int niter, cuba_iter_stat* stats, int* nstats) override
+	{
+		if (!haveProblem) return fail(CUBA_ERR_STATE, "optimize before set_problem");
+		const int maxq = 10;
+		const double tau = 1e-5;
+		double nu = 2, lambda = 0, F = 0;
+		int n = 0;
+		bool haveF = false;
+		for (int it = 0; it < niter; it++) {
+			double chi0 = 0;
+			int rc = stage_linearize(&chi0); if (rc) return rc;
+			// after an accepted trial the reference recomputes the same residuals (cpp:808); the value is F
+			if (!haveF) F = chi0;
+			F = chi0; haveF = true;
+			if (it == 0) {
+				double md = 0;
+				rc = stage_max_diagonal(&md); if (rc) return rc;
+				lambda = tau * md;
+			}
+			int q = 0, trials = 0, pcgIters = 0, pcgFailed = 0;
+			double rho = -1;
+			for (; q < maxq && rho < 0; q++) {
+				trials++;
+				int iters = 0, ok = 1;
+				rc = stage_solve(lambda, nullptr, nullptr); if (rc) return rc;
+				double Fhat = 0, scale = 0;
+				rc = stage_update(lambda, &Fhat, &scale); if (rc) return rc;
+				if (S.numP > 0 && S.numL > 0) { iters = hScal->pcg.iters; ok = hScal->pcg.status == 0; }
+				pcgIters += iters; if (!ok) pcgFailed++;
+				scale += 1e-3;
+				rho = ok ? (F - Fhat) / scale : -1;
+				if (!(rho == rho)) rho = -1;   // NaN trial -> reject
+				if (rho > 0) {
+					const double a = 2 * rho - 1;
+					lambda *= std::max(1. / 3, std::min(1 - a * a * a, 2. / 3));
+					nu = 2; F = Fhat;
+					rc = stage_commit(1); if (rc) return rc;
+					break;
+				} else {
+					lambda *= nu; nu *= 2;
+					rc = stage_commit(0); if (rc) return rc;
+				}
+			}
+			if (stats) {
+				stats[n].iteration = it; stats[n].trials = trials; stats[n].chi2 = F; stats[n].lambda = lambda;
+				stats[n].pcg_iters = pcgIters; stats[n].pcg_failed = pcgFailed;
+			}
+			n++;
+			if (q == maxq || rho <= 0 || !std::isfinite(lambda)) break;
+		}
+		if (nstats) *nstats = n;
+		return CUBA_OK;
+	}
+
+	int get_state(double* q, double* t, double* X) override
+	{
+		if (!haveProblem) return fail(CUBA_ERR_STATE, "get_state before set_problem");
+		std::vector<T> hp((size_t)S.Pall * 8), hx((size_t)S.Lall * 4);
+		CUDA_TRY(cudaMemcpyAsync(hp.data(), pose[cur].p, sizeof(T) * hp.size(), cudaMemcpyDeviceToHost, stream));
+		if (world > 1 && S.numL > 0) {
+			// gather the sharded landmarks: zero foreign entries, sum over ranks
+			DBuf<T> tmp;
+			CUDA_TRY(tmp.alloc((size_t)S.Lall * 4));
+			CUDA_TRY(cudaMemsetAsync(tmp.p, 0, sizeof(T) * 4 * (size_t)S.Lall, stream));
+			if (S.lmEnd > S.lmBeg)
+				CUDA_TRY(cudaMemcpyAsync(tmp.p + 4 * (size_t)S.lmBeg, Xw[cur].p + 4 * (size_t)S.lmBeg, sizeof(T) * 4 * (size_t)(S.lmEnd - S.lmBeg), cudaMemcpyDeviceToDevice, stream));
+			int rc = allreduce(tmp.p, 4 * (size_t)S.Lall, true); if (rc) return rc;
+			CUDA_TRY(cudaMemcpyAsync(hx.data(), tmp.p, sizeof(T) * hx.size(), cudaMemcpyDeviceToHost, stream));
+			CUDA_TRY(cudaStreamSynchronize(stream));
+		} else {
+			CUDA_TRY(cudaMemcpyAsync(hx.data(), Xw[cur].p, sizeof(T) * hx.size(), cudaMemcpyDeviceToHost, stream));
+			CUDA_TRY(cudaStreamSynchronize(stream));
+		}
+		for (int i = 0; i < S.Pall; i++) {
+			if (q) for (int k = 0; k < 4; k++) q[4 * (size_t)i + k] = (double)hp[8 * (size_t)i + k];
+			if (t) for (int k = 0; k < 3; k++) t[3 * (size_t)i + k] = (double)hp[8 * (size_t)i + 4 + k];
+		}
+		if (X) for (int i = 0; i < S.Lall; i++) for (int k = 0; k < 3; k++) X[3 * (size_t)i + k] = (double)hx[4 * (size_t)i + k];
+		return CUBA_OK;
+	}
+
+	int get_chi2(double* out) override
+	{
+		if (!haveProblem) return fail(CUBA_ERR_STATE, "get_chi2 before set_problem");
+		CUDA_TRY(cudaMemsetAsync(chiSq.p, 0, sizeof(double) * (size_t)std::max(S.E, 1), stream));
+		if (S.eLocal > 0) {
+			k_chi_sqs<T><<<(S.eLocal + 255) / 256, 256, 0, stream>>>(chiArgs(cur), e_user, chiSq);
+			launches++;
+			CUDA_TRY(cudaGetLastError());
+		}
+		if (world > 1) { int rc = allreduce(chiSq.p, (size_t)S.E, false); if (rc) return rc; }
+		CUDA_TRY(cudaMemcpyAsync(out, chiSq.p, sizeof(double) * (size_t)S.E, cudaMemcpyDeviceToHost, stream));
+		CUDA_TRY(cudaStreamSynchronize(stream));
+		return CUBA_OK;
+	}
+
+	int get_profile(double* sec) override
+	{
+		resolveProfile();
+		for (int i = 0; i < CUBA_PROF_NUM; i++) sec[i] = prof[i];
+		return CUBA_OK;
+	}
+
+	// ---- debug getters ---------------------------------------------------------------------------------
+	int dbg_hpl_structure(int32_t* colPtr, int32_t* rowInd, int32_t* e2h) override
+	{
+		if (!haveProblem) return fail(CUBA_ERR_STATE, "no problem");
+		if (colPtr) memcpy(colPtr, S.hplColPtr.data(), sizeof(int) * S.hplColPtr.size());
+		if (rowInd) memcpy(rowInd, S.hplRowInd.data(), sizeof(int) * S.hplRowInd.size());
+		if (e2h) memcpy(e2h, S.edge2Hpl.data(), sizeof(int) * S.edge2Hpl.size());
+		return CUBA_OK;
+	}
+	int dbg_hsc_structure(int32_t* rowPtr, int32_t* colInd) override
+	{
+		if (!haveProblem) return fail(CUBA_ERR_STATE, "no problem");
+		if (rowPtr) memcpy(rowPtr, S.hscRowPtr.data(), sizeof(int) * S.hscRowPtr.size());
+		if (colInd) memcpy(colInd, S.hscColInd.data(), sizeof(int) * S.hscColInd.size());
+		return CUBA_OK;
+	}
+	int download(const T* d, size_t n, double* out)
+	{
+		std::vector<T> h(n);
+		CUDA_TRY(cudaMemcpyAsync(h.data(), d, sizeof(T) * n, cudaMemcpyDeviceToHost, stream));
+		CUDA_TRY(cudaStreamSynchronize(stream));
+		for (size_t i = 0; i < n; i++) out[i] = (double)h[i];
+		return CUBA_OK;
+	}
+	int dbg_system(double* oHpp, double* obp, double* oHll, double* obl, double* oHpl) override
+	{
+		if (!haveProblem) return fail(CUBA_ERR_STATE, "no problem");
+		int rc;
+		if (oHpp && (rc = download(Hpp, 36 * (size_t)S.numP, oHpp))) return rc;
+		if (obp && (rc = download(bp, 6 * (size_t)S.numP, obp))) return rc;
+		if (oHll && (rc = download(Hll, 9 * (size_t)S.numL, oHll))) return rc;
+		if (obl && (rc = download(bl, 3 * (size_t)S.numL, obl))) return rc;
+		if (oHpl) {
+			// local blocks land at their global positions; foreign blocks read as zero
+			memset(oHpl, 0, sizeof(double) * 18 * (size_t)S.nhpl);
+			if ((rc = download(Hpl, 18 * (size_t)S.nhplLocal, oHpl + 18 * (size_t)S.hplBase))) return rc;
+		}
+		return CUBA_OK;
+	}
+	int dbg_schur(double* oHsc, double* obsc, double* oinv) override
+	{
+		if (!haveProblem) return fail(CUBA_ERR_STATE, "no problem");
+		int rc;
+		if (oHsc) {
+			std::vector<double> full(36 * (size_t)S.nfull);
+			if ((rc = download(fVal, full.size(), full.data()))) return rc;
+			for (int k = 0; k < S.nblk; k++) memcpy(oHsc + 36 * (size_t)k, full.data() + 36 * (size_t)S.u2f[k], sizeof(double) * 36);
+		}
+		if (obsc && (rc = download(bsc, 6 * (size_t)S.numP, obsc))) return rc;
+		if (oinv && (rc = download(invHll, 9 * (size_t)S.numL, oinv))) return rc;
+		return CUBA_OK;
+	}
+	int dbg_delta(double* oxp, double* oxl) override
+	{
+		if (!haveProblem) return fail(CUBA_ERR_STATE, "no problem");
+		int rc;
+		if (oxp && (rc = download(xp, 6 * (size_t)S.numP, oxp))) return rc;
+		if (oxl && (rc = download(xl, 3 * (size_t)S.numL, oxl))) return rc;
+		return CUBA_OK;
+	}
+
+	// ---- micro-benchmarks --------------------------------------------------------------------------------
+	int bench_stage(int stage, int reps, int flush, double lambda, double* ms) override
+	{
+		if (!haveProblem) return fail(CUBA_ERR_STATE, "bench before set_problem");
+		if (reps < 1) reps = 1;
+		const size_t flushN = (size_t)40 << 20;   // 320 MB of doubles > 126 MB L2
+		if (flush) CUDA_TRY(flushBuf.alloc(flushN));
+		cudaEvent_t a, b;
+		CUDA_TRY(cudaEventCreate(&a)); CUDA_TRY(cudaEventCreate(&b));
+		double total = 0;
+		const T lam = (T)lambda;
+		for (int r = 0; r < reps; r++) {
+			if (flush) { k_fill<<<numSMs * 8, 256, 0, stream>>>(flushBuf.p, flushN, (double)r); launches++; }
+			CUDA_TRY(cudaEventRecord(a, stream));
+			int rc = CUBA_OK;
+			switch (stage) {
+			case 0: rc = launch_linearize_landmark(); if (!rc) rc = launch_linearize_pose(); break;
+			case 1: rc = launch_linearize_landmark(); break;
+			case 2: rc = launch_linearize_pose(); break;
+			case 3: rc = launch_schur(lam); break;
+			case 4: rc = launch_pcg(); break;
+			case 5: rc = launch_backsub(lam); if (!rc) rc = stage_update_nofetch(lam); break;
+			case 6: rc = launch_chi2(cur, 0); break;
+			default: rc = fail(CUBA_ERR_INVALID, "bench_stage: unknown stage");
+			}
+			if (rc) return rc;
+			CUDA_TRY(cudaEventRecord(b, stream));
+			CUDA_TRY(cudaEventSynchronize(b));
+			float t = 0;
+			CUDA_TRY(cudaEventElapsedTime(&t, a, b));
+			total += t;
+		}
+		cudaEventDestroy(a); cudaEventDestroy(b);
+		resolveProfile();
+		if (ms) *ms = total / reps;
+		return CUBA_OK;
+	}
+	int stage_update_nofetch(T lam)
+	{
+		if (S.numP > 0) {
+			k_update_poses<T><<<nPoseBlocks, RED_BLOCK, 0, stream>>>(xp, bp, S.numP, lam, pose[cur], pose[cur ^ 1], scalePartialP);
+			launches++;
+			CUDA_TRY(cudaGetLastError());
+		}
+		return launch_chi2(cur ^ 1, 1);
+	}
+};
+
+}  // namespace cuba_b200
+
+// ======================================================================================================
+// C ABI
+// ======================================================================================================
+using namespace cuba_b200;
+
+struct cuba_engine { std::unique_ptr<EngineBase> impl; };
+
+extern "C" {
+
+const char* cuba_last_error(void) { return g_err.c_str(); }
+int cuba_version(void) { return 100; }
+
+int cuba_engine_create(const cuba_config* cfg, cuba_engine** out)
+{
+	if (!out) return fail(CUBA_ERR_INVALID, "create: null out");
+	cuba_config c;
+	memset(&c, 0, sizeof(c));
+	c.device = -1; c.deterministic = 1;
+	if (cfg) c = *cfg;
+	std::unique_ptr<EngineBase> impl;
+	int rc;
+	if (c.use_fp32) { auto* e = new Engine<float>(); e->cfg = c; impl.reset(e); rc = e->init(); }
+	else { auto* e = new Engine<double>(); e->cfg = c; impl.reset(e); rc = e->init(); }
+	if (rc) return rc;
+	*out = new cuba_engine{ std::move(impl) };
+	return CUBA_OK;
+}
+
+int cuba_engine_destroy(cuba_engine* e) { delete e; return CUBA_OK; }
+
+#define ENGINE_OR_FAIL(e) if (!(e) || !(e)->impl) return fail(CUBA_ERR_INVALID, "null engine")
+
+int cuba_engine_set_robust_kernel(cuba_engine* e, int edge_type, int kernel_type, double delta)
+{
+	ENGINE_OR_FAIL(e);
+	if (edge_type < 0 || edge_type > 1 || kernel_type < 0 || kernel_type > 2) return fail(CUBA_ERR_INVALID, "set_robust_kernel: bad type");
+	e->impl->rk_type[edge_type] = kernel_type; e->impl->rk_delta[edge_type] = delta;
+	return CUBA_OK;
+}
+
+int cuba_comm_unique_id(void* out128)
+{
+	std::string why;
+	if (!g_nccl.load(why)) return fail(CUBA_ERR_COMM, why);
+	Nccl::UniqueId id;
+	const int rc = g_nccl.GetUniqueId(&id);
+	if (rc) return fail(CUBA_ERR_COMM, "ncclGetUniqueId failed");
+	memcpy(out128, &id, 128);
+	return CUBA_OK;
+}
+
+int cuba_engine_set_comm(cuba_engine* e, int rank, int world, const void* uid)
+{
+	ENGINE_OR_FAIL(e);
+	if (world < 1 || rank < 0 || rank >= world) return fail(CUBA_ERR_INVALID, "set_comm: bad rank/world");
+	if (e->impl->haveProblem) return fail(CUBA_ERR_STATE, "set_comm must precede set_problem");
+	e->impl->rank = rank; e->impl->world = world;
+	if (world == 1) return CUBA_OK;
+	if (!uid) return fail(CUBA_ERR_INVALID, "set_comm: null unique id");
+	std::string why;
+	if (!g_nccl.load(why)) return fail(CUBA_ERR_COMM, why);
+	Nccl::UniqueId id;
+	memcpy(&id, uid, 128);
+	const int rc = g_nccl.CommInitRank(&e->impl->comm, world, id, rank);
+	if (rc) return fail(CUBA_ERR_COMM, std::string("ncclCommInitRank failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+	return CUBA_OK;
+}
+
+int cuba_engine_set_problem(cuba_engine* e, const cuba_problem* p) { ENGINE_OR_FAIL(e); return e->impl->set_problem(p); }
+int cuba_engine_set_state(cuba_engine* e, const double* q, const double* t, const double* Xw)
+{
+	ENGINE_OR_FAIL(e);
+	if (!q || !t || !Xw) return fail(CUBA_ERR_INVALID, "set_state: null array");
+	return e->impl->set_state(q, t, Xw);
+}
+int cuba_engine_get_sizes(const cuba_engine* e, cuba_sizes* out) { ENGINE_OR_FAIL(e); if (!out) return fail(CUBA_ERR_INVALID, "null out"); return e->impl->get_sizes(out); }
+int cuba_engine_optimize(cuba_engine* e, int niter, cuba_iter_stat* stats, int* nstats) { ENGINE_OR_FAIL(e); return e->impl->optimize(niter, stats, nstats); }
+int cuba_engine_get_state(cuba_engine* e, double* q, double* t, double* Xw) { ENGINE_OR_FAIL(e); return e->impl->get_state(q, t, Xw); }
+int cuba_engine_get_chi2(cuba_engine* e, double* per_edge) { ENGINE_OR_FAIL(e); if (!per_edge) return fail(CUBA_ERR_INVALID, "null out"); return e->impl->get_chi2(per_edge); }
+int cuba_engine_get_profile(cuba_engine* e, double* sec) { ENGINE_OR_FAIL(e); if (!sec) return fail(CUBA_ERR_INVALID, "null out"); return e->impl->get_profile(sec); }
+int cuba_engine_get_launch_count(cuba_engine* e, long long* count) { ENGINE_OR_FAIL(e); if (count) *count = e->impl->launches; return CUBA_OK; }
+
+int cuba_stage_linearize(cuba_engine* e, double* chi2) { ENGINE_OR_FAIL(e); return e->impl->stage_linearize(chi2); }
+int cuba_stage_max_diagonal(cuba_engine* e, double* md) { ENGINE_OR_FAIL(e); return e->impl->stage_max_diagonal(md); }
+int cuba_stage_solve(cuba_engine* e, double lambda, int* iters, int* ok)
+{
+	ENGINE_OR_FAIL(e);
+	int it = 0, k = 1;
+	const int rc = e->impl->stage_solve(lambda, &it, &k);
+	if (iters) *iters = it;
+	if (ok) *ok = k;
+	return rc;
+}
+int cuba_stage_update(cuba_engine* e, double lambda, double* chi, double* scale) { ENGINE_OR_FAIL(e); return e->impl->stage_update(lambda, chi, scale); }
+int cuba_stage_commit(cuba_engine* e, int accept) { ENGINE_OR_FAIL(e); return e->impl->stage_commit(accept); }
+int cuba_stage_chi2(cuba_engine* e, double* chi) { ENGINE_OR_FAIL(e); return e->impl->stage_chi2(chi); }
+
+int cuba_debug_get_hpl_structure(cuba_engine* e, int32_t* colPtr, int32_t* rowInd, int32_t* e2h) { ENGINE_OR_FAIL(e); return e->impl->dbg_hpl_structure(colPtr, rowInd, e2h); }
+int cuba_debug_get_hsc_structure(cuba_engine* e, int32_t* rowPtr, int32_t* colInd) { ENGINE_OR_FAIL(e); return e->impl->dbg_hsc_structure(rowPtr, colInd); }
+int cuba_debug_get_system(cuba_engine* e, double* Hpp, double* bp, double* Hll, double* bl, double* Hpl) { ENGINE_OR_FAIL(e); return e->impl->dbg_system(Hpp, bp, Hll, bl, Hpl); }
+int cuba_debug_get_schur(cuba_engine* e, double* Hsc, double* bsc, double* invHll) { ENGINE_OR_FAIL(e); return e->impl->dbg_schur(Hsc, bsc, invHll); }
+int cuba_debug_get_delta(cuba_engine* e, double* xp, double* xl) { ENGINE_OR_FAIL(e); return e->impl->dbg_delta(xp, xl); }
+int cuba_debug_build_structure_host(const cuba_problem* p, int rank, int world, cuba_sizes* sizes,
+	int32_t* hplColPtr, int32_t* hplRowInd, int32_t* edge2Hpl, int32_t* hscRowPtr, int32_t* hscColInd,
+	int32_t* fullRowPtr, int32_t* fullColInd, int32_t* shard)
+{
+	if (!p) return fail(CUBA_ERR_INVALID, "null problem");
+	Structure S;
+	const char* err = "";
+	if (!build_structure(p->Pall, p->numP, p->Lall, p->numL, p->E2, p->idx2, p->E3, p->idx3, rank, world, TILE, S, &err))
+		return fail(CUBA_ERR_INVALID, err);
+	if (sizes) {
+		sizes->Pall = S.Pall; sizes->numP = S.numP; sizes->Lall = S.Lall; sizes->numL = S.numL; sizes->E2 = S.E2; sizes->E3 = S.E3;
+		sizes->nhpl = S.nhpl; sizes->nblk = S.nblk; sizes->nmul = (int32_t)S.nmul; sizes->nblk_full = S.nfull;
+	}
+	auto cp = [](int32_t* dst, const std::vector<int>& v) { if (dst && !v.empty()) memcpy(dst, v.data(), sizeof(int) * v.size()); };
+	cp(hplColPtr, S.hplColPtr); cp(hplRowInd, S.hplRowInd); cp(edge2Hpl, S.edge2Hpl);
+	cp(hscRowPtr, S.hscRowPtr); cp(hscColInd, S.hscColInd); cp(fullRowPtr, S.fRowPtr); cp(fullColInd, S.fColInd);
+	if (shard) { shard[0] = S.lmBeg; shard[1] = S.lmEnd; shard[2] = S.eLocal; shard[3] = (int32_t)S.nmulLocal; }
+	// internal consistency (cheap): tiles cover the shard, products reference blocks of one landmark with row(i)<=row(j)
+	if ((int)S.tileLm.size() < 1 || S.tileLm.front() != S.lmBeg || S.tileLm.back() != S.lmEnd) return fail(CUBA_ERR_INVALID, "structure self-check: tiles");
+	for (size_t t = 0; t + 1 < S.tileLm.size(); t++) {
+		const int nl = S.tileLm[t + 1] - S.tileLm[t];
+		const int ne = S.lmPtr[S.tileLm[t + 1]] - S.lmPtr[S.tileLm[t]];
+		if (nl < 1 || nl > TILE || (ne > TILE && nl != 1)) return fail(CUBA_ERR_INVALID, "structure self-check: tile size");
+	}
+	for (int k = 0; k < S.nblk; k++)
+		for (int n = S.prodPtr[k]; n < S.prodPtr[k + 1]; n++) {
+			const int i = S.prodI[n] + S.hplBase, j = S.prodJ[n] + S.hplBase;
+			if (S.hplRowInd[i] != S.blkRow[k] || S.hplRowInd[j] != S.blkCol[k] || S.hplLm[S.prodI[n]] != S.hplLm[S.prodJ[n]] || i > j)
+				return fail(CUBA_ERR_INVALID, "structure self-check: product list");
+		}
+	return CUBA_OK;
+}
+
+int cuba_bench_stage(cuba_engine* e, int stage, int reps, int flush, double lambda, double* ms) { ENGINE_OR_FAIL(e); return e->impl->bench_stage(stage, reps, flush, lambda, ms); }
+
+}  // extern "C"

@@ -1,0 +1,772 @@
+// cuba_kernels.cuh -- sm_100a kernels of the LM inner loop (templated on the scalar type).
+//
+// Data layout in HBM:
+//   pose  [Pall][8]  q(x,y,z,w) t(x,y,z) pad      cam [Pall][8] fx fy cx cy bf pad pad pad
+//   Xw    [Lall][4]  X Y Z pad
+//   landmark-major edge stream (sorted by (iL,iP)), SoA: mx,my,mz,om (T), ip (bit31 = stereo), il, hpl
+//   pose-major edge stream (sorted by (iP,iL), free poses only), SoA: mx,my,mz,om (T), il (bit31 = stereo)
+//   Hpp [numP][36] bp [numP][6] Hll [numL][9] bl [numL][3] Hpl [nhpl][18]   (blocks column-major)
+//   Hsc: symmetric-full BSR (fRowPtr,fColInd,fVal[nfull][36]) for the PCG; upper view for parity.
+#pragma once
+
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cuba_math.cuh"
+
+namespace cuba_b200 {
+
+namespace cg = cooperative_groups;
+
+constexpr int TILE = 256;        // edges per landmark tile == threads per CTA of the landmark kernels
+constexpr int POSE_BLOCK = 128;  // threads per CTA of the pose pass
+constexpr int SCHUR_BLOCK = 128; // 4 warps, one destination block per warp
+constexpr int PCG_BLOCK = 256;
+constexpr int RED_BLOCK = 256;
+
+template <typename T> struct V2;
+template <> struct V2<double> { using type = double2; };
+template <> struct V2<float> { using type = float2; };
+
+template <typename T>
+__device__ __forceinline__ void ld2(const T* __restrict__ p, T& a, T& b)
+{
+	const typename V2<T>::type v = __ldg(reinterpret_cast<const typename V2<T>::type*>(p));
+	a = v.x; b = v.y;
+}
+template <typename T>
+__device__ __forceinline__ void st2(T* p, T a, T b)
+{
+	typename V2<T>::type v; v.x = a; v.y = b;
+	*reinterpret_cast<typename V2<T>::type*>(p) = v;
+}
+
+template <typename T>
+__device__ __forceinline__ void load_pose(const T* __restrict__ pose, const T* __restrict__ cam, int ip, T q[4], T t[3], T c[5])
+{
+	const T* p = pose + 8 * (size_t)ip;
+	T pad;
+	ld2(p, q[0], q[1]); ld2(p + 2, q[2], q[3]); ld2(p + 4, t[0], t[1]); ld2(p + 6, t[2], pad);
+	const T* k = cam + 8 * (size_t)ip;
+	ld2(k, c[0], c[1]); ld2(k + 2, c[2], c[3]); ld2(k + 4, c[4], pad);
+}
+
+template <typename T>
+__device__ __forceinline__ void load_xw(const T* __restrict__ Xw, int il, T X[3])
+{
+	T pad;
+	ld2(Xw + 4 * (size_t)il, X[0], X[1]); ld2(Xw + 4 * (size_t)il + 2, X[2], pad);
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+// deterministic block sum (fixed tree); result valid in thread 0. s_red must hold blockDim/32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* s_red)
+{
+	v = warp_sum(v);
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	if (lane == 0) s_red[wid] = v;
+	__syncthreads();
+	double r = 0;
+	if (threadIdx.x == 0) for (int i = 0; i < (int)(blockDim.x >> 5); i++) r += s_red[i];
+	__syncthreads();
+	return r;
+}
+
+struct RobustParams { int type[2]; double delta[2]; };
+
+// ------------------------------------------------------------------------------------------------
+// Landmark pass of the Jacobian+Hessian stage: one CTA per tile of whole landmarks (<= TILE edges,
+// or one giant landmark).  Thread per edge: residual, robust weight, JP/JL, Hpl block (global store),
+// Hll/bl contributions staged in shared memory and summed per landmark run -- no atomics.
+// Also emits the robustified chi2 partial of the tile.
+// Replaces computeActiveErrorsKernel + constructQuadraticFormKernel (reference cu:732-839) for the
+// landmark-side outputs.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct LinLmArgs {
+	const T* pose; const T* cam; const T* Xw;
+	const T* mx; const T* my; const T* mz; const T* om;
+	const int* ip; const int* il; const int* hpl;
+	const int* lmPtr; const int* tileLm;
+	int numP, numL;
+	T* Hpl; T* Hll; T* bl;
+	double* chiPartial;
+	RobustParams rk;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(TILE) k_linearize_landmark(const LinLmArgs<T> a)
+{
+	__shared__ T s_val[9][TILE + 1];
+	__shared__ T s_acc[TILE * 9];
+	__shared__ int s_ptr[TILE + 1];
+	__shared__ double s_red[TILE / 32];
+
+	const int tid = threadIdx.x;
+	const int l0 = a.tileLm[blockIdx.x], l1 = a.tileLm[blockIdx.x + 1];
+	const int nl = l1 - l0;
+	for (int i = tid; i <= nl; i += TILE) s_ptr[i] = a.lmPtr[l0 + i];
+	for (int i = tid; i < nl * 9; i += TILE) s_acc[i] = T(0);
+	__syncthreads();
+	const int e0 = s_ptr[0], e1 = s_ptr[nl];
+
+	double chi = 0;
+	for (int cs = e0; cs < e1; cs += TILE) {
+		const int e = cs + tid;
+		T v[9];
+#pragma unroll
+		for (int i = 0; i < 9; i++) v[i] = T(0);
+		if (e < e1) {
+			const int ipf = a.ip[e];
+			const bool stereo = ipf < 0;
+			const int ip = ipf & 0x7fffffff;
+			const int il = a.il[e];
+			T q[4], t[3], c[5], X[3], m[3], Xc[3], r[3];
+			load_pose(a.pose, a.cam, ip, q, t, c);
+			load_xw(a.Xw, il, X);
+			m[0] = a.mx[e]; m[1] = a.my[e]; m[2] = stereo ? a.mz[e] : T(0);
+			const T om = a.om[e];
+			edge_residual(q, t, c, X, m, stereo, Xc, r);
+			const T e2 = om * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+			T rho, drho;
+			robust<T>(a.rk.type[stereo ? 1 : 0], (T)a.rk.delta[stereo ? 1 : 0], e2, rho, drho);
+			chi += (double)rho;
+			const T w = om * drho;
+			if (il < a.numL) {
+				T JP[3][6], JL[3][3];
+				edge_jacobians(q, c, Xc, stereo, JP, JL);
+				T wJL[3][3], wr[3];
+#pragma unroll
+				for (int mm = 0; mm < 3; mm++) {
+					wr[mm] = w * r[mm];
+#pragma unroll
+					for (int n = 0; n < 3; n++) wJL[mm][n] = w * JL[mm][n];
+				}
+				// unique Hll entries 00,01,02,11,12,22 then bl
+				v[0] = JL[0][0] * wJL[0][0] + JL[1][0] * wJL[1][0] + JL[2][0] * wJL[2][0];
+				v[1] = JL[0][0] * wJL[0][1] + JL[1][0] * wJL[1][1] + JL[2][0] * wJL[2][1];
+				v[2] = JL[0][0] * wJL[0][2] + JL[1][0] * wJL[1][2] + JL[2][0] * wJL[2][2];
+				v[3] = JL[0][1] * wJL[0][1] + JL[1][1] * wJL[1][1] + JL[2][1] * wJL[2][1];
+				v[4] = JL[0][1] * wJL[0][2] + JL[1][1] * wJL[1][2] + JL[2][1] * wJL[2][2];
+				v[5] = JL[0][2] * wJL[0][2] + JL[1][2] * wJL[1][2] + JL[2][2] * wJL[2][2];
+				v[6] = JL[0][0] * wr[0] + JL[1][0] * wr[1] + JL[2][0] * wr[2];
+				v[7] = JL[0][1] * wr[0] + JL[1][1] * wr[1] + JL[2][1] * wr[2];
+				v[8] = JL[0][2] * wr[0] + JL[1][2] * wr[1] + JL[2][2] * wr[2];
+				const int hp = a.hpl[e];
+				if (hp >= 0) {
+					T* dst = a.Hpl + 18 * (size_t)hp;
+#pragma unroll
+					for (int n = 0; n < 3; n++) {
+#pragma unroll
+						for (int l = 0; l < 6; l += 2) {
+							const T h0 = JP[0][l] * wJL[0][n] + JP[1][l] * wJL[1][n] + JP[2][l] * wJL[2][n];
+							const T h1 = JP[0][l + 1] * wJL[0][n] + JP[1][l + 1] * wJL[1][n] + JP[2][l + 1] * wJL[2][n];
+							st2(dst + n * 6 + l, h0, h1);
+						}
+					}
+				}
+			}
+		}
+#pragma unroll
+		for (int i = 0; i < 9; i++) s_val[i][tid] = v[i];
+		__syncthreads();
+		for (int wi = tid; wi < nl * 9; wi += TILE) {
+			const int j = wi / 9, cc = wi - 9 * j;
+			int s = s_ptr[j], t = s_ptr[j + 1];
+			s = (s > cs ? s : cs) - cs;
+			t = (t < cs + TILE ? t : cs + TILE) - cs;
+			if (t > s) {
+				T sum = T(0);
+				for (int k = s; k < t; k++) sum += s_val[cc][k];
+				s_acc[wi] += sum;
+			}
+		}
+		__syncthreads();
+	}
+	// write Hll (full symmetric 3x3, column-major) and bl of the tile's free landmarks, coalesced
+	{
+		const int map9[9] = { 0, 1, 2, 1, 3, 4, 2, 4, 5 };
+		for (int wi = tid; wi < nl * 9; wi += TILE) {
+			const int j = wi / 9, cc = wi - 9 * j;
+			if (l0 + j < a.numL) a.Hll[9 * (size_t)l0 + wi] = s_acc[j * 9 + map9[cc]];
+		}
+		for (int wi = tid; wi < nl * 3; wi += TILE) {
+			const int j = wi / 3, cc = wi - 3 * j;
+			if (l0 + j < a.numL) a.bl[3 * (size_t)l0 + wi] = s_acc[j * 9 + 6 + cc];
+		}
+	}
+	const double tot = block_sum(chi, s_red);
+	if (tid == 0) a.chiPartial[blockIdx.x] = tot;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pose pass of the Jacobian+Hessian stage: one CTA per free pose over its pose-major edge list.
+// Each thread accumulates the 21 upper entries of JP^T w JP and the 6 of JP^T w r in registers;
+// one fixed-order block reduction per pose -- no atomics.  (reference cu:815-824)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct LinPoseArgs {
+	const T* pose; const T* cam; const T* Xw;
+	const T* mx; const T* my; const T* mz; const T* om; const int* il;
+	const int* posePtr;
+	T* Hpp; T* bp;
+	RobustParams rk;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(POSE_BLOCK) k_linearize_pose(const LinPoseArgs<T> a)
+{
+	__shared__ T s_part[POSE_BLOCK / 32][27];
+	__shared__ T s_fin[27];
+	const int p = blockIdx.x, tid = threadIdx.x;
+	const int e0 = a.posePtr[p], e1 = a.posePtr[p + 1];
+	T q[4], t[3], c[5];
+	load_pose(a.pose, a.cam, p, q, t, c);
+	T acc[27];
+#pragma unroll
+	for (int i = 0; i < 27; i++) acc[i] = T(0);
+	for (int e = e0 + tid; e < e1; e += POSE_BLOCK) {
+		const int ilf = a.il[e];
+		const bool stereo = ilf < 0;
+		const int il = ilf & 0x7fffffff;
+		T X[3], m[3], Xc[3], r[3];
+		load_xw(a.Xw, il, X);
+		m[0] = a.mx[e]; m[1] = a.my[e]; m[2] = stereo ? a.mz[e] : T(0);
+		const T om = a.om[e];
+		edge_residual(q, t, c, X, m, stereo, Xc, r);
+		const T e2 = om * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+		T rho, drho;
+		robust<T>(a.rk.type[stereo ? 1 : 0], (T)a.rk.delta[stereo ? 1 : 0], e2, rho, drho);
+		const T w = om * drho;
+		T JP[3][6], JL[3][3];
+		edge_jacobians(q, c, Xc, stereo, JP, JL);
+		T wJP[3][6];
+#pragma unroll
+		for (int mm = 0; mm < 3; mm++)
+#pragma unroll
+			for (int l = 0; l < 6; l++) wJP[mm][l] = w * JP[mm][l];
+		int k = 0;
+#pragma unroll
+		for (int n = 0; n < 6; n++)
+#pragma unroll
+			for (int l = 0; l <= n; l++) {
+				acc[k] += JP[0][l] * wJP[0][n] + JP[1][l] * wJP[1][n] + JP[2][l] * wJP[2][n];
+				k++;
+			}
+#pragma unroll
+		for (int l = 0; l < 6; l++) acc[21 + l] += wJP[0][l] * r[0] + wJP[1][l] * r[1] + wJP[2][l] * r[2];
+	}
+	const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+	for (int i = 0; i < 27; i++) {
+		const T s = warp_sum(acc[i]);
+		if (lane == 0) s_part[wid][i] = s;
+	}
+	__syncthreads();
+	if (tid < 27) {
+		T s = T(0);
+#pragma unroll
+		for (int w = 0; w < POSE_BLOCK / 32; w++) s += s_part[w][tid];
+		s_fin[tid] = s;
+	}
+	__syncthreads();
+	if (tid < 36) {
+		const int n = tid / 6, l = tid - 6 * n;   // column n, row l
+		const int lo = l < n ? l : n, hi = l < n ? n : l;
+		a.Hpp[36 * (size_t)p + tid] = s_fin[hi * (hi + 1) / 2 + lo];
+	} else if (tid < 42) {
+		a.bp[6 * (size_t)p + (tid - 36)] = s_fin[21 + (tid - 36)];
+	}
+}
+
+// max over the diagonals of Hpp and Hll, starting from 0 (reference cu:877-904).
+template <typename T>
+__global__ void k_max_diagonal(const T* Hpp, int numP, const T* Hll, int numL, unsigned long long* out)
+{
+	double m = 0;
+	const int n1 = numP * 6, n2 = numL * 3;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += gridDim.x * blockDim.x) {
+		double v;
+		if (i < n1) { const int j = i / 6, k = i - 6 * j; v = (double)Hpp[36 * (size_t)j + 7 * k]; }
+		else { const int ii = i - n1; const int j = ii / 3, k = ii - 3 * j; v = (double)Hll[9 * (size_t)j + 4 * k]; }
+		m = v > m ? v : m;
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) { const double x = __shfl_xor_sync(0xffffffffu, m, o); m = x > m ? x : m; }
+	if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
+// invHll = (Hll + lambda I)^-1, closed form (reference cu:417-452, 941-942)
+template <typename T>
+__global__ void k_inv_hll(const T* __restrict__ Hll, int numL, T lambda, T* __restrict__ invHll)
+{
+	const int l = blockIdx.x * blockDim.x + threadIdx.x;
+	if (l >= numL) return;
+	const T* H = Hll + 9 * (size_t)l;
+	T B[6];
+	sym3_inverse<T>(H[0] + lambda, H[3], H[6], H[4] + lambda, H[7], H[8] + lambda, B);
+	T* o = invHll + 9 * (size_t)l;
+	o[0] = B[0]; o[1] = B[1]; o[2] = B[2];
+	o[3] = B[1]; o[4] = B[3]; o[5] = B[4];
+	o[6] = B[2]; o[7] = B[4]; o[8] = B[5];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Schur complement: one warp per upper-triangular destination block k = (a,b), a<=b.  The product
+// list is sorted by destination at structure time, so every block is a fixed-order sum -- no fp64
+// atomics (the reference does 36 per product, cu:964-977).  W = Hpl_i * invHll is recomputed per
+// product instead of being stored (reference stores Hpl_invHll, cu:933-953).
+//   Hsc(a,b) = [a==b](Hpp_a + lambda I) - sum_products (Hpl_i invHll_l) Hpl_j^T
+//   bsc(a)   = bp_a - sum_{i in row a} (Hpl_i invHll_l) bl_l
+// Both the (a,b) block and its transpose (b,a) of the symmetric-full BSR are written.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct SchurArgs {
+	const T* Hpl; const T* invHll; const T* bl; const T* Hpp; const T* bp;
+	const int* prodPtr; const int* prodI; const int* prodJ; const int* hplLm;
+	const int* blkRow; const int* blkCol; const int* u2f; const int* u2fT;
+	int nblk;
+	T lambda;
+	int addDiag;   // 1: add Hpp+lambda*I and bp (single GPU, or rank 0 of a sharded run)
+	T* fVal; T* bsc;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(SCHUR_BLOCK) k_schur(const SchurArgs<T> a)
+{
+	__shared__ T s_red[SCHUR_BLOCK / 32][42][33];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const int k = blockIdx.x * (SCHUR_BLOCK / 32) + wid;
+	if (k >= a.nblk) return;
+	const int ra = a.blkRow[k], cb = a.blkCol[k];
+	const bool diag = ra == cb;
+	const int n0 = a.prodPtr[k], n1 = a.prodPtr[k + 1];
+	T C[36], v[6];
+#pragma unroll
+	for (int i = 0; i < 36; i++) C[i] = T(0);
+#pragma unroll
+	for (int i = 0; i < 6; i++) v[i] = T(0);
+	for (int n = n0 + lane; n < n1; n += 32) {
+		const int i = a.prodI[n], j = a.prodJ[n];
+		const int l = a.hplLm[i];
+		T Ai[18], Aj[18], inv[6];
+		const T* pi = a.Hpl + 18 * (size_t)i;
+		const T* pj = a.Hpl + 18 * (size_t)j;
+#pragma unroll
+		for (int x = 0; x < 18; x += 2) { ld2(pi + x, Ai[x], Ai[x + 1]); ld2(pj + x, Aj[x], Aj[x + 1]); }
+		const T* iv = a.invHll + 9 * (size_t)l;
+		inv[0] = iv[0]; inv[1] = iv[3]; inv[2] = iv[6]; inv[3] = iv[4]; inv[4] = iv[7]; inv[5] = iv[8];
+		T b3[3] = { T(0), T(0), T(0) };
+		if (diag) { b3[0] = a.bl[3 * (size_t)l]; b3[1] = a.bl[3 * (size_t)l + 1]; b3[2] = a.bl[3 * (size_t)l + 2]; }
+#pragma unroll
+		for (int r = 0; r < 6; r++) {
+			// row r of W = Ai * inv  (Ai(r,kk) = Ai[kk*6+r], inv symmetric)
+			const T w0 = Ai[r] * inv[0] + Ai[6 + r] * inv[1] + Ai[12 + r] * inv[2];
+			const T w1 = Ai[r] * inv[1] + Ai[6 + r] * inv[3] + Ai[12 + r] * inv[4];
+			const T w2 = Ai[r] * inv[2] + Ai[6 + r] * inv[4] + Ai[12 + r] * inv[5];
+#pragma unroll
+			for (int c = 0; c < 6; c++) C[c * 6 + r] += w0 * Aj[c] + w1 * Aj[6 + c] + w2 * Aj[12 + c];
+			v[r] += w0 * b3[0] + w1 * b3[1] + w2 * b3[2];
+		}
+	}
+	const int nact = (n1 - n0) < 32 ? (n1 - n0) : 32;
+	T(*red)[33] = s_red[wid];
+	if (lane < nact) {
+#pragma unroll
+		for (int i = 0; i < 36; i++) red[i][lane] = C[i];
+#pragma unroll
+		for (int i = 0; i < 6; i++) red[36 + i][lane] = v[i];
+	}
+	__syncwarp();
+	for (int e = lane; e < 42; e += 32) {
+		T s = T(0);
+		for (int x = 0; x < nact; x++) s += red[e][x];
+		if (e < 36) {
+			const int c = e / 6, r = e - 6 * c;
+			T val = -s;
+			if (diag && a.addDiag) val += a.Hpp[36 * (size_t)ra + e] + (r == c ? a.lambda : T(0));
+			a.fVal[36 * (size_t)a.u2f[k] + e] = val;
+			if (!diag) a.fVal[36 * (size_t)a.u2fT[k] + r * 6 + c] = val;
+		} else if (diag) {
+			const int r = e - 36;
+			a.bsc[6 * (size_t)ra + r] = (a.addDiag ? a.bp[6 * (size_t)ra + r] : T(0)) - s;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block-Jacobi preconditioned CG on the symmetric-full BSR Schur matrix: ONE cooperative launch per
+// solve, two grid barriers per iteration, all reductions in fixed order (deterministic).
+// Replaces convertBSRToCSR + cuSOLVER csrchol factor/solve (reference cuda_linear_solver.cpp:301-335).
+// ------------------------------------------------------------------------------------------------
+struct PcgStatus { int iters; int status; double rz0; double rz; };  // status: 0 converged, 1 max iters, 2 breakdown
+
+template <typename T>
+struct PcgArgs {
+	const int* fRowPtr; const int* fColInd; const T* fVal;
+	const T* b;         // bsc
+	int numP;
+	T* x; T* r; T* z; T* q; T* p0; T* p1; T* Minv;
+	double* partial;    // [2 * gridDim] scratch
+	int maxIters; double tol2;
+	PcgStatus* status;
+};
+
+__device__ __forceinline__ double grid_reduce(cg::grid_group& grid, double local, double* partial, double* s_red, double* s_bcast)
+{
+	const double bs = block_sum(local, s_red);
+	if (threadIdx.x == 0) partial[blockIdx.x] = bs;
+	grid.sync();
+	if (threadIdx.x < 32) {
+		double s = 0;
+		for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) s += partial[i];
+		s = warp_sum(s);
+		if (threadIdx.x == 0) *s_bcast = s;
+	}
+	__syncthreads();
+	const double out = *s_bcast;
+	__syncthreads();
+	return out;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(PCG_BLOCK) k_pcg(const PcgArgs<T> a)
+{
+	cg::grid_group grid = cg::this_grid();
+	__shared__ double s_red[PCG_BLOCK / 32];
+	__shared__ double s_bcast;
+	const int lane = threadIdx.x & 31;
+	const int gwarp = (blockIdx.x * PCG_BLOCK + threadIdx.x) >> 5;
+	const int nwarps = (gridDim.x * PCG_BLOCK) >> 5;
+	const int gtid = blockIdx.x * PCG_BLOCK + threadIdx.x, gthreads = gridDim.x * PCG_BLOCK;
+	int bad = 0;
+
+	// setup: Minv = inverse of the diagonal blocks; x = 0; r = b; z = Minv r
+	for (int i = gtid; i < a.numP; i += gthreads) {
+		int d = -1;
+		for (int n = a.fRowPtr[i]; n < a.fRowPtr[i + 1]; n++) if (a.fColInd[n] == i) { d = n; break; }
+		T M[36];
+		for (int e = 0; e < 36; e++) M[e] = d >= 0 ? a.fVal[36 * (size_t)d + e] : ((e % 7) == 0 ? T(1) : T(0));
+		if (!spd6_inverse(M)) { bad = 1; for (int e = 0; e < 36; e++) M[e] = (e % 7) == 0 ? T(1) : T(0); }
+		T rr[6], zz[6];
+		for (int e = 0; e < 36; e++) a.Minv[36 * (size_t)i + e] = M[e];
+		for (int e = 0; e < 6; e++) { rr[e] = a.b[6 * (size_t)i + e]; a.r[6 * (size_t)i + e] = rr[e]; a.x[6 * (size_t)i + e] = T(0); }
+		for (int rI = 0; rI < 6; rI++) {
+			T s = T(0);
+			for (int c = 0; c < 6; c++) s += M[c * 6 + rI] * rr[c];
+			zz[rI] = s;
+			a.z[6 * (size_t)i + rI] = s;
+			a.p0[6 * (size_t)i + rI] = T(0);
+		}
+	}
+	double loc = 0;
+	// (re-read to keep the reduction order independent of the thread->pose mapping above)
+	grid.sync();
+	for (int i = gtid; i < a.numP * 6; i += gthreads) loc += (double)a.r[i] * (double)a.z[i];
+	double rz = grid_reduce(grid, loc, a.partial, s_red, &s_bcast);
+	const double nbad = grid_reduce(grid, (double)bad, a.partial + gridDim.x, s_red, &s_bcast);
+	const double rz0 = rz;
+	int status = 1, it = 0;
+	if (nbad > 0 || !(rz0 == rz0)) { status = 2; }
+	else if (rz0 <= 0) { status = 0; }
+	else {
+		T* pold = a.p0; T* pnew = a.p1;
+		double beta = 0;
+		for (it = 0; it < a.maxIters;) {
+			// phase A: p = z + beta*pold (own rows -> pnew), q = S p, partial p.q
+			loc = 0;
+			for (int i = gwarp; i < a.numP; i += nwarps) {
+				T acc[6] = { T(0), T(0), T(0), T(0), T(0), T(0) };
+				const int n1 = a.fRowPtr[i + 1];
+				for (int n = a.fRowPtr[i] + lane; n < n1; n += 32) {
+					const int j = a.fColInd[n];
+					T pj[6];
+#pragma unroll
+					for (int c = 0; c < 6; c++) pj[c] = a.z[6 * (size_t)j + c] + (T)beta * pold[6 * (size_t)j + c];
+					const T* B = a.fVal + 36 * (size_t)n;
+#pragma unroll
+					for (int c = 0; c < 6; c++) {
+						T b0, b1, b2, b3, b4, b5;
+						ld2(B + c * 6, b0, b1); ld2(B + c * 6 + 2, b2, b3); ld2(B + c * 6 + 4, b4, b5);
+						acc[0] += b0 * pj[c]; acc[1] += b1 * pj[c]; acc[2] += b2 * pj[c];
+						acc[3] += b3 * pj[c]; acc[4] += b4 * pj[c]; acc[5] += b5 * pj[c];
+					}
+				}
+#pragma unroll
+				for (int c = 0; c < 6; c++) acc[c] = warp_sum(acc[c]);
+				if (lane < 6) {
+					T qi = acc[0];
+#pragma unroll
+					for (int c = 1; c < 6; c++) if (lane == c) qi = acc[c];
+					const T pi = a.z[6 * (size_t)i + lane] + (T)beta * pold[6 * (size_t)i + lane];
+					pnew[6 * (size_t)i + lane] = pi;
+					a.q[6 * (size_t)i + lane] = qi;
+					loc += (double)pi * (double)qi;
+				}
+			}
+			const double pq = grid_reduce(grid, loc, a.partial, s_red, &s_bcast);
+			if (!(pq > 0) || !(pq == pq)) { status = 2; break; }
+			const double alpha = rz / pq;
+			// phase B: x += alpha p; r -= alpha q; z = Minv r; partial r.z
+			loc = 0;
+			for (int i = gwarp; i < a.numP; i += nwarps) {
+				T ri = T(0);
+				if (lane < 6) {
+					const size_t o = 6 * (size_t)i + lane;
+					a.x[o] += (T)alpha * pnew[o];
+					ri = a.r[o] - (T)alpha * a.q[o];
+					a.r[o] = ri;
+				}
+				T zi = T(0);
+				const T* M = a.Minv + 36 * (size_t)i;
+#pragma unroll
+				for (int c = 0; c < 6; c++) {
+					const T rc = __shfl_sync(0xffffffffu, ri, c);
+					if (lane < 6) zi += M[c * 6 + lane] * rc;
+				}
+				if (lane < 6) { a.z[6 * (size_t)i + lane] = zi; loc += (double)ri * (double)zi; }
+			}
+			const double rzn = grid_reduce(grid, loc, a.partial + gridDim.x, s_red, &s_bcast);
+			it++;
+			if (!(rzn == rzn)) { status = 2; break; }
+			beta = rzn / rz;
+			rz = rzn;
+			T* tmp = pold; pold = pnew; pnew = tmp;
+			if (rz <= a.tol2 * rz0) { status = 0; break; }
+		}
+	}
+	if (gtid == 0) { a.status->iters = it; a.status->status = status; a.status->rz0 = rz0; a.status->rz = rz; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Back-substitution + landmark update + landmark part of the LM scale, landmark tiles again:
+//   xl = invHll (bl - sum_i Hpl_i^T xp[row_i]) ; Xw_trial = Xw + xl ; scale += xl.(lambda xl + bl)
+// (reference cu:1029-1043, 1057-1068, 1070-1091)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct BacksubArgs {
+	const T* Hpl; const T* invHll; const T* bl; const T* xp;
+	const int* ip; const int* hpl; const int* lmPtr; const int* tileLm;
+	int numL;
+	T lambda;
+	const T* XwCur; T* XwTrial; T* xl;
+	double* scalePartial;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(TILE) k_backsub(const BacksubArgs<T> a)
+{
+	__shared__ T s_val[3][TILE + 1];
+	__shared__ T s_acc[TILE * 3];
+	__shared__ int s_ptr[TILE + 1];
+	__shared__ double s_red[TILE / 32];
+	const int tid = threadIdx.x;
+	const int l0 = a.tileLm[blockIdx.x], l1 = a.tileLm[blockIdx.x + 1];
+	const int nl = l1 - l0;
+	double sc = 0;
+	if (l0 < a.numL) {   // tiles of fixed landmarks have nothing to solve (uniform branch)
+		for (int i = tid; i <= nl; i += TILE) s_ptr[i] = a.lmPtr[l0 + i];
+		for (int i = tid; i < nl * 3; i += TILE) s_acc[i] = T(0);
+		__syncthreads();
+		const int e0 = s_ptr[0], e1 = s_ptr[nl];
+		for (int cs = e0; cs < e1; cs += TILE) {
+			const int e = cs + tid;
+			T v0 = T(0), v1 = T(0), v2 = T(0);
+			if (e < e1) {
+				const int hp = a.hpl[e];
+				if (hp >= 0) {
+					const int ip = a.ip[e] & 0x7fffffff;
+					const T* A = a.Hpl + 18 * (size_t)hp;
+					const T* x = a.xp + 6 * (size_t)ip;
+					T xr[6];
+					ld2(x, xr[0], xr[1]); ld2(x + 2, xr[2], xr[3]); ld2(x + 4, xr[4], xr[5]);
+					T A0[6], A1[6], A2[6];
+#pragma unroll
+					for (int r = 0; r < 6; r += 2) { ld2(A + r, A0[r], A0[r + 1]); ld2(A + 6 + r, A1[r], A1[r + 1]); ld2(A + 12 + r, A2[r], A2[r + 1]); }
+#pragma unroll
+					for (int r = 0; r < 6; r++) { v0 += A0[r] * xr[r]; v1 += A1[r] * xr[r]; v2 += A2[r] * xr[r]; }
+				}
+			}
+			s_val[0][tid] = v0; s_val[1][tid] = v1; s_val[2][tid] = v2;
+			__syncthreads();
+			for (int wi = tid; wi < nl * 3; wi += TILE) {
+				const int j = wi / 3, cc = wi - 3 * j;
+				int s = s_ptr[j], t = s_ptr[j + 1];
+				s = (s > cs ? s : cs) - cs;
+				t = (t < cs + TILE ? t : cs + TILE) - cs;
+				if (t > s) {
+					T sum = T(0);
+					for (int k = s; k < t; k++) sum += s_val[cc][k];
+					s_acc[wi] += sum;
+				}
+			}
+			__syncthreads();
+		}
+		for (int j = tid; j < nl; j += TILE) {
+			const int l = l0 + j;
+			if (l < a.numL) {
+				const T* bl = a.bl + 3 * (size_t)l;
+				const T c0 = bl[0] - s_acc[3 * j], c1 = bl[1] - s_acc[3 * j + 1], c2 = bl[2] - s_acc[3 * j + 2];
+				const T* iv = a.invHll + 9 * (size_t)l;
+				const T x0 = iv[0] * c0 + iv[3] * c1 + iv[6] * c2;
+				const T x1 = iv[1] * c0 + iv[4] * c1 + iv[7] * c2;
+				const T x2 = iv[2] * c0 + iv[5] * c1 + iv[8] * c2;
+				a.xl[3 * (size_t)l] = x0; a.xl[3 * (size_t)l + 1] = x1; a.xl[3 * (size_t)l + 2] = x2;
+				const T* X = a.XwCur + 4 * (size_t)l;
+				T* Y = a.XwTrial + 4 * (size_t)l;
+				Y[0] = X[0] + x0; Y[1] = X[1] + x1; Y[2] = X[2] + x2; Y[3] = T(0);
+				sc += (double)(x0 * (a.lambda * x0 + bl[0]) + x1 * (a.lambda * x1 + bl[1]) + x2 * (a.lambda * x2 + bl[2]));
+			}
+		}
+	}
+	const double tot = block_sum(sc, s_red);
+	if (tid == 0) a.scalePartial[blockIdx.x] = tot;
+}
+
+// landmark-only BA (no free pose): xl = (Hll + lambda I)^-1 bl  (reference cu:1124-1131)
+template <typename T>
+__global__ void k_solve_landmarks_only(const T* invHll, const T* bl, int numL, T lambda, const T* XwCur, T* XwTrial, T* xl, double* scalePartial)
+{
+	__shared__ double s_red[RED_BLOCK / 32];
+	const int l = blockIdx.x * blockDim.x + threadIdx.x;
+	double sc = 0;
+	if (l < numL) {
+		const T* iv = invHll + 9 * (size_t)l; const T* b = bl + 3 * (size_t)l;
+		const T x0 = iv[0] * b[0] + iv[3] * b[1] + iv[6] * b[2];
+		const T x1 = iv[1] * b[0] + iv[4] * b[1] + iv[7] * b[2];
+		const T x2 = iv[2] * b[0] + iv[5] * b[1] + iv[8] * b[2];
+		xl[3 * (size_t)l] = x0; xl[3 * (size_t)l + 1] = x1; xl[3 * (size_t)l + 2] = x2;
+		const T* X = XwCur + 4 * (size_t)l; T* Y = XwTrial + 4 * (size_t)l;
+		Y[0] = X[0] + x0; Y[1] = X[1] + x1; Y[2] = X[2] + x2; Y[3] = T(0);
+		sc = (double)(x0 * (lambda * x0 + b[0]) + x1 * (lambda * x1 + b[1]) + x2 * (lambda * x2 + b[2]));
+	}
+	const double tot = block_sum(sc, s_red);
+	if (threadIdx.x == 0) scalePartial[blockIdx.x] = tot;
+}
+
+// pose-only BA (no free landmark): xp = (Hpp + lambda I)^-1 bp  (reference cu:1133-1140 solves the
+// 6x6 by a 3+3 Schur split; we use the Cholesky inverse -- same solution up to rounding)
+template <typename T>
+__global__ void k_solve_poses_only(const T* Hpp, const T* bp, int numP, T lambda, T* xp)
+{
+	const int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= numP) return;
+	T M[36];
+	for (int e = 0; e < 36; e++) M[e] = Hpp[36 * (size_t)p + e] + ((e % 7) == 0 ? lambda : T(0));
+	if (!spd6_inverse(M)) { for (int e = 0; e < 6; e++) xp[6 * (size_t)p + e] = T(0); return; }
+	for (int r = 0; r < 6; r++) {
+		T s = T(0);
+		for (int c = 0; c < 6; c++) s += M[c * 6 + r] * bp[6 * (size_t)p + c];
+		xp[6 * (size_t)p + r] = s;
+	}
+}
+
+// SE(3) update of the free poses into the trial buffer + pose part of the LM scale (cu:1045-1055,1070-1091)
+template <typename T>
+__global__ void k_update_poses(const T* xp, const T* bp, int numP, T lambda, const T* poseCur, T* poseTrial, double* scalePartial)
+{
+	__shared__ double s_red[RED_BLOCK / 32];
+	const int p = blockIdx.x * blockDim.x + threadIdx.x;
+	double sc = 0;
+	if (p < numP) {
+		T u[6], q[4], t[3];
+		for (int i = 0; i < 6; i++) u[i] = xp[6 * (size_t)p + i];
+		const T* s = poseCur + 8 * (size_t)p;
+		for (int i = 0; i < 4; i++) q[i] = s[i];
+		for (int i = 0; i < 3; i++) t[i] = s[4 + i];
+		se3_update(u, q, t);
+		T* d = poseTrial + 8 * (size_t)p;
+		for (int i = 0; i < 4; i++) d[i] = q[i];
+		for (int i = 0; i < 3; i++) d[4 + i] = t[i];
+		d[7] = T(0);
+		T acc = T(0);
+		for (int i = 0; i < 6; i++) acc += u[i] * (lambda * u[i] + bp[6 * (size_t)p + i]);
+		sc = (double)acc;
+	}
+	const double tot = block_sum(sc, s_red);
+	if (threadIdx.x == 0) scalePartial[blockIdx.x] = tot;
+}
+
+// Residual-only pass: robustified chi2 of a state (trial evaluation) -- reference cu:732-786 without
+// the errors/Xcs side outputs.  Grid-stride over the landmark-major edge stream, block partials.
+template <typename T>
+struct ChiArgs {
+	const T* pose; const T* cam; const T* Xw;
+	const T* mx; const T* my; const T* mz; const T* om; const int* ip; const int* il;
+	int E;
+	RobustParams rk;
+	double* chiPartial;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(RED_BLOCK) k_chi2(const ChiArgs<T> a)
+{
+	__shared__ double s_red[RED_BLOCK / 32];
+	double chi = 0;
+	for (int e = blockIdx.x * RED_BLOCK + threadIdx.x; e < a.E; e += gridDim.x * RED_BLOCK) {
+		const int ipf = a.ip[e];
+		const bool stereo = ipf < 0;
+		T q[4], t[3], c[5], X[3], m[3], Xc[3], r[3];
+		load_pose(a.pose, a.cam, ipf & 0x7fffffff, q, t, c);
+		load_xw(a.Xw, a.il[e], X);
+		m[0] = a.mx[e]; m[1] = a.my[e]; m[2] = stereo ? a.mz[e] : T(0);
+		edge_residual(q, t, c, X, m, stereo, Xc, r);
+		const T e2 = a.om[e] * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+		T rho, drho;
+		robust<T>(a.rk.type[stereo ? 1 : 0], (T)a.rk.delta[stereo ? 1 : 0], e2, rho, drho);
+		chi += (double)rho;
+	}
+	const double tot = block_sum(chi, s_red);
+	if (threadIdx.x == 0) a.chiPartial[blockIdx.x] = tot;
+}
+
+// per-edge non-robust omega*|r|^2 in edge-id order (reference cu:841-875)
+template <typename T>
+__global__ void k_chi_sqs(const ChiArgs<T> a, const int* userId, double* out)
+{
+	const int e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= a.E) return;
+	const int ipf = a.ip[e];
+	const bool stereo = ipf < 0;
+	T q[4], t[3], c[5], X[3], m[3], Xc[3], r[3];
+	load_pose(a.pose, a.cam, ipf & 0x7fffffff, q, t, c);
+	load_xw(a.Xw, a.il[e], X);
+	m[0] = a.mx[e]; m[1] = a.my[e]; m[2] = stereo ? a.mz[e] : T(0);
+	edge_residual(q, t, c, X, m, stereo, Xc, r);
+	out[userId[e]] = (double)(a.om[e] * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]));
+}
+
+// Fixed-order sum of up to three partial arrays into out[0..2] (single CTA).
+__global__ void __launch_bounds__(RED_BLOCK) k_sum_partials(const double* p0, int n0, const double* p1, int n1, const double* p2, int n2, double* out)
+{
+	__shared__ double s_red[RED_BLOCK / 32];
+	const double* ps[3] = { p0, p1, p2 };
+	const int ns[3] = { n0, n1, n2 };
+	for (int k = 0; k < 3; k++) {
+		double s = 0;
+		for (int i = threadIdx.x; i < ns[k]; i += RED_BLOCK) s += ps[k][i];
+		const double tot = block_sum(s, s_red);
+		if (threadIdx.x == 0) out[k] = tot;
+	}
+}
+
+// L2 flush helper for the micro-benchmarks: overwrite a buffer larger than L2.
+__global__ void k_fill(double* p, size_t n, double v)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+}  // namespace cuba_b200

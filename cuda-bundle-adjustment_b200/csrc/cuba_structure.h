@@ -1,0 +1,69 @@
+// cuba_structure.h -- host-side construction of every index structure of the LM path from the flat
+// (iP,iL) edge list.  Pure C++ (no CUDA) so the not-gpu tests can exercise it through
+// cuba_debug_build_structure_host().
+//
+// What it replaces in the reference (paths relative to the reference checkout):
+//   gpu::buildHplStructure            src/cuda_block_solver.cu:1158-1173   (Hpl CSC, edge2Hpl)
+//   HschurSparseBlockMatrix::constructFromVertices  src/sparse_block_matrix.cpp:55-133 (Hsc upper BSR)
+//   gpu::findHschureMulBlockIndices   cu:979-1000,1175-1190                 (block-product list)
+// plus what is new here: the canonical (iL,iP) edge order, landmark tiles, the pose-major edge copy,
+// the destination-sorted product list and the symmetric-full BSR used by the PCG.
+#pragma once
+
+#include <cstdint>
+#include <vector>
+
+namespace cuba_b200 {
+
+struct Structure {
+	// sizes
+	int Pall = 0, numP = 0, Lall = 0, numL = 0, E2 = 0, E3 = 0, E = 0;
+	int nhpl = 0;          // global number of Hpl blocks (free-free edges)
+	int nblk = 0;          // upper-triangular Hsc blocks
+	long long nmul = 0;    // global number of block products
+	int nfull = 0;         // blocks of the symmetric-full BSR
+	// landmark shard owned by this rank: landmarks [lmBeg, lmEnd)
+	int lmBeg = 0, lmEnd = 0;
+	int eLocal = 0;        // edges of the shard
+	int hplBase = 0;       // first global Hpl index of the shard
+	int nhplLocal = 0;
+	long long nmulLocal = 0;
+
+	// global structures (bit-exact contract with the reference)
+	std::vector<int> hplColPtr;   // [numL+1]
+	std::vector<int> hplRowInd;   // [nhpl]
+	std::vector<int> edge2Hpl;    // [E] user edge id -> Hpl block (-1 when an end is fixed)
+	std::vector<int> hscRowPtr;   // [numP+1] upper BSR
+	std::vector<int> hscColInd;   // [nblk]
+
+	// landmark-major edge stream of the shard (sorted by (iL,iP,edge id))
+	std::vector<int> order;       // [eLocal] user edge id of each stream slot
+	std::vector<int> e_ip;        // bit31 = stereo
+	std::vector<int> e_il;
+	std::vector<int> e_hpl;       // LOCAL Hpl index or -1
+	std::vector<int> lmPtr;       // [Lall+1] stream offsets; landmarks outside the shard have empty runs
+	std::vector<int> tileLm;      // [ntiles+1] first landmark of each tile
+	std::vector<int> hplLm;       // [nhplLocal] landmark of each local Hpl block
+
+	// pose-major stream of the shard (free poses only), sorted by (iP,iL)
+	std::vector<int> posePtr;     // [numP+1]
+	std::vector<int> p_src;       // [npose_edges] landmark-major slot each entry was copied from
+	std::vector<int> p_il;        // bit31 = stereo
+
+	// destination-sorted product list of the shard's landmarks
+	std::vector<int> blkRow, blkCol;   // [nblk]
+	std::vector<int> prodPtr;          // [nblk+1]
+	std::vector<int> prodI, prodJ;     // [nmulLocal] LOCAL Hpl indices, row(prodI) <= row(prodJ)
+
+	// symmetric-full BSR
+	std::vector<int> fRowPtr;     // [numP+1]
+	std::vector<int> fColInd;     // [nfull]
+	std::vector<int> u2f, u2fT;   // [nblk] upper block -> full position of (a,b) and of (b,a)
+};
+
+// idx2/idx3: (iP,iL) pairs.  rank/world select the landmark shard (world==1: everything).
+// Returns false and fills err on inconsistent input.
+bool build_structure(int Pall, int numP, int Lall, int numL, int E2, const int32_t* idx2, int E3, const int32_t* idx3,
+	int rank, int world, int tileEdges, Structure& S, const char** err);
+
+}  // namespace cuba_b200

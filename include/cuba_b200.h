@@ -1,0 +1,194 @@
+/*
+ * cuba_b200.h -- C ABI of the B200-native Levenberg-Marquardt bundle-adjustment engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of fixstars/cuda-bundle-adjustment:
+ * everything the reference's CudaBlockSolver does below `optimize()` (paths relative to the reference
+ * checkout):
+ *
+ *   what this ABI replaces                                   reference interface
+ *   ------------------------------------------------------   -------------------------------------------------
+ *   cuba_engine_set_problem   (flat arrays -> device, + all   CudaBlockSolver::initialize/buildStructure,
+ *                              sparsity structures)           src/cuda_bundle_adjustment.cpp:115-366;
+ *                                                             gpu::buildHplStructure / findHschureMulBlockIndices,
+ *                                                             src/cuda_block_solver.h:36-41;
+ *                                                             HschurSparseBlockMatrix, src/sparse_block_matrix.h:81-98
+ *   cuba_engine_optimize      (whole LM loop)                 CudaBundleAdjustmentImpl::optimize, cpp:793-857
+ *   cuba_stage_linearize      (residual+Jacobian+Hessian)     gpu::computeActiveErrors + gpu::constructQuadraticForm,
+ *                                                             src/cuda_block_solver.h:43-57
+ *   cuba_stage_max_diagonal                                   gpu::maxDiagonal, h:65-67
+ *   cuba_stage_solve          (Schur + PCG + back-subst.)     gpu::addLambda/computeBschure/computeHschure/
+ *                                                             convertHschureBSRToCSR/schurComplementPost, h:69-88 and
+ *                                                             SparseLinearSolver::solve, src/cuda_linear_solver.h:28-39
+ *   cuba_stage_update         (SE3 exp update + trial chi2)   gpu::updatePoses/updateLandmarks/computeScale, h:90-94
+ *   cuba_engine_get_state / _get_chi2 / _get_profile          CudaBlockSolver::finalize/getChiSqs/getTimeProfile,
+ *                                                             cpp:512-562
+ *
+ * Plain C types only: pointers and sizes, no torch / Eigen / STL types.  All host arrays are fp64 and
+ * column-major where they hold blocks (reference MatView, src/cuda_block_solver.cu:79-85); an engine
+ * configured for fp32 narrows at this boundary like the reference's ScalarCast (cpp:54-69).
+ *
+ * Every function returns CUBA_OK (0) or a negative error code; cuba_last_error() gives the message.
+ * The library has NO CPU fallback: without a usable CUDA device every compute entry point fails with
+ * CUBA_ERR_CUDA.
+ */
+#ifndef CUBA_B200_H
+#define CUBA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUBA_OK 0
+#define CUBA_ERR_INVALID (-1)  /* bad argument / inconsistent problem                */
+#define CUBA_ERR_CUDA (-2)     /* CUDA runtime failure or no device                  */
+#define CUBA_ERR_STATE (-3)    /* call order violated (e.g. optimize before problem) */
+#define CUBA_ERR_COMM (-4)     /* NCCL failure                                       */
+
+/* robust kernels: reference include/cuda_bundle_adjustment_types.h:213-218, cu:692-727 */
+#define CUBA_ROBUST_NONE 0
+#define CUBA_ROBUST_HUBER 1
+#define CUBA_ROBUST_TUKEY 2
+
+/* edge types: reference include/cuda_bundle_adjustment_types.h:143-148 */
+#define CUBA_EDGE_MONOCULAR 0
+#define CUBA_EDGE_STEREO 1
+
+/* time-profile buckets: same 8 items as the reference, cpp:77-88,547-557 */
+#define CUBA_PROF_INITIALIZE 0
+#define CUBA_PROF_BUILD_STRUCTURE 1
+#define CUBA_PROF_COMPUTE_ERROR 2
+#define CUBA_PROF_BUILD_SYSTEM 3
+#define CUBA_PROF_SCHUR_COMPLEMENT 4
+#define CUBA_PROF_DECOMP_SYMBOLIC 5   /* always 0: PCG has no symbolic phase */
+#define CUBA_PROF_DECOMP_NUMERICAL 6  /* the PCG solve                        */
+#define CUBA_PROF_UPDATE 7
+#define CUBA_PROF_NUM 8
+
+typedef struct cuba_config {
+	int device;            /* CUDA device ordinal, -1 = current device                            */
+	int use_fp32;          /* 0 = fp64 (default); 1 = reference's USE_FLOAT32 behaviour           */
+	int pcg_max_iters;     /* <=0: default                                         */
+	double pcg_tol;        /* stop when sqrt(r'z / r0'z0) <= pcg_tol; <=0: default 1e-13           */
+	int deterministic;     /* 1 (default): fixed-order reductions, bit-reproducible run to run     */
+	int reserved[7];
+} cuba_config;
+
+/* Flat problem: exactly what CudaBlockSolver::initialize produces (cpp:115-261).
+ * Vertices are indexed by iP / iL: free vertices first (iP < numP, iL < numL), fixed ones appended.
+ * Edges with both ends fixed must not be present.  Edge ids: monocular 0..E2-1, stereo E2..E2+E3-1. */
+typedef struct cuba_problem {
+	int32_t Pall, numP;
+	int32_t Lall, numL;
+	const double* q;       /* [4*Pall] unit quaternions, coefficient order x,y,z,w                */
+	const double* t;       /* [3*Pall]                                                            */
+	const double* cam;     /* [5*Pall] fx,fy,cx,cy,bf per pose                                    */
+	const double* Xw;      /* [3*Lall]                                                            */
+	int32_t E2;
+	const int32_t* idx2;   /* [2*E2] (iP,iL) per monocular edge                                   */
+	const double* meas2;   /* [2*E2] (u,v)                                                        */
+	const double* omega2;  /* [E2] scalar information                                             */
+	int32_t E3;
+	const int32_t* idx3;   /* [2*E3]                                                              */
+	const double* meas3;   /* [3*E3] (u_left, v, u_right)                                         */
+	const double* omega3;  /* [E3]                                                                */
+} cuba_problem;
+
+/* reference BatchInfo (include/cuda_bundle_adjustment_types.h:226-232) plus solver diagnostics */
+typedef struct cuba_iter_stat {
+	int32_t iteration;
+	int32_t trials;        /* LM trials spent in this outer iteration (1 = first trial accepted)   */
+	double chi2;           /* objective after the iteration (robustified, like the reference)      */
+	double lambda;         /* damping after the iteration                                          */
+	int32_t pcg_iters;     /* PCG iterations summed over the trials                                */
+	int32_t pcg_failed;    /* number of trials whose PCG did not converge / broke down             */
+} cuba_iter_stat;
+
+typedef struct cuba_sizes {
+	int32_t Pall, numP, Lall, numL, E2, E3;
+	int32_t nhpl;          /* free-free edges = Hpl blocks                                         */
+	int32_t nblk;          /* upper-triangular Hsc blocks                                          */
+	int32_t nmul;          /* Schur block products                                                 */
+	int32_t nblk_full;     /* blocks of the symmetric-full BSR used by the PCG                     */
+} cuba_sizes;
+
+typedef struct cuba_engine cuba_engine;
+
+const char* cuba_last_error(void);
+int cuba_version(void);
+
+int cuba_engine_create(const cuba_config* cfg /* NULL = defaults */, cuba_engine** out);
+int cuba_engine_destroy(cuba_engine* e);
+
+/* setRobustKernels (include/cuda_bundle_adjustment.h:93): one kernel per edge type */
+int cuba_engine_set_robust_kernel(cuba_engine* e, int edge_type, int kernel_type, double delta);
+
+/* Landmark sharding for multi-GPU runs (one process per GPU).  Must precede set_problem.
+ * `nccl_unique_id` = 128 bytes produced by cuba_comm_unique_id() on rank 0 and broadcast by the host
+ * (torch.distributed / MPI / a file).  world == 1 disables it. */
+int cuba_comm_unique_id(void* out128);
+int cuba_engine_set_comm(cuba_engine* e, int rank, int world, const void* nccl_unique_id);
+
+/* Upload the problem and build every index structure (initialize + buildStructure). */
+int cuba_engine_set_problem(cuba_engine* e, const cuba_problem* p);
+/* Replace only the estimate (q,t,Xw), keeping structure -- repeated optimize() on the same graph. */
+int cuba_engine_set_state(cuba_engine* e, const double* q, const double* t, const double* Xw);
+
+int cuba_engine_get_sizes(const cuba_engine* e, cuba_sizes* out);
+
+/* optimize(niterations): stats[niterations]; *nstats = number of entries written (cpp:848-851). */
+int cuba_engine_optimize(cuba_engine* e, int niterations, cuba_iter_stat* stats, int* nstats);
+
+/* finalize(): current estimate, [4*Pall], [3*Pall], [3*Lall]; any pointer may be NULL */
+int cuba_engine_get_state(cuba_engine* e, double* q, double* t, double* Xw);
+/* getChiSqs(): non-robust omega*|r|^2 per edge, edge-id order, [E2+E3] */
+int cuba_engine_get_chi2(cuba_engine* e, double* per_edge);
+/* seconds per profile bucket accumulated since set_problem, [CUBA_PROF_NUM] */
+int cuba_engine_get_profile(cuba_engine* e, double* seconds);
+/* number of kernels this library launched since create (for bench.py's gpu_launches) */
+int cuba_engine_get_launch_count(cuba_engine* e, long long* count);
+
+/* ---- stage-wise entry points (used by optimize(); exported for stage parity tests) ---- */
+int cuba_stage_linearize(cuba_engine* e, double* chi2);
+int cuba_stage_max_diagonal(cuba_engine* e, double* maxdiag);
+/* Schur complement with damping lambda, PCG, back-substitution.  *ok = 0 when PCG failed. */
+int cuba_stage_solve(cuba_engine* e, double lambda, int* pcg_iters, int* ok);
+/* trial update into the spare state buffer + its chi2 and the LM scale (without the +1e-3) */
+int cuba_stage_update(cuba_engine* e, double lambda, double* chi2_trial, double* scale);
+/* accept (swap buffers) or reject (keep) the trial state */
+int cuba_stage_commit(cuba_engine* e, int accept);
+/* residual-only pass on the current state */
+int cuba_stage_chi2(cuba_engine* e, double* chi2);
+
+/* ---- debug getters (host copies; blocks column-major; any pointer may be NULL) ---- */
+/* Hpl CSC sorted by (iL,iP): colPtr[numL+1], rowInd[nhpl], edge2Hpl[E2+E3] (-1 = no block) */
+int cuba_debug_get_hpl_structure(cuba_engine* e, int32_t* colPtr, int32_t* rowInd, int32_t* edge2Hpl);
+/* Hsc upper-triangular BSR: rowPtr[numP+1], colInd[nblk] */
+int cuba_debug_get_hsc_structure(cuba_engine* e, int32_t* rowPtr, int32_t* colInd);
+int cuba_debug_get_system(cuba_engine* e, double* Hpp /*36*numP*/, double* bp /*6*numP*/, double* Hll /*9*numL*/,
+	double* bl /*3*numL*/, double* Hpl /*18*nhpl*/);
+int cuba_debug_get_schur(cuba_engine* e, double* Hsc /*36*nblk, upper*/, double* bsc /*6*numP*/, double* invHll /*9*numL*/);
+int cuba_debug_get_delta(cuba_engine* e, double* xp /*6*numP*/, double* xl /*3*numL*/);
+
+/* Host-only (no CUDA call): builds the index structures from the (iP,iL) lists exactly as
+ * cuba_engine_set_problem does and copies them out -- the not-gpu tests check them against the oracle.
+ * Sizes are returned first with all array pointers NULL, then the arrays on a second call. */
+int cuba_debug_build_structure_host(const cuba_problem* p, int rank, int world, cuba_sizes* sizes,
+	int32_t* hplColPtr /*numL+1*/, int32_t* hplRowInd /*nhpl*/, int32_t* edge2Hpl /*E2+E3*/,
+	int32_t* hscRowPtr /*numP+1*/, int32_t* hscColInd /*nblk*/,
+	int32_t* fullRowPtr /*numP+1*/, int32_t* fullColInd /*nblk_full*/,
+	int32_t* shard /*[4]: lmBeg, lmEnd, edges, local products*/);
+
+/* ---- micro-benchmark hooks for bench.py / profiles (device-resident data, CUDA-event timed) ---- */
+/* Runs the named stage `reps` times back to back and returns the average device milliseconds per
+ * repetition.  stage: 0 linearize (landmark pass + pose pass), 1 landmark pass only, 2 pose pass only,
+ * 3 schur, 4 pcg, 5 backsub+update+residual, 6 residual only.  flush_l2 != 0 writes a >L2 buffer
+ * between repetitions (outside the timed interval). */
+int cuba_bench_stage(cuba_engine* e, int stage, int reps, int flush_l2, double lambda, double* avg_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUBA_B200_H */
