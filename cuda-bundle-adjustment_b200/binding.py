@@ -47,9 +47,9 @@ _lib = None
 
 _SYMBOLS = [
     "cuba_last_error", "cuba_version", "cuba_engine_create", "cuba_engine_destroy", "cuba_engine_set_robust_kernel",
-    "cuba_comm_unique_id", "cuba_engine_set_comm", "cuba_engine_set_problem", "cuba_engine_set_state", "cuba_engine_get_sizes",
+    "cuba_comm_unique_id", "cuba_engine_set_comm", "cuba_engine_set_problem", "cuba_engine_set_state", "cuba_engine_get_sizes", "cuba_engine_reset_state", "cuba_engine_get_stream", "cuba_engine_flush_l2",
     "cuba_engine_optimize", "cuba_engine_get_state", "cuba_engine_get_chi2", "cuba_engine_get_profile",
-    "cuba_engine_get_launch_count", "cuba_stage_linearize", "cuba_stage_max_diagonal", "cuba_stage_solve", "cuba_stage_update",
+    "cuba_engine_get_launch_count", "cuba_get_transfer_bytes", "cuba_stage_linearize", "cuba_stage_max_diagonal", "cuba_stage_solve", "cuba_stage_update",
     "cuba_stage_commit", "cuba_stage_chi2", "cuba_debug_get_hpl_structure", "cuba_debug_get_hsc_structure",
     "cuba_debug_get_system", "cuba_debug_get_schur", "cuba_debug_get_delta", "cuba_debug_build_structure_host", "cuba_bench_stage",
 ]
@@ -79,11 +79,15 @@ def load_library():
         "cuba_engine_set_problem": [vp, C.POINTER(_Problem)],
         "cuba_engine_set_state": [vp, vp, vp, vp],
         "cuba_engine_get_sizes": [vp, C.POINTER(_Sizes)],
+        "cuba_engine_reset_state": [vp],
+        "cuba_engine_get_stream": [vp, C.POINTER(vp)],
+        "cuba_engine_flush_l2": [vp],
         "cuba_engine_optimize": [vp, i, vp, C.POINTER(i)],
         "cuba_engine_get_state": [vp, vp, vp, vp],
         "cuba_engine_get_chi2": [vp, vp],
         "cuba_engine_get_profile": [vp, vp],
         "cuba_engine_get_launch_count": [vp, C.POINTER(C.c_longlong)],
+        "cuba_get_transfer_bytes": [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)],
         "cuba_stage_linearize": [vp, C.POINTER(d)],
         "cuba_stage_max_diagonal": [vp, C.POINTER(d)],
         "cuba_stage_solve": [vp, d, C.POINTER(i), C.POINTER(i)],
@@ -124,6 +128,13 @@ def _problem_struct(prob):
     P = _Problem(prob.Pall, prob.numP, prob.Lall, prob.numL, _p(keep[0]), _p(keep[1]), _p(keep[2]), _p(keep[3]),
                  prob.E2, _p(keep[4]), _p(keep[5]), _p(keep[6]), prob.E3, _p(keep[7]), _p(keep[8]), _p(keep[9]))
     return P, keep
+
+
+def transfer_bytes():
+    """(h2d, d2h) bytes copied so far by this thread's engines"""
+    a, b = C.c_longlong(0), C.c_longlong(0)
+    _check(load_library().cuba_get_transfer_bytes(C.byref(a), C.byref(b)))
+    return a.value, b.value
 
 
 def build_structure_host(prob, rank=0, world=1):
@@ -194,6 +205,17 @@ class Engine:
     def set_state(self, q, t, Xw):
         q, t, Xw = (np.ascontiguousarray(a, dtype=np.float64) for a in (q, t, Xw))
         _check(self.L.cuba_engine_set_state(self.h, _p(q), _p(t), _p(Xw)))
+
+    def reset_state(self):
+        _check(self.L.cuba_engine_reset_state(self.h))
+
+    def stream_ptr(self):
+        s = C.c_void_p()
+        _check(self.L.cuba_engine_get_stream(self.h, C.byref(s)))
+        return s.value or 0
+
+    def flush_l2(self):
+        _check(self.L.cuba_engine_flush_l2(self.h))
 
     def optimize(self, niterations):
         stats = (_IterStat * max(niterations, 1))()

@@ -32,6 +32,8 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 		}                                                                                                   \
 	} while (0)
 
+static thread_local long long g_h2dBytes = 0, g_d2hBytes = 0;   // host<->device traffic of this thread's engines
+
 template <typename U>
 struct DBuf {
 	U* p = nullptr; size_t n = 0;
@@ -51,6 +53,7 @@ struct DBuf {
 	{
 		cudaError_t e = alloc(count);
 		if (e != cudaSuccess || !count) return e;
+		g_h2dBytes += (long long)(sizeof(U) * count);
 		return cudaMemcpyAsync(p, h, sizeof(U) * count, cudaMemcpyHostToDevice, s);
 	}
 	cudaError_t upload(const std::vector<U>& h, cudaStream_t s) { return upload(h.data(), h.size(), s); }
@@ -100,6 +103,9 @@ struct EngineBase {
 	virtual int set_problem(const cuba_problem* p) = 0;
 	virtual int set_state(const double* q, const double* t, const double* Xw) = 0;
 	virtual int get_sizes(cuba_sizes* out) const = 0;
+	virtual int reset_state() = 0;
+	virtual int get_stream(void** s) = 0;
+	virtual int flush_l2() = 0;
 	virtual int optimize(int niter, cuba_iter_stat* stats, int* nstats) = 0;
 	virtual int get_state(double* q, double* t, double* Xw) = 0;
 	virtual int get_chi2(double* out) = 0;
@@ -127,7 +133,7 @@ struct Engine : EngineBase {
 	int cur = 0;            // current state buffer
 	bool trialValid = false;
 	// state
-	DBuf<T> pose[2], Xw[2], cam;
+	DBuf<T> pose[2], Xw[2], cam, pose0, Xw0;
 	// edge streams
 	DBuf<T> e_mx, e_my, e_mz, e_om, p_mx, p_my, p_mz, p_om;
 	DBuf<int> e_ip, e_il, e_hpl, e_user, lmPtr, tileLm, hplLm, posePtr, p_il;
@@ -234,6 +240,7 @@ struct Engine : EngineBase {
 		}
 		for (int i = 0; i < Lall; i++) for (int k = 0; k < 3; k++) hx[4 * (size_t)i + k] = (T)p->Xw[3 * (size_t)i + k];
 		for (int b = 0; b < 2; b++) { CUDA_TRY(pose[b].upload(hp, stream)); CUDA_TRY(Xw[b].upload(hx, stream)); }
+		CUDA_TRY(pose0.upload(hp, stream)); CUDA_TRY(Xw0.upload(hx, stream));
 		CUDA_TRY(cam.upload(hc, stream));
 		// landmark-major edge stream
 		std::vector<T> mx(eL), my(eL), mz(eL), om(eL);
@@ -307,8 +314,30 @@ struct Engine : EngineBase {
 		}
 		for (int i = 0; i < S.Lall; i++) for (int k = 0; k < 3; k++) hx[4 * (size_t)i + k] = (T)X[3 * (size_t)i + k];
 		for (int b = 0; b < 2; b++) { CUDA_TRY(pose[b].upload(hp, stream)); CUDA_TRY(Xw[b].upload(hx, stream)); }
+		CUDA_TRY(pose0.upload(hp, stream)); CUDA_TRY(Xw0.upload(hx, stream));
 		CUDA_TRY(cudaStreamSynchronize(stream));
 		trialValid = false;
+		return CUBA_OK;
+	}
+
+	int reset_state() override
+	{
+		if (!haveProblem) return fail(CUBA_ERR_STATE, "reset_state before set_problem");
+		for (int b = 0; b < 2; b++) {
+			CUDA_TRY(cudaMemcpyAsync(pose[b].p, pose0.p, sizeof(T) * 8 * (size_t)S.Pall, cudaMemcpyDeviceToDevice, stream));
+			CUDA_TRY(cudaMemcpyAsync(Xw[b].p, Xw0.p, sizeof(T) * 4 * (size_t)S.Lall, cudaMemcpyDeviceToDevice, stream));
+		}
+		trialValid = false;
+		return CUBA_OK;
+	}
+	int get_stream(void** s) override { *s = (void*)stream; return CUBA_OK; }
+	int flush_l2() override
+	{
+		const size_t flushN = (size_t)40 << 20;
+		CUDA_TRY(flushBuf.alloc(flushN));
+		k_fill<<<numSMs * 8, 256, 0, stream>>>(flushBuf.p, flushN, 1.0);
+		launches++;
+		CUDA_TRY(cudaGetLastError());
 		return CUBA_OK;
 	}
 
@@ -365,6 +394,7 @@ struct Engine : EngineBase {
 	}
 	int fetchScalars()
 	{
+		g_d2hBytes += (long long)sizeof(Scalars);
 		CUDA_TRY(cudaMemcpyAsync(hScal, dScal.p, sizeof(Scalars), cudaMemcpyDeviceToHost, stream));
 		CUDA_TRY(cudaStreamSynchronize(stream));
 		return CUBA_OK;
@@ -625,6 +655,7 @@ struct Engine : EngineBase {
 	{
 		if (!haveProblem) return fail(CUBA_ERR_STATE, "get_state before set_problem");
 		std::vector<T> hp((size_t)S.Pall * 8), hx((size_t)S.Lall * 4);
+		g_d2hBytes += (long long)(sizeof(T) * (hp.size() + hx.size()));
 		CUDA_TRY(cudaMemcpyAsync(hp.data(), pose[cur].p, sizeof(T) * hp.size(), cudaMemcpyDeviceToHost, stream));
 		if (world > 1 && S.numL > 0) {
 			// gather the sharded landmarks: zero foreign entries, sum over ranks
@@ -658,6 +689,7 @@ struct Engine : EngineBase {
 			CUDA_TRY(cudaGetLastError());
 		}
 		if (world > 1) { int rc = allreduce(chiSq.p, (size_t)S.E, false); if (rc) return rc; }
+		g_d2hBytes += (long long)(sizeof(double) * (size_t)S.E);
 		CUDA_TRY(cudaMemcpyAsync(out, chiSq.p, sizeof(double) * (size_t)S.E, cudaMemcpyDeviceToHost, stream));
 		CUDA_TRY(cudaStreamSynchronize(stream));
 		return CUBA_OK;
@@ -856,11 +888,15 @@ int cuba_engine_set_state(cuba_engine* e, const double* q, const double* t, cons
 	if (!q || !t || !Xw) return fail(CUBA_ERR_INVALID, "set_state: null array");
 	return e->impl->set_state(q, t, Xw);
 }
+int cuba_engine_reset_state(cuba_engine* e) { ENGINE_OR_FAIL(e); return e->impl->reset_state(); }
+int cuba_engine_get_stream(cuba_engine* e, void** s) { ENGINE_OR_FAIL(e); if (!s) return fail(CUBA_ERR_INVALID, "null out"); return e->impl->get_stream(s); }
+int cuba_engine_flush_l2(cuba_engine* e) { ENGINE_OR_FAIL(e); return e->impl->flush_l2(); }
 int cuba_engine_get_sizes(const cuba_engine* e, cuba_sizes* out) { ENGINE_OR_FAIL(e); if (!out) return fail(CUBA_ERR_INVALID, "null out"); return e->impl->get_sizes(out); }
 int cuba_engine_optimize(cuba_engine* e, int niter, cuba_iter_stat* stats, int* nstats) { ENGINE_OR_FAIL(e); return e->impl->optimize(niter, stats, nstats); }
 int cuba_engine_get_state(cuba_engine* e, double* q, double* t, double* Xw) { ENGINE_OR_FAIL(e); return e->impl->get_state(q, t, Xw); }
 int cuba_engine_get_chi2(cuba_engine* e, double* per_edge) { ENGINE_OR_FAIL(e); if (!per_edge) return fail(CUBA_ERR_INVALID, "null out"); return e->impl->get_chi2(per_edge); }
 int cuba_engine_get_profile(cuba_engine* e, double* sec) { ENGINE_OR_FAIL(e); if (!sec) return fail(CUBA_ERR_INVALID, "null out"); return e->impl->get_profile(sec); }
+int cuba_get_transfer_bytes(long long* h2d, long long* d2h) { if (h2d) *h2d = g_h2dBytes; if (d2h) *d2h = g_d2hBytes; return CUBA_OK; }
 int cuba_engine_get_launch_count(cuba_engine* e, long long* count) { ENGINE_OR_FAIL(e); if (count) *count = e->impl->launches; return CUBA_OK; }
 
 int cuba_stage_linearize(cuba_engine* e, double* chi2) { ENGINE_OR_FAIL(e); return e->impl->stage_linearize(chi2); }

@@ -136,7 +136,15 @@ int cuba_engine_set_problem(cuba_engine* e, const cuba_problem* p);
 /* Replace only the estimate (q,t,Xw), keeping structure -- repeated optimize() on the same graph. */
 int cuba_engine_set_state(cuba_engine* e, const double* q, const double* t, const double* Xw);
 
+/* Restore the estimate last given by set_problem / set_state from its device-resident copy (no host
+ * traffic): lets a benchmark time optimize() repeatedly with all inputs already in HBM. */
+int cuba_engine_reset_state(cuba_engine* e);
+
 int cuba_engine_get_sizes(const cuba_engine* e, cuba_sizes* out);
+/* The CUDA stream (cudaStream_t) every kernel of this engine is launched on -- for CUDA-event timing. */
+int cuba_engine_get_stream(cuba_engine* e, void** stream);
+/* Overwrite a buffer larger than L2 on the engine's stream (benchmark hygiene between timed steps). */
+int cuba_engine_flush_l2(cuba_engine* e);
 
 /* optimize(niterations): stats[niterations]; *nstats = number of entries written (cpp:848-851). */
 int cuba_engine_optimize(cuba_engine* e, int niterations, cuba_iter_stat* stats, int* nstats);
@@ -149,6 +157,9 @@ int cuba_engine_get_chi2(cuba_engine* e, double* per_edge);
 int cuba_engine_get_profile(cuba_engine* e, double* seconds);
 /* number of kernels this library launched since create (for bench.py's gpu_launches) */
 int cuba_engine_get_launch_count(cuba_engine* e, long long* count);
+
+/* cumulative host->device / device->host bytes copied by this thread's engines (for bench.py's e2e record) */
+int cuba_get_transfer_bytes(long long* h2d, long long* d2h);
 
 /* ---- stage-wise entry points (used by optimize(); exported for stage parity tests) ---- */
 int cuba_stage_linearize(cuba_engine* e, double* chi2);
