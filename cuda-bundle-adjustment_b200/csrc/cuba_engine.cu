@@ -272,12 +272,12 @@ struct Engine : EngineBase {
 		CUDA_TRY(pr.alloc(6 * nP)); CUDA_TRY(pz.alloc(6 * nP)); CUDA_TRY(pq.alloc(6 * nP)); CUDA_TRY(pp0.alloc(6 * nP)); CUDA_TRY(pp1.alloc(6 * nP));
 		CUDA_TRY(Minv.alloc(36 * nP));
 		// landmarks outside this rank's shard keep zero Hll/bl/xl (they are never touched locally)
-		CUDA_TRY(cudaMemsetAsync(Hll.p, 0, sizeof(T) * 9 * (nL ? nL : 1), stream));
-		CUDA_TRY(cudaMemsetAsync(bl.p, 0, sizeof(T) * 3 * (nL ? nL : 1), stream));
-		CUDA_TRY(cudaMemsetAsync(xl.p, 0, sizeof(T) * 3 * (nL ? nL : 1), stream));
-		CUDA_TRY(cudaMemsetAsync(xp.p, 0, sizeof(T) * 6 * (nP ? nP : 1), stream));
-		CUDA_TRY(cudaMemsetAsync(Hpp.p, 0, sizeof(T) * 36 * (nP ? nP : 1), stream));
-		CUDA_TRY(cudaMemsetAsync(bp.p, 0, sizeof(T) * 6 * (nP ? nP : 1), stream));
+		if (nL) CUDA_TRY(cudaMemsetAsync(Hll.p, 0, sizeof(T) * 9 * nL, stream));
+		if (nL) CUDA_TRY(cudaMemsetAsync(bl.p, 0, sizeof(T) * 3 * nL, stream));
+		if (nL) CUDA_TRY(cudaMemsetAsync(xl.p, 0, sizeof(T) * 3 * nL, stream));
+		if (nP) CUDA_TRY(cudaMemsetAsync(xp.p, 0, sizeof(T) * 6 * nP, stream));
+		if (nP) CUDA_TRY(cudaMemsetAsync(Hpp.p, 0, sizeof(T) * 36 * nP, stream));
+		if (nP) CUDA_TRY(cudaMemsetAsync(bp.p, 0, sizeof(T) * 6 * nP, stream));
 		ntiles = (int)S.tileLm.size() - 1;
 		nPoseBlocks = (S.numP + RED_BLOCK - 1) / RED_BLOCK;
 		nChiBlocks = std::max(1, std::min((eL + RED_BLOCK - 1) / RED_BLOCK, numSMs * 8));
