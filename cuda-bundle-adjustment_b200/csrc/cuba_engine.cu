@@ -297,6 +297,7 @@ struct Engine : EngineBase {
 		}
 		CUDA_TRY(cudaStreamSynchronize(stream));
 		cur = 0; trialValid = false;
+		resolveProfile();   // drop the events of earlier problems
 		for (int i = 0; i < CUBA_PROF_NUM; i++) prof[i] = 0;
 		const auto t1 = std::chrono::steady_clock::now();
 		prof[CUBA_PROF_BUILD_STRUCTURE] += std::chrono::duration<double>(t1 - t0).count();

@@ -34,7 +34,7 @@ def test_stage_parity(pkg, oracle, problems, name, kernel):
     assert abs(chi - ochi) <= STAGE_TOL * ochi
     for nme, a, b in zip(("Hpp", "bp", "Hll", "bl", "Hpl"), eng.system(), o.system()):
         assert relerr(a, b) < STAGE_TOL, nme
-    md = eng.max_diagonal(); assert md == pytest.approx(o.max_diagonal(), rel=1e-14)
+    md = eng.max_diagonal(); assert md == pytest.approx(o.max_diagonal(), rel=1e-12)
     lam = 1e-5 * md
     iters, ok = eng.solve(lam); assert ok and o.solve(lam)
     for nme, a, b in zip(("Hsc", "bsc", "invHll"), eng.schur(), o.schur()):
