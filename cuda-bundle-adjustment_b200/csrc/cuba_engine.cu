@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -15,6 +16,7 @@
 
 #include "../../include/cuba_b200.h"
 #include "cuba_kernels.cuh"
+#include "cuba_pcg2.cuh"
 #include "cuba_structure.h"
 
 namespace cuba_b200 {
@@ -144,6 +146,13 @@ struct Engine : EngineBase {
 	DBuf<T> pr, pz, pq, pp0, pp1, Minv;
 	DBuf<double> pcgPartial;
 	int pcgGrid = 0;
+	// pcg v2 (cuba_pcg2.cuh)
+	DBuf<T> fHat, Linv, vR0, vR1, vS0, vS1, vW0, vW1, vP, vY;
+	DBuf<int> fLocal, ctaRow, needPtr, needCol;
+	DBuf<double> pcg2Partial;
+	DBuf<GridBar> gridBar;
+	int pcg2Grid = 0, pcg2Cap = 0, pcg2NeedMax = 0;
+	size_t pcg2Smem = 0;
 	// reductions
 	DBuf<double> chiPartial, scalePartialL, scalePartialP, chiSq;
 	DBuf<Scalars> dScal;
@@ -295,6 +304,7 @@ struct Engine : EngineBase {
 			pcgGrid = std::max(1, std::min(wantBlocks, numSMs * std::min(perSM, 2)));
 			CUDA_TRY(pcgPartial.alloc(2 * (size_t)pcgGrid));
 		}
+		if (S.numP > 0) { int rc = setup_pcg2(); if (rc) return rc; }
 		CUDA_TRY(cudaStreamSynchronize(stream));
 		cur = 0; trialValid = false;
 		resolveProfile();   // drop the events of earlier problems
@@ -500,8 +510,92 @@ struct Engine : EngineBase {
 		return CUBA_OK;
 	}
 
+	// Row partition, need lists and shared-memory budget of k_pcg2.
+	int setup_pcg2()
+	{
+		const int numP = S.numP;
+		int dev = 0, smemMax = 0;
+		CUDA_TRY(cudaGetDevice(&dev));
+		CUDA_TRY(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+		const size_t budget = (size_t)smemMax > 4096 ? (size_t)smemMax - 2048 : 0;   // leave room for the static arrays
+		const size_t matBytes = (size_t)S.nfull * (36 * sizeof(T) + 4);
+		int G = std::max((numP + 7) / 8, (int)((matBytes + budget - 1) / std::max<size_t>(budget, 1)));
+		G = std::max(1, std::min(G, std::min(numSMs, numP)));
+		// contiguous row ranges balanced by block count
+		std::vector<int> rows(G + 1, 0);
+		{
+			int r = 0;
+			for (int c = 0; c < G; c++) {
+				rows[c] = r;
+				const long long target = (long long)S.nfull * (c + 1) / G;
+				const int minRows = 1, remainingCtas = G - c - 1;
+				int end = r + minRows;
+				while (end < numP - remainingCtas && S.fRowPtr[end] < target) end++;
+				r = std::min(end, numP - remainingCtas);
+			}
+			rows[G] = numP;
+		}
+		std::vector<int> nptr(G + 1, 0), ncol, local(S.nfull, 0);
+		int needMax = 0, blkMax = 0;
+		std::vector<int> mark(numP, -1);
+		for (int c = 0; c < G; c++) {
+			std::vector<int> cols;
+			for (int n = S.fRowPtr[rows[c]]; n < S.fRowPtr[rows[c + 1]]; n++) {
+				const int j = S.fColInd[n];
+				if (mark[j] != c) { mark[j] = c; cols.push_back(j); }
+			}
+			std::sort(cols.begin(), cols.end());
+			nptr[c] = (int)ncol.size();
+			for (size_t k = 0; k < cols.size(); k++) ncol.push_back(cols[k]);
+			// local index of each block's column: binary search in the sorted list
+			for (int n = S.fRowPtr[rows[c]]; n < S.fRowPtr[rows[c + 1]]; n++)
+				local[n] = (int)(std::lower_bound(cols.begin(), cols.end(), S.fColInd[n]) - cols.begin());
+			needMax = std::max(needMax, (int)cols.size());
+			blkMax = std::max(blkMax, S.fRowPtr[rows[c + 1]] - S.fRowPtr[rows[c]]);
+		}
+		nptr[G] = (int)ncol.size();
+		const size_t needBytes = (size_t)needMax * 6 * sizeof(T);
+		size_t cap = budget > needBytes ? (budget - needBytes) / (36 * sizeof(T) + 4) : 0;
+		cap = std::min<size_t>(cap, (size_t)blkMax);
+		pcg2Grid = G; pcg2Cap = (int)cap; pcg2NeedMax = needMax;
+		pcg2Smem = (size_t)cap * 36 * sizeof(T) + needBytes + (size_t)cap * 4 + 16;
+		CUDA_TRY(cudaFuncSetAttribute(k_pcg2<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pcg2Smem));
+		int perSM = 0;
+		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_pcg2<T>, PCG2_BLOCK, pcg2Smem));
+		if (perSM < 1) return fail(CUBA_ERR_CUDA, "k_pcg2 cannot be resident with the requested shared memory");
+		CUDA_TRY(ctaRow.upload(rows, stream)); CUDA_TRY(needPtr.upload(nptr, stream)); CUDA_TRY(needCol.upload(ncol, stream));
+		CUDA_TRY(fLocal.upload(local, stream));
+		const size_t n6 = 6 * (size_t)numP;
+		CUDA_TRY(fHat.alloc(36 * (size_t)S.nfull)); CUDA_TRY(Linv.alloc(36 * (size_t)numP));
+		CUDA_TRY(vR0.alloc(n6)); CUDA_TRY(vR1.alloc(n6)); CUDA_TRY(vS0.alloc(n6)); CUDA_TRY(vS1.alloc(n6));
+		CUDA_TRY(vW0.alloc(n6)); CUDA_TRY(vW1.alloc(n6)); CUDA_TRY(vP.alloc(n6)); CUDA_TRY(vY.alloc(n6));
+		CUDA_TRY(pcg2Partial.alloc(4 * (size_t)G));
+		CUDA_TRY(gridBar.alloc(1));
+		CUDA_TRY(cudaMemsetAsync(gridBar.p, 0, sizeof(GridBar), stream));
+		return CUBA_OK;
+	}
+
+	int launch_pcg2()
+	{
+		ProfScope ps(this, CUBA_PROF_DECOMP_NUMERICAL);
+		Pcg2Args<T> a;
+		a.fRowPtr = fRowPtr; a.fColInd = fColInd; a.fLocal = fLocal; a.fVal = fVal; a.fHat = fHat;
+		a.ctaRow = ctaRow; a.needPtr = needPtr; a.needCol = needCol; a.b = bsc; a.numP = S.numP; a.Linv = Linv;
+		a.R0 = vR0; a.R1 = vR1; a.S0 = vS0; a.S1 = vS1; a.W0 = vW0; a.W1 = vW1; a.P = vP; a.Y = vY; a.x = xp;
+		a.partial = pcg2Partial; a.bar = gridBar; a.capBlocks = pcg2Cap; a.needMax = pcg2NeedMax;
+		a.maxIters = cfg.pcg_max_iters > 0 ? cfg.pcg_max_iters : std::max(200, 40 * S.numP);
+		const double tol = cfg.pcg_tol > 0 ? cfg.pcg_tol : (sizeof(T) == 8 ? 1e-13 : 1e-6);
+		a.tol2 = tol * tol;
+		a.status = &dScal.p->pcg;
+		void* args[] = { (void*)&a };
+		CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_pcg2<T>, dim3(pcg2Grid), dim3(PCG2_BLOCK), args, pcg2Smem, stream));
+		launches++;
+		return CUBA_OK;
+	}
+
 	int launch_pcg()
 	{
+		if (cfg.reserved[0] != 1) return launch_pcg2();   // reserved[0] == 1 selects the first-generation kernel
 		ProfScope ps(this, CUBA_PROF_DECOMP_NUMERICAL);
 		PcgArgs<T> a;
 		a.fRowPtr = fRowPtr; a.fColInd = fColInd; a.fVal = fVal; a.b = bsc; a.numP = S.numP;

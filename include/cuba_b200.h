@@ -73,7 +73,8 @@ typedef struct cuba_config {
 	int pcg_max_iters;     /* <=0: default                                         */
 	double pcg_tol;        /* stop when sqrt(r'z / r0'z0) <= pcg_tol; <=0: default 1e-13           */
 	int deterministic;     /* 1 (default): fixed-order reductions, bit-reproducible run to run     */
-	int reserved[7];
+	int reserved[7];       /* reserved[0]: PCG kernel, 0 = k_pcg2 (shared-memory resident, one barrier per
+	                          iteration; default), 1 = k_pcg (first generation, two cooperative-groups syncs) */
 } cuba_config;
 
 /* Flat problem: exactly what CudaBlockSolver::initialize produces (cpp:115-261).

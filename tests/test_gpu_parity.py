@@ -143,6 +143,21 @@ def test_against_compiled_reference(pkg, problems, name, kernel):
     eng.close()
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+def test_both_pcg_kernels_solve_the_same_system(pkg, oracle, problems, variant):
+    """k_pcg2 (shared-memory resident, single barrier) and k_pcg (first generation) against the direct solve"""
+    prob = problems("kitti07_shaped"); rk = KERNELS["huber"]
+    eng = make_engine(pkg, prob, rk, pcg_variant=variant)
+    o = oracle.Oracle(prob, *rk)
+    eng.linearize(); o.compute_errors(); o.build_system()
+    for lam in (1e3, 1.0, 1e-2):
+        iters, ok = eng.solve(lam); assert ok and iters > 0
+        assert o.solve(lam)
+        for nme, a, b in zip(("xp", "xl"), eng.delta(), o.delta()):
+            assert relerr(a, b) < TOL, (nme, lam, iters)
+    eng.close()
+
+
 def _variant(pkg, base, **kw):
     from test_structure import _variant as v
     return v(pkg, base, **kw)
