@@ -151,7 +151,7 @@ struct Engine : EngineBase {
 	DBuf<int> fLocal, ctaRow, needPtr, needCol;
 	DBuf<double> pcg2Partial;
 	DBuf<GridBar> gridBar;
-	int pcg2Grid = 0, pcg2Cap = 0, pcg2NeedMax = 0;
+	int pcg2Grid = 0, pcg2Cap = 0, pcg2NeedMax = 0, pcg2MaxRows = 0;
 	size_t pcg2Smem = 0;
 	// reductions
 	DBuf<double> chiPartial, scalePartialL, scalePartialP, chiSq;
@@ -536,7 +536,7 @@ struct Engine : EngineBase {
 			rows[G] = numP;
 		}
 		std::vector<int> nptr(G + 1, 0), ncol, local(S.nfull, 0);
-		int needMax = 0, blkMax = 0;
+		int needMax = 0, blkMax = 0, maxRows = 0;
 		std::vector<int> mark(numP, -1);
 		for (int c = 0; c < G; c++) {
 			std::vector<int> cols;
@@ -550,14 +550,18 @@ struct Engine : EngineBase {
 			// local index of each block's column: binary search in the sorted list
 			for (int n = S.fRowPtr[rows[c]]; n < S.fRowPtr[rows[c + 1]]; n++)
 				local[n] = (int)(std::lower_bound(cols.begin(), cols.end(), S.fColInd[n]) - cols.begin());
+			// the diagonal block of each own row is encoded as -1-loc (A^_ii = I is applied implicitly)
+			for (int r = rows[c]; r < rows[c + 1]; r++)
+				for (int n = S.fRowPtr[r]; n < S.fRowPtr[r + 1]; n++) if (S.fColInd[n] == r) local[n] = -1 - local[n];
+			maxRows = std::max(maxRows, rows[c + 1] - rows[c]);
 			needMax = std::max(needMax, (int)cols.size());
 			blkMax = std::max(blkMax, S.fRowPtr[rows[c + 1]] - S.fRowPtr[rows[c]]);
 		}
 		nptr[G] = (int)ncol.size();
-		const size_t needBytes = (size_t)needMax * 6 * sizeof(T);
+		const size_t needBytes = (size_t)needMax * (6 * sizeof(T) + 4) + ((size_t)maxRows + 1) * 4;
 		size_t cap = budget > needBytes ? (budget - needBytes) / (36 * sizeof(T) + 4) : 0;
 		cap = std::min<size_t>(cap, (size_t)blkMax);
-		pcg2Grid = G; pcg2Cap = (int)cap; pcg2NeedMax = needMax;
+		pcg2Grid = G; pcg2Cap = (int)cap; pcg2NeedMax = needMax; pcg2MaxRows = maxRows;
 		pcg2Smem = (size_t)cap * 36 * sizeof(T) + needBytes + (size_t)cap * 4 + 16;
 		CUDA_TRY(cudaFuncSetAttribute(k_pcg2<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pcg2Smem));
 		int perSM = 0;
@@ -582,7 +586,7 @@ struct Engine : EngineBase {
 		a.fRowPtr = fRowPtr; a.fColInd = fColInd; a.fLocal = fLocal; a.fVal = fVal; a.fHat = fHat;
 		a.ctaRow = ctaRow; a.needPtr = needPtr; a.needCol = needCol; a.b = bsc; a.numP = S.numP; a.Linv = Linv;
 		a.R0 = vR0; a.R1 = vR1; a.S0 = vS0; a.S1 = vS1; a.W0 = vW0; a.W1 = vW1; a.P = vP; a.Y = vY; a.x = xp;
-		a.partial = pcg2Partial; a.bar = gridBar; a.capBlocks = pcg2Cap; a.needMax = pcg2NeedMax;
+		a.partial = pcg2Partial; a.bar = gridBar; a.capBlocks = pcg2Cap; a.needMax = pcg2NeedMax; a.maxRows = pcg2MaxRows;
 		a.maxIters = cfg.pcg_max_iters > 0 ? cfg.pcg_max_iters : std::max(200, 40 * S.numP);
 		const double tol = cfg.pcg_tol > 0 ? cfg.pcg_tol : (sizeof(T) == 8 ? 1e-13 : 1e-6);
 		a.tol2 = tol * tol;

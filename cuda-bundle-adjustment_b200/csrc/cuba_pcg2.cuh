@@ -29,22 +29,31 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p)
 	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
 	return v;
 }
+__device__ __forceinline__ unsigned int atom_add_acqrel_u32(unsigned int* p, unsigned int v)
+{
+	unsigned int old;
+	asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+	return old;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v)
+{
+	asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
 
-// All CTAs of a cooperative launch.  gen is the caller's local generation counter.
+// Sense-reversing barrier over all CTAs of a cooperative launch: one acq_rel atomic per CTA, acquire spin.
+// bar.sync orders the CTA's earlier writes before thread 0's release (PTX causality order), so no separate
+// __threadfence() is needed; data written by other CTAs must afterwards be read with __ldcg (L1 may be stale).
 __device__ __forceinline__ void grid_barrier(GridBar* b, unsigned int nblocks, unsigned int& gen)
 {
 	__syncthreads();
 	if (threadIdx.x == 0) {
-		__threadfence();
-		const unsigned int prev = atomicAdd(&b->count, 1u);
+		const unsigned int prev = atom_add_acqrel_u32(&b->count, 1u);
 		if (prev == nblocks - 1) {
 			b->count = 0;
-			__threadfence();
-			atomicExch(&b->gen, gen + 1);
+			st_release_u32(&b->gen, gen + 1);
 		} else {
 			while (ld_acquire_u32(&b->gen) == gen) { }
 		}
-		__threadfence();
 	}
 	gen++;
 	__syncthreads();
@@ -66,6 +75,7 @@ struct Pcg2Args {
 	GridBar* bar;
 	int capBlocks;          // blocks of A^ a CTA can keep in shared memory
 	int needMax;            // max need-list length over CTAs
+	int maxRows;            // max rows per CTA
 	int maxIters; double tol2;
 	PcgStatus* status;
 };
@@ -104,25 +114,26 @@ template <typename T>
 __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg2(const Pcg2Args<T> a)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	T* s_blk = reinterpret_cast<T*>(smem_raw);                        // [capBlocks][36]
-	T* s_rj = s_blk + (size_t)a.capBlocks * 36;                       // [needMax][6]
-	int* s_loc = reinterpret_cast<int*>(s_rj + (size_t)a.needMax * 6); // [capBlocks] local column of cached block
+	T* s_blk = reinterpret_cast<T*>(smem_raw);                          // [capBlocks][36]  cached A^ blocks
+	T* s_rj = s_blk + (size_t)a.capBlocks * 36;                         // [needMax][6]     gathered residual
+	int* s_loc = reinterpret_cast<int*>(s_rj + (size_t)a.needMax * 6);  // [capBlocks]      need index of a block's column (<0: diagonal)
+	int* s_rowPtr = s_loc + a.capBlocks;                                // [maxRows+1]      local block offsets of the own rows
+	int* s_need = s_rowPtr + a.maxRows + 1;                             // [needMax]        global column of each need entry
 	__shared__ double s_red[PCG2_BLOCK / 32][2];
 	__shared__ double s_bc[2];
+	__shared__ unsigned int s_gen;
 
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const int G = gridDim.x, cta = blockIdx.x;
-	const int row0 = a.ctaRow[cta], row1 = a.ctaRow[cta + 1];
+	const int row0 = a.ctaRow[cta], row1 = a.ctaRow[cta + 1], nrows = row1 - row0;
 	const int need0 = a.needPtr[cta], nneed = a.needPtr[cta + 1] - need0;
 	const int blk0 = a.fRowPtr[row0], nblkCta = a.fRowPtr[row1] - blk0;
 	const int ncached = nblkCta < a.capBlocks ? nblkCta : a.capBlocks;
-	unsigned int gen = 0;
-	if (tid == 0) gen = ld_acquire_u32(&a.bar->gen);
-	gen = __shfl_sync(0xffffffffu, gen, 0);
-	__shared__ unsigned int s_gen;
-	if (tid == 0) s_gen = gen;
+	if (tid == 0) s_gen = ld_acquire_u32(&a.bar->gen);
+	for (int i = tid; i <= nrows; i += PCG2_BLOCK) s_rowPtr[i] = a.fRowPtr[row0 + i] - blk0;
+	for (int i = tid; i < nneed; i += PCG2_BLOCK) s_need[i] = a.needCol[need0 + i];
 	__syncthreads();
-	gen = s_gen;
+	unsigned int gen = s_gen;
 
 	// ---- S1: factor the diagonal blocks of the own rows, b^ = L^-1 b, initial vectors --------------
 	int bad = 0;
@@ -147,7 +158,7 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg2(const Pcg2Args<T> a)
 	grid_barrier(a.bar, G, gen);
 	double nbad = 0;
 	if (tid < 32) {
-		for (int i = tid; i < G; i += 32) nbad += a.partial[(size_t)i * 2];
+		for (int i = tid; i < G; i += 32) nbad += __ldcg(a.partial + (size_t)i * 2);
 		nbad = warp_sum(nbad);
 		if (tid == 0) s_bc[0] = nbad;
 	}
@@ -158,26 +169,23 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg2(const Pcg2Args<T> a)
 	// ---- S2: A^_ij = L_i^-1 S_ij L_j^-T for the own rows -> shared memory (+ global for the overflow) ----
 	for (int n = tid; n < nblkCta; n += PCG2_BLOCK) {
 		const int g = blk0 + n;
-		// row of block g: binary search in fRowPtr[row0..row1]
-		int lo = row0, hi = row1 - 1;
-		while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (a.fRowPtr[mid] <= g) lo = mid; else hi = mid - 1; }
-		const int i = lo, j = a.fColInd[g];
+		int lo = 0, hi = nrows - 1;       // row of block n: largest i with s_rowPtr[i] <= n
+		while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_rowPtr[mid] <= n) lo = mid; else hi = mid - 1; }
+		const int i = row0 + lo, j = a.fColInd[g];
 		const T* B = a.fVal + 36 * (size_t)g;
 		const T* Li = a.Linv + 36 * (size_t)i;
 		const T* Lj = a.Linv + 36 * (size_t)j;
 		T tmp[36], out[36];
-		// tmp = Li * B  (Li lower triangular)
 		for (int c = 0; c < 6; c++)
 			for (int r = 0; r < 6; r++) {
 				T s = T(0);
 				for (int k = 0; k <= r; k++) s += Li[k * 6 + r] * B[c * 6 + k];
 				tmp[c * 6 + r] = s;
 			}
-		// out = tmp * Lj^T : out(r,c) = sum_k tmp(r,k) Lj(c,k), k <= c
 		for (int c = 0; c < 6; c++)
 			for (int r = 0; r < 6; r++) {
 				T s = T(0);
-				for (int k = 0; k <= c; k++) s += tmp[k * 6 + r] * Lj[k * 6 + c];
+				for (int k = 0; k <= c; k++) s += tmp[k * 6 + r] * __ldcg(Lj + k * 6 + c);
 				out[c * 6 + r] = s;
 			}
 		if (n < ncached) {
@@ -193,33 +201,66 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg2(const Pcg2Args<T> a)
 	double gamma = 0, gamma0 = 0, alpha = 0, beta = 0;
 	if (nbad > 0) status = 2;
 	else {
-		// pass k = -1 computes w0 = A^ r0 and the first inner products; pass k >= 0 is iteration k
-		for (int k = -1; k < a.maxIters; k++) {
-			const int par = (k + 2) & 1;                       // parity of k (k=-1 -> 1)
-			const T* Rin = (par == 0) ? a.R0 : a.R1;           // r_k   (for k=-1: unused, r0 is in R0)
+		// pass k = -1 computes w0 = A^ r0 and the first inner products; pass k >= 0 is CG iteration k.
+		// The inner products of pass k-1 are read at the top of pass k, together with the vector prefetch,
+		// so one iteration costs one grid barrier and one round of L2 reads.
+		for (int k = -1;; k++) {
+			const int par = (k + 2) & 1;
+			const T* Rin = (par == 0) ? a.R0 : a.R1;           // r_k
 			T* Rout = (par == 0) ? a.R1 : a.R0;                // r_{k+1}
 			const T* Win = (par == 0) ? a.W0 : a.W1;           // w_k
 			T* Wout = (par == 0) ? a.W1 : a.W0;                // w_{k+1}
 			const T* Sprev = (par == 0) ? a.S1 : a.S0;         // s_{k-1}
 			T* Scur = (par == 0) ? a.S0 : a.S1;                // s_k
-			// ---- gather: updated residual of every needed column into shared memory ----
-			for (int wi = tid; wi < nneed * 6; wi += PCG2_BLOCK) {
-				const int c = wi / 6, comp = wi - 6 * c;
-				const size_t o = 6 * (size_t)a.needCol[need0 + c] + comp;
-				T rnew;
-				if (k < 0) rnew = a.R0[o];
-				else {
-					const T s = Win[o] + (T)beta * Sprev[o];
-					rnew = Rin[o] - (T)alpha * s;
-				}
-				s_rj[wi] = rnew;
+			// ---- prefetch the first gather item of every thread (independent of alpha/beta) ----
+			T g_r = T(0), g_w = T(0), g_s = T(0);
+			if (tid < nneed * 6) {
+				const int c = tid / 6, comp = tid - 6 * c;
+				const size_t o = 6 * (size_t)s_need[c] + comp;
+				if (k < 0) g_r = __ldcg(a.R0 + o);
+				else { g_r = __ldcg(Rin + o); g_w = __ldcg(Win + o); g_s = __ldcg(Sprev + o); }
 			}
-			// ---- owners: p, x, s, r updates for the own rows ----
+			// ---- scalars of this pass from the partial sums of the previous one ----
 			if (k >= 0) {
-				for (int wi = tid; wi < (row1 - row0) * 6; wi += PCG2_BLOCK) {
+				if (tid < 32) {
+					double g2 = 0, d2 = 0;
+					const double* src = a.partial + (size_t)(1 - par) * G * 2;   // written in pass k-1
+					for (int i = tid; i < G; i += 32) { g2 += __ldcg(src + 2 * i); d2 += __ldcg(src + 2 * i + 1); }
+					g2 = warp_sum(g2); d2 = warp_sum(d2);
+					if (tid == 0) { s_bc[0] = g2; s_bc[1] = d2; }
+				}
+				__syncthreads();
+				const double gnew = s_bc[0], delta = s_bc[1];
+				if (!(gnew == gnew) || !(delta == delta)) { status = 2; break; }
+				if (k == 0) {
+					gamma0 = gamma = gnew;
+					if (gamma0 <= 0) { status = 0; break; }
+					if (!(delta > 0)) { status = 2; break; }
+					alpha = gamma / delta; beta = 0;
+				} else {
+					it = k;
+					if (gnew <= a.tol2 * gamma0) { gamma = gnew; status = 0; break; }
+					beta = gnew / gamma;
+					const double den = delta - beta * gnew / alpha;
+					gamma = gnew;
+					if (!(den > 0)) { status = 2; break; }
+					alpha = gnew / den;
+				}
+				if (k >= a.maxIters) { status = 1; break; }
+			}
+			// ---- gather: updated residual r_{k+1} of every needed column into shared memory ----
+			if (tid < nneed * 6) s_rj[tid] = (k < 0) ? g_r : g_r - (T)alpha * (g_w + (T)beta * g_s);
+			for (int wi = tid + PCG2_BLOCK; wi < nneed * 6; wi += PCG2_BLOCK) {
+				const int c = wi / 6, comp = wi - 6 * c;
+				const size_t o = 6 * (size_t)s_need[c] + comp;
+				s_rj[wi] = (k < 0) ? __ldcg(a.R0 + o) : __ldcg(Rin + o) - (T)alpha * (__ldcg(Win + o) + (T)beta * __ldcg(Sprev + o));
+			}
+			// ---- owners: p, y, s, r updates for the own rows ----
+			if (k >= 0) {
+				for (int wi = tid; wi < nrows * 6; wi += PCG2_BLOCK) {
 					const size_t o = 6 * (size_t)row0 + wi;
-					const T rk = Rin[o];
-					const T s = Win[o] + (T)beta * Sprev[o];
+					const T rk = __ldcg(Rin + o);
+					const T s = __ldcg(Win + o) + (T)beta * __ldcg(Sprev + o);
 					const T p = rk + (T)beta * a.P[o];
 					a.P[o] = p;
 					a.Y[o] += (T)alpha * p;
@@ -230,15 +271,14 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg2(const Pcg2Args<T> a)
 			__syncthreads();
 			// ---- w_{k+1} = A^ r_{k+1} for the own rows (warp per row), partial gamma', delta ----
 			double pg = 0, pd = 0;
-			for (int i = row0 + wid; i < row1; i += PCG2_BLOCK / 32) {
+			for (int li = wid; li < nrows; li += PCG2_BLOCK / 32) {
 				T acc[6] = { T(0), T(0), T(0), T(0), T(0), T(0) };
-				const int n0 = a.fRowPtr[i] - blk0, n1 = a.fRowPtr[i + 1] - blk0;
+				const int n0 = s_rowPtr[li], n1 = s_rowPtr[li + 1];
 				int selfLoc = -1;
 				for (int n = n0 + lane; n < n1; n += 32) {
 					const bool cached = n < ncached;
 					const int loc = cached ? s_loc[n] : a.fLocal[blk0 + n];
-					const int j = a.needCol[need0 + loc];
-					if (j == i) { selfLoc = loc; continue; }
+					if (loc < 0) { selfLoc = -1 - loc; continue; }
 					const T* B = cached ? (s_blk + 36 * (size_t)n) : (a.fHat + 36 * (size_t)(blk0 + n));
 					const T* rj = s_rj + 6 * (size_t)loc;
 #pragma unroll
@@ -250,7 +290,6 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg2(const Pcg2Args<T> a)
 				}
 #pragma unroll
 				for (int c = 0; c < 6; c++) acc[c] = warp_sum(acc[c]);
-				// the lane that met the diagonal block knows the local index of the own row
 				selfLoc = __reduce_max_sync(0xffffffffu, selfLoc);
 				if (lane < 6) {
 					T wv = acc[0];
@@ -258,51 +297,26 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg2(const Pcg2Args<T> a)
 					for (int c = 1; c < 6; c++) if (lane == c) wv = acc[c];
 					const T ri = s_rj[6 * (size_t)selfLoc + lane];
 					wv += ri;                                   // A^_ii = I
-					Wout[6 * (size_t)i + lane] = wv;
+					Wout[6 * (size_t)(row0 + li) + lane] = wv;
 					pg += (double)ri * (double)ri;
 					pd += (double)wv * (double)ri;
 				}
 			}
-			// ---- reduce the two inner products behind one grid barrier ----
+			// ---- publish the two inner products, one grid barrier ----
 			pg = warp_sum(pg); pd = warp_sum(pd);
 			if (lane == 0) { s_red[wid][0] = pg; s_red[wid][1] = pd; }
 			__syncthreads();
 			if (tid == 0) {
 				double g2 = 0, d2 = 0;
 				for (int w = 0; w < PCG2_BLOCK / 32; w++) { g2 += s_red[w][0]; d2 += s_red[w][1]; }
-				double* dst = a.partial + ((size_t)(par) * G + cta) * 2;
+				double* dst = a.partial + ((size_t)par * G + cta) * 2;
 				dst[0] = g2; dst[1] = d2;
 			}
 			grid_barrier(a.bar, G, gen);
-			if (tid < 32) {
-				double g2 = 0, d2 = 0;
-				const double* src = a.partial + (size_t)par * G * 2;
-				for (int i = tid; i < G; i += 32) { g2 += src[2 * i]; d2 += src[2 * i + 1]; }
-				g2 = warp_sum(g2); d2 = warp_sum(d2);
-				if (tid == 0) { s_bc[0] = g2; s_bc[1] = d2; }
-			}
-			__syncthreads();
-			const double gnew = s_bc[0], delta = s_bc[1];
-			__syncthreads();
-			if (!(gnew == gnew) || !(delta == delta)) { status = 2; break; }
-			if (k < 0) {
-				gamma0 = gamma = gnew;
-				if (gamma0 <= 0) { status = 0; break; }
-				if (!(delta > 0)) { status = 2; break; }
-				alpha = gamma / delta; beta = 0;
-			} else {
-				it = k + 1;
-				if (gnew <= a.tol2 * gamma0) { gamma = gnew; status = 0; break; }
-				beta = gnew / gamma;
-				const double den = delta - beta * gnew / alpha;
-				if (!(den > 0)) { gamma = gnew; status = 2; break; }
-				alpha = gnew / den;
-				gamma = gnew;
-			}
 		}
 	}
 	// ---- x = L^-T y for the own rows ----
-	for (int wi = tid; wi < (row1 - row0) * 6; wi += PCG2_BLOCK) {
+	for (int wi = tid; wi < nrows * 6; wi += PCG2_BLOCK) {
 		const int i = row0 + wi / 6, r = wi % 6;
 		const T* Li = a.Linv + 36 * (size_t)i;
 		T s = T(0);
