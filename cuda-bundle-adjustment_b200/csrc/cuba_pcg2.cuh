@@ -114,7 +114,8 @@ template <typename T>
 __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg2(const Pcg2Args<T> a)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	T* s_blk = reinterpret_cast<T*>(smem_raw);                          // [capBlocks][36]  cached A^ blocks
+	T* s_blk = reinterpret_cast<T*>(smem_raw);                          // [36][capBlocks]  cached A^ blocks, element-major:
+	                                                                    // lane-per-block reads are bank-conflict free
 	T* s_rj = s_blk + (size_t)a.capBlocks * 36;                         // [needMax][6]     gathered residual
 	int* s_loc = reinterpret_cast<int*>(s_rj + (size_t)a.needMax * 6);  // [capBlocks]      need index of a block's column (<0: diagonal)
 	int* s_rowPtr = s_loc + a.capBlocks;                                // [maxRows+1]      local block offsets of the own rows
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg2(const Pcg2Args<T> a)
 				out[c * 6 + r] = s;
 			}
 		if (n < ncached) {
-			for (int e = 0; e < 36; e++) s_blk[36 * (size_t)n + e] = out[e];
+			for (int e = 0; e < 36; e++) s_blk[(size_t)e * a.capBlocks + n] = out[e];
 			s_loc[n] = a.fLocal[g];
 		} else {
 			for (int e = 0; e < 36; e++) a.fHat[36 * (size_t)g + e] = out[e];
@@ -279,13 +280,24 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg2(const Pcg2Args<T> a)
 					const bool cached = n < ncached;
 					const int loc = cached ? s_loc[n] : a.fLocal[blk0 + n];
 					if (loc < 0) { selfLoc = -1 - loc; continue; }
-					const T* B = cached ? (s_blk + 36 * (size_t)n) : (a.fHat + 36 * (size_t)(blk0 + n));
 					const T* rj = s_rj + 6 * (size_t)loc;
+					if (cached) {
+						const T* B = s_blk + n;
+						const size_t st = (size_t)a.capBlocks;
 #pragma unroll
-					for (int c = 0; c < 6; c++) {
-						const T rc = rj[c];
+						for (int c = 0; c < 6; c++) {
+							const T rc = rj[c];
 #pragma unroll
-						for (int r = 0; r < 6; r++) acc[r] += B[c * 6 + r] * rc;
+							for (int r = 0; r < 6; r++) acc[r] += B[(c * 6 + r) * st] * rc;
+						}
+					} else {
+						const T* B = a.fHat + 36 * (size_t)(blk0 + n);
+#pragma unroll
+						for (int c = 0; c < 6; c++) {
+							const T rc = rj[c];
+#pragma unroll
+							for (int r = 0; r < 6; r++) acc[r] += B[c * 6 + r] * rc;
+						}
 					}
 				}
 #pragma unroll
