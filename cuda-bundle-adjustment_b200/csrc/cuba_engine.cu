@@ -18,6 +18,7 @@
 #include "cuba_kernels.cuh"
 #include "cuba_pcg2.cuh"
 #include "cuba_structure.h"
+#include "cuba_structure_gpu.cuh"
 
 namespace cuba_b200 {
 
@@ -38,18 +39,19 @@ static thread_local long long g_h2dBytes = 0, g_d2hBytes = 0;   // host<->device
 
 template <typename U>
 struct DBuf {
-	U* p = nullptr; size_t n = 0;
+	U* p = nullptr; size_t n = 0, cap = 0;
 	DBuf() {}
 	DBuf(const DBuf&) = delete;
 	DBuf& operator=(const DBuf&) = delete;
 	~DBuf() { release(); }
-	void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+	void release() { if (p) cudaFree(p); p = nullptr; n = 0; cap = 0; }
+	// grow-only: re-initialising an engine with a problem of the same (or smaller) size allocates nothing
 	cudaError_t alloc(size_t count)
 	{
-		if (count == n && p) return cudaSuccess;
+		if (p && count <= cap) { n = count; return cudaSuccess; }
 		release();
-		n = count;
-		return cudaMalloc((void**)&p, sizeof(U) * (count ? count : 1));
+		n = count; cap = count ? count : 1;
+		return cudaMalloc((void**)&p, sizeof(U) * cap);
 	}
 	cudaError_t upload(const U* h, size_t count, cudaStream_t s)
 	{
@@ -167,6 +169,7 @@ struct Engine : EngineBase {
 		for (auto& pe : profEvents) { cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second); }
 		for (auto ev : eventPool) cudaEventDestroy(ev);
 		if (hScal) cudaFreeHost(hScal);
+		if (hMeta) cudaFreeHost(hMeta);
 		if (stream) cudaStreamDestroy(stream);
 		if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
 	}
@@ -231,27 +234,62 @@ struct Engine : EngineBase {
 	}
 
 	// ---- problem upload -------------------------------------------------------------------------------
+	// ---- problem upload ----------------------------------------------------------------------------
+	int upload_state(const double* q, const double* t, const double* c, const double* X)
+	{
+		const int Pall = S.Pall, Lall = S.Lall;
+		std::vector<T> hp((size_t)Pall * 8, T(0)), hx((size_t)Lall * 4, T(0));
+		for (int i = 0; i < Pall; i++) {
+			for (int k = 0; k < 4; k++) hp[8 * (size_t)i + k] = (T)q[4 * (size_t)i + k];
+			for (int k = 0; k < 3; k++) hp[8 * (size_t)i + 4 + k] = (T)t[3 * (size_t)i + k];
+		}
+		for (int i = 0; i < Lall; i++) for (int k = 0; k < 3; k++) hx[4 * (size_t)i + k] = (T)X[3 * (size_t)i + k];
+		CUDA_TRY(pose0.upload(hp, stream)); CUDA_TRY(Xw0.upload(hx, stream));
+		for (int b = 0; b < 2; b++) {
+			CUDA_TRY(pose[b].alloc(hp.size())); CUDA_TRY(Xw[b].alloc(hx.size()));
+			if (!hp.empty()) CUDA_TRY(cudaMemcpyAsync(pose[b].p, pose0.p, sizeof(T) * hp.size(), cudaMemcpyDeviceToDevice, stream));
+			if (!hx.empty()) CUDA_TRY(cudaMemcpyAsync(Xw[b].p, Xw0.p, sizeof(T) * hx.size(), cudaMemcpyDeviceToDevice, stream));
+		}
+		if (c) {
+			std::vector<T> hc((size_t)Pall * 8, T(0));
+			for (int i = 0; i < Pall; i++) for (int k = 0; k < 5; k++) hc[8 * (size_t)i + k] = (T)c[5 * (size_t)i + k];
+			CUDA_TRY(cam.upload(hc, stream));
+		}
+		// pageable host staging buffers must outlive the asynchronous copies
+		CUDA_TRY(cudaStreamSynchronize(stream));
+		return CUBA_OK;
+	}
+
 	int set_problem(const cuba_problem* p) override
 	{
 		if (!p) return fail(CUBA_ERR_INVALID, "set_problem: null problem");
+		if (p->Pall < 0 || p->Lall < 0 || p->numP < 0 || p->numL < 0 || p->numP > p->Pall || p->numL > p->Lall || p->E2 < 0 || p->E3 < 0)
+			return fail(CUBA_ERR_INVALID, "set_problem: invalid sizes");
 		const auto t0 = std::chrono::steady_clock::now();
+		haveProblem = false;
+		hostStructureValid = false;
+		int rc = (cfg.reserved[1] == 1) ? build_on_host(p) : build_on_gpu(p);
+		if (rc) return rc;
+		rc = upload_state(p->q, p->t, p->cam, p->Xw); if (rc) return rc;
+		rc = alloc_system(); if (rc) return rc;
+		CUDA_TRY(cudaStreamSynchronize(stream));
+		cur = 0; trialValid = false;
+		resolveProfile();   // drop the events of earlier problems
+		for (int i = 0; i < CUBA_PROF_NUM; i++) prof[i] = 0;
+		const auto t1 = std::chrono::steady_clock::now();
+		prof[CUBA_PROF_BUILD_STRUCTURE] += std::chrono::duration<double>(t1 - t0).count();
+		haveProblem = true;
+		return CUBA_OK;
+	}
+
+	// host structure builder (cuba_structure.cpp): reference path for the GPU builder, cfg.reserved[1] == 1
+	int build_on_host(const cuba_problem* p)
+	{
 		const char* err = "";
 		if (!build_structure(p->Pall, p->numP, p->Lall, p->numL, p->E2, p->idx2, p->E3, p->idx3, rank, world, TILE, S, &err))
 			return fail(CUBA_ERR_INVALID, err);
-		haveProblem = false;
-		const int Pall = S.Pall, Lall = S.Lall, eL = S.eLocal;
-		// state + cameras (narrowed to T at this boundary like the reference's ScalarCast, cpp:54-69)
-		std::vector<T> hp((size_t)Pall * 8, T(0)), hc((size_t)Pall * 8, T(0)), hx((size_t)Lall * 4, T(0));
-		for (int i = 0; i < Pall; i++) {
-			for (int k = 0; k < 4; k++) hp[8 * (size_t)i + k] = (T)p->q[4 * (size_t)i + k];
-			for (int k = 0; k < 3; k++) hp[8 * (size_t)i + 4 + k] = (T)p->t[3 * (size_t)i + k];
-			for (int k = 0; k < 5; k++) hc[8 * (size_t)i + k] = (T)p->cam[5 * (size_t)i + k];
-		}
-		for (int i = 0; i < Lall; i++) for (int k = 0; k < 3; k++) hx[4 * (size_t)i + k] = (T)p->Xw[3 * (size_t)i + k];
-		for (int b = 0; b < 2; b++) { CUDA_TRY(pose[b].upload(hp, stream)); CUDA_TRY(Xw[b].upload(hx, stream)); }
-		CUDA_TRY(pose0.upload(hp, stream)); CUDA_TRY(Xw0.upload(hx, stream));
-		CUDA_TRY(cam.upload(hc, stream));
-		// landmark-major edge stream
+		hostStructureValid = true;
+		const int eL = S.eLocal;
 		std::vector<T> mx(eL), my(eL), mz(eL), om(eL);
 		for (int e = 0; e < eL; e++) {
 			const int u = S.order[e];
@@ -262,18 +300,196 @@ struct Engine : EngineBase {
 		CUDA_TRY(e_ip.upload(S.e_ip, stream)); CUDA_TRY(e_il.upload(S.e_il, stream)); CUDA_TRY(e_hpl.upload(S.e_hpl, stream));
 		CUDA_TRY(e_user.upload(S.order, stream));
 		CUDA_TRY(lmPtr.upload(S.lmPtr, stream)); CUDA_TRY(tileLm.upload(S.tileLm, stream)); CUDA_TRY(hplLm.upload(S.hplLm, stream));
-		// pose-major stream
 		const size_t nPe = S.p_src.size();
 		std::vector<T> qx(nPe), qy(nPe), qz(nPe), qo(nPe);
 		for (size_t k = 0; k < nPe; k++) { const int e = S.p_src[k]; qx[k] = mx[e]; qy[k] = my[e]; qz[k] = mz[e]; qo[k] = om[e]; }
 		CUDA_TRY(p_mx.upload(qx, stream)); CUDA_TRY(p_my.upload(qy, stream)); CUDA_TRY(p_mz.upload(qz, stream)); CUDA_TRY(p_om.upload(qo, stream));
 		CUDA_TRY(p_il.upload(S.p_il, stream)); CUDA_TRY(posePtr.upload(S.posePtr, stream));
-		// Schur structures
 		CUDA_TRY(prodPtr.upload(S.prodPtr, stream)); CUDA_TRY(prodI.upload(S.prodI, stream)); CUDA_TRY(prodJ.upload(S.prodJ, stream));
 		CUDA_TRY(blkRow.upload(S.blkRow, stream)); CUDA_TRY(blkCol.upload(S.blkCol, stream));
 		CUDA_TRY(u2f.upload(S.u2f, stream)); CUDA_TRY(u2fT.upload(S.u2fT, stream));
 		CUDA_TRY(fRowPtr.upload(S.fRowPtr, stream)); CUDA_TRY(fColInd.upload(S.fColInd, stream));
-		// system buffers
+		CUDA_TRY(cudaStreamSynchronize(stream));   // host staging vectors die here
+		ntiles = (int)S.tileLm.size() - 1;
+		return CUBA_OK;
+	}
+
+	// ---- device structure builder (cuba_structure_gpu.cuh) ------------------------------------------------
+	DBuf<int> g_idx2, g_idx3, g_val, g_valS, g_ff, g_hplG, g_lmPtrG, g_hplRowInd, g_hplLmG, g_edge2Hpl, g_hplColPtr, g_hscRowPtr;
+	DBuf<int> g_pval, g_pvalS, g_pi, g_pj, g_head, g_blkId, g_cnt, g_off, g_fval, g_fvalS, g_pkeyVal, g_psrc;
+	DBuf<double> g_meas2, g_meas3, g_om2, g_om3;
+	DBuf<unsigned long long> g_key, g_keyS, g_pkey, g_pkeyS, g_fkey, g_fkeyS;
+	DBuf<unsigned int> g_k32, g_k32S;
+	DBuf<char> cubTmp;
+	DBuf<sgpu::Meta> g_meta;
+	sgpu::Meta* hMeta = nullptr;
+	bool hostStructureValid = false;
+
+	template <typename K>
+	int sortPairs(K* kin, K* kout, int* vin, int* vout, int n, int endBit)
+	{
+		if (n <= 0) return CUBA_OK;
+		size_t bytes = 0;
+		CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, n, 0, endBit, stream));
+		CUDA_TRY(cubTmp.alloc(bytes));
+		CUDA_TRY(cub::DeviceRadixSort::SortPairs(cubTmp.p, bytes, kin, kout, vin, vout, n, 0, endBit, stream));
+		launches += 4;
+		return CUBA_OK;
+	}
+	int exclusiveSum(const int* in, int* out, int n)
+	{
+		if (n <= 0) return CUBA_OK;
+		size_t bytes = 0;
+		CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, stream));
+		CUDA_TRY(cubTmp.alloc(bytes));
+		CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTmp.p, bytes, in, out, n, stream));
+		launches += 2;
+		return CUBA_OK;
+	}
+	int fetchMeta()
+	{
+		if (!hMeta) CUDA_TRY(cudaMallocHost((void**)&hMeta, sizeof(sgpu::Meta)));
+		CUDA_TRY(cudaMemcpyAsync(hMeta, g_meta.p, sizeof(sgpu::Meta), cudaMemcpyDeviceToHost, stream));
+		CUDA_TRY(cudaStreamSynchronize(stream));
+		if (hMeta->error == 1) return fail(CUBA_ERR_INVALID, "build_structure: edge index out of range");
+		if (hMeta->error == 2) return fail(CUBA_ERR_INVALID, "build_structure: edge with both ends fixed");
+		if (hMeta->error == 3) return fail(CUBA_ERR_INVALID, "build_structure: landmark without edges (the reference's initialize() drops such vertices)");
+		return CUBA_OK;
+	}
+#define KLAUNCH(kernel, n, ...)                                                             \
+	do {                                                                                     \
+		if ((n) > 0) {                                                                       \
+			kernel<<<sgpu::grid_for(n), sgpu::BLK, 0, stream>>>(__VA_ARGS__);                 \
+			launches++;                                                                      \
+			CUDA_TRY(cudaGetLastError());                                                    \
+		}                                                                                    \
+	} while (0)
+
+	int build_on_gpu(const cuba_problem* p)
+	{
+		using namespace sgpu;
+		S = Structure();
+		const int Pall = p->Pall, numP = p->numP, Lall = p->Lall, numL = p->numL, E2 = p->E2, E3 = p->E3, E = E2 + E3;
+		S.Pall = Pall; S.numP = numP; S.Lall = Lall; S.numL = numL; S.E2 = E2; S.E3 = E3; S.E = E;
+		// raw problem -> device (the only bulk H2D traffic of set_problem besides the state)
+		CUDA_TRY(g_idx2.upload(p->idx2, 2 * (size_t)E2, stream)); CUDA_TRY(g_idx3.upload(p->idx3, 2 * (size_t)E3, stream));
+		CUDA_TRY(g_meas2.upload(p->meas2, 2 * (size_t)E2, stream)); CUDA_TRY(g_meas3.upload(p->meas3, 3 * (size_t)E3, stream));
+		CUDA_TRY(g_om2.upload(p->omega2, (size_t)E2, stream)); CUDA_TRY(g_om3.upload(p->omega3, (size_t)E3, stream));
+		CUDA_TRY(g_meta.alloc(1));
+		CUDA_TRY(cudaMemsetAsync(g_meta.p, 0, sizeof(Meta), stream));
+		// 1. canonical (iL, iP, edge id) order
+		CUDA_TRY(g_key.alloc(E)); CUDA_TRY(g_keyS.alloc(E)); CUDA_TRY(g_val.alloc(E)); CUDA_TRY(g_valS.alloc(E));
+		KLAUNCH(k_make_keys, E, E2, g_idx2.p, E3, g_idx3.p, Pall, numP, Lall, numL, g_key.p, g_val.p, g_meta.p);
+		int rc = sortPairs(g_key.p, g_keyS.p, g_val.p, g_valS.p, E, 32 + bits_for((unsigned long long)std::max(Lall, 1))); if (rc) return rc;
+		CUDA_TRY(g_lmPtrG.alloc((size_t)Lall + 1));
+		KLAUNCH(k_ptr_from_high, Lall + 1, g_keyS.p, E, Lall, g_lmPtrG.p);
+		KLAUNCH(k_check_nonempty, Lall, g_lmPtrG.p, Lall, g_meta.p);
+		// 2. Hpl blocks = free-free edges in canonical order
+		CUDA_TRY(g_ff.alloc(E)); CUDA_TRY(g_hplG.alloc(E));
+		KLAUNCH(k_flag_freefree, E, g_keyS.p, E, numP, numL, g_ff.p);
+		rc = exclusiveSum(g_ff.p, g_hplG.p, E); if (rc) return rc;
+		k_shard_meta<<<1, 32, 0, stream>>>(g_lmPtrG.p, Lall, E, rank, world, g_ff.p, g_hplG.p, g_meta.p);
+		launches++;
+		CUDA_TRY(cudaGetLastError());
+		rc = fetchMeta(); if (rc) return rc;                                   // sync point 1
+		S.nhpl = hMeta->nhpl; S.lmBeg = hMeta->lmBeg; S.lmEnd = hMeta->lmEnd; S.eLocal = hMeta->kEnd - hMeta->kBeg;
+		S.hplBase = hMeta->hplBase; S.nhplLocal = hMeta->hplEnd - hMeta->hplBase;
+		const int kBeg = hMeta->kBeg, kEnd = hMeta->kEnd, eL = S.eLocal, nhpl = S.nhpl;
+		CUDA_TRY(g_hplRowInd.alloc(nhpl)); CUDA_TRY(g_hplLmG.alloc(nhpl)); CUDA_TRY(g_edge2Hpl.alloc(E)); CUDA_TRY(g_hplColPtr.alloc((size_t)numL + 1));
+		KLAUNCH(k_hpl_global, E, g_keyS.p, g_valS.p, g_ff.p, g_hplG.p, E, g_hplRowInd.p, g_hplLmG.p, g_edge2Hpl.p);
+		KLAUNCH(k_hpl_colptr, numL + 1, g_lmPtrG.p, g_hplG.p, E, numL, nhpl, g_hplColPtr.p);
+		// 3. landmark-major stream of the shard, tiles
+		CUDA_TRY(e_user.alloc(eL)); CUDA_TRY(e_ip.alloc(eL)); CUDA_TRY(e_il.alloc(eL)); CUDA_TRY(e_hpl.alloc(eL));
+		CUDA_TRY(e_mx.alloc(eL)); CUDA_TRY(e_my.alloc(eL)); CUDA_TRY(e_mz.alloc(eL)); CUDA_TRY(e_om.alloc(eL));
+		KLAUNCH(k_edge_stream<T>, eL, g_keyS.p, g_valS.p, g_ff.p, g_hplG.p, kBeg, eL, S.hplBase, E2, g_meas2.p, g_om2.p, g_meas3.p, g_om3.p,
+			e_user.p, e_ip.p, e_il.p, e_hpl.p, e_mx.p, e_my.p, e_mz.p, e_om.p);
+		CUDA_TRY(lmPtr.alloc((size_t)Lall + 1));
+		KLAUNCH(k_local_lmptr, Lall + 1, g_lmPtrG.p, Lall, kBeg, kEnd, lmPtr.p);
+		CUDA_TRY(hplLm.alloc(S.nhplLocal));
+		if (S.nhplLocal > 0) CUDA_TRY(cudaMemcpyAsync(hplLm.p, g_hplLmG.p + S.hplBase, sizeof(int) * (size_t)S.nhplLocal, cudaMemcpyDeviceToDevice, stream));
+		const int nt = (eL + TILE - 1) / TILE;
+		CUDA_TRY(tileLm.alloc((size_t)nt + 1));
+		KLAUNCH(k_tiles, nt + 1, lmPtr.p, S.lmBeg, S.lmEnd, TILE, nt, tileLm.p);
+		ntiles = nt;
+		// 4. pose-major stream (free poses only)
+		CUDA_TRY(g_k32.alloc(eL)); CUDA_TRY(g_k32S.alloc(eL)); CUDA_TRY(g_pval.alloc(eL)); CUDA_TRY(g_psrc.alloc(eL));
+		KLAUNCH(k_pose_keys, eL, e_ip.p, eL, numP, g_k32.p, g_pval.p);
+		rc = sortPairs(g_k32.p, g_k32S.p, g_pval.p, g_psrc.p, eL, bits_for((unsigned long long)numP)); if (rc) return rc;
+		CUDA_TRY(posePtr.alloc((size_t)numP + 1));
+		KLAUNCH(k_ptr_from_u32, numP + 1, g_k32S.p, eL, numP, posePtr.p);
+		CUDA_TRY(p_il.alloc(eL)); CUDA_TRY(p_mx.alloc(eL)); CUDA_TRY(p_my.alloc(eL)); CUDA_TRY(p_mz.alloc(eL)); CUDA_TRY(p_om.alloc(eL));
+		KLAUNCH(k_pose_stream<T>, eL, g_psrc.p, posePtr.p, numP, eL, e_ip.p, e_il.p, e_mx.p, e_my.p, e_mz.p, e_om.p, p_il.p, p_mx.p, p_my.p, p_mz.p, p_om.p);
+		// 5. block products keyed by destination block, + one dummy per diagonal
+		CUDA_TRY(g_cnt.alloc((size_t)nhpl + 1)); CUDA_TRY(g_off.alloc((size_t)nhpl + 1));
+		CUDA_TRY(cudaMemsetAsync(g_cnt.p, 0, sizeof(int) * ((size_t)nhpl + 1), stream));
+		KLAUNCH(k_prod_count, nhpl, g_hplLmG.p, g_hplColPtr.p, nhpl, g_cnt.p);
+		rc = exclusiveSum(g_cnt.p, g_off.p, nhpl + 1); if (rc) return rc;
+		long long nmul = 0;
+		{
+			int last = 0;
+			CUDA_TRY(cudaMemcpyAsync(&last, g_off.p + nhpl, sizeof(int), cudaMemcpyDeviceToHost, stream));
+			CUDA_TRY(cudaStreamSynchronize(stream));                              // sync point 2
+			nmul = last;
+		}
+		S.nmul = nmul;
+		const long long N = nmul + numP;
+		if (N > 0x7fffffffLL) return fail(CUBA_ERR_INVALID, "build_structure: more than 2^31 block products");
+		S.nmulLocal = N;
+		CUDA_TRY(g_pkey.alloc((size_t)N)); CUDA_TRY(g_pkeyS.alloc((size_t)N)); CUDA_TRY(g_pkeyVal.alloc((size_t)N)); CUDA_TRY(g_pvalS.alloc((size_t)N));
+		CUDA_TRY(g_pi.alloc((size_t)N)); CUDA_TRY(g_pj.alloc((size_t)N));
+		KLAUNCH(k_prod_emit, nhpl, g_hplLmG.p, g_hplColPtr.p, g_hplRowInd.p, g_off.p, nhpl, S.lmBeg, S.lmEnd, S.hplBase, g_pkey.p, g_pkeyVal.p, g_pi.p, g_pj.p);
+		KLAUNCH(k_prod_diag, numP, numP, nmul, g_pkey.p, g_pkeyVal.p, g_pi.p, g_pj.p);
+		rc = sortPairs(g_pkey.p, g_pkeyS.p, g_pkeyVal.p, g_pvalS.p, (int)N, 32 + bits_for((unsigned long long)std::max(numP, 1))); if (rc) return rc;
+		CUDA_TRY(g_head.alloc((size_t)N)); CUDA_TRY(g_blkId.alloc((size_t)N));
+		KLAUNCH(k_heads, N, g_pkeyS.p, (int)N, g_head.p);
+		rc = exclusiveSum(g_head.p, g_blkId.p, (int)N); if (rc) return rc;
+		k_nblk<<<1, 32, 0, stream>>>(g_head.p, g_blkId.p, (int)N, g_meta.p);
+		launches++;
+		rc = fetchMeta(); if (rc) return rc;                                   // sync point 3
+		const int nblk = hMeta->nblk;
+		S.nblk = nblk;
+		CUDA_TRY(blkRow.alloc(nblk)); CUDA_TRY(blkCol.alloc(nblk)); CUDA_TRY(prodPtr.alloc((size_t)nblk + 1));
+		CUDA_TRY(prodI.alloc((size_t)N)); CUDA_TRY(prodJ.alloc((size_t)N));
+		KLAUNCH(k_blocks, N + 1, g_pkeyS.p, g_pvalS.p, g_head.p, g_blkId.p, g_pi.p, g_pj.p, (int)N, blkRow.p, blkCol.p, prodPtr.p, prodI.p, prodJ.p);
+		CUDA_TRY(g_hscRowPtr.alloc((size_t)numP + 1));
+		KLAUNCH(k_rowptr_from_rows, numP + 1, blkRow.p, nblk, numP, g_hscRowPtr.p);
+		// 6. symmetric-full BSR for the PCG
+		const int nfull = 2 * nblk - numP;
+		S.nfull = nfull;
+		CUDA_TRY(g_fkey.alloc(2 * (size_t)nblk)); CUDA_TRY(g_fkeyS.alloc(2 * (size_t)nblk)); CUDA_TRY(g_fval.alloc(2 * (size_t)nblk)); CUDA_TRY(g_fvalS.alloc(2 * (size_t)nblk));
+		KLAUNCH(k_full_entries, nblk, blkRow.p, blkCol.p, nblk, numP, g_fkey.p, g_fval.p);
+		rc = sortPairs(g_fkey.p, g_fkeyS.p, g_fval.p, g_fvalS.p, 2 * nblk, 32 + bits_for((unsigned long long)std::max(numP, 1))); if (rc) return rc;
+		CUDA_TRY(fColInd.alloc(nfull)); CUDA_TRY(u2f.alloc(nblk)); CUDA_TRY(u2fT.alloc(nblk)); CUDA_TRY(fRowPtr.alloc((size_t)numP + 1));
+		KLAUNCH(k_full_finish, nfull, g_fkeyS.p, g_fvalS.p, nfull, blkRow.p, blkCol.p, fColInd.p, u2f.p, u2fT.p);
+		KLAUNCH(k_ptr_from_high, numP + 1, g_fkeyS.p, nfull, numP, fRowPtr.p);
+		// the PCG partition is computed on the host from the (small) full pattern
+		S.fRowPtr.resize((size_t)numP + 1); S.fColInd.resize(nfull);
+		g_d2hBytes += (long long)(sizeof(int) * ((size_t)numP + 1 + nfull));
+		CUDA_TRY(cudaMemcpyAsync(S.fRowPtr.data(), fRowPtr.p, sizeof(int) * ((size_t)numP + 1), cudaMemcpyDeviceToHost, stream));
+		if (nfull > 0) CUDA_TRY(cudaMemcpyAsync(S.fColInd.data(), fColInd.p, sizeof(int) * (size_t)nfull, cudaMemcpyDeviceToHost, stream));
+		CUDA_TRY(cudaStreamSynchronize(stream));                                  // sync point 4
+		return CUBA_OK;
+	}
+
+	// host copies of the index structures, only for the debug getters
+	int ensureHostStructure()
+	{
+		if (hostStructureValid) return CUBA_OK;
+		auto dl = [&](std::vector<int>& dst, const int* src, size_t n) -> cudaError_t {
+			dst.resize(n);
+			return n ? cudaMemcpyAsync(dst.data(), src, sizeof(int) * n, cudaMemcpyDeviceToHost, stream) : cudaSuccess;
+		};
+		CUDA_TRY(dl(S.hplColPtr, g_hplColPtr.p, (size_t)S.numL + 1)); CUDA_TRY(dl(S.hplRowInd, g_hplRowInd.p, S.nhpl));
+		CUDA_TRY(dl(S.edge2Hpl, g_edge2Hpl.p, S.E)); CUDA_TRY(dl(S.hscRowPtr, g_hscRowPtr.p, (size_t)S.numP + 1));
+		CUDA_TRY(dl(S.hscColInd, blkCol.p, S.nblk)); CUDA_TRY(dl(S.u2f, u2f.p, S.nblk)); CUDA_TRY(dl(S.u2fT, u2fT.p, S.nblk));
+		CUDA_TRY(cudaStreamSynchronize(stream));
+		hostStructureValid = true;
+		return CUBA_OK;
+	}
+
+	int alloc_system()
+	{
+		const int eL = S.eLocal;
 		const size_t nP = S.numP, nL = S.numL;
 		CUDA_TRY(Hpp.alloc(36 * nP)); CUDA_TRY(bp.alloc(6 * nP)); CUDA_TRY(Hll.alloc(9 * nL)); CUDA_TRY(bl.alloc(3 * nL));
 		CUDA_TRY(Hpl.alloc(18 * (size_t)S.nhplLocal)); CUDA_TRY(invHll.alloc(9 * nL));
@@ -287,14 +503,13 @@ struct Engine : EngineBase {
 		if (nP) CUDA_TRY(cudaMemsetAsync(xp.p, 0, sizeof(T) * 6 * nP, stream));
 		if (nP) CUDA_TRY(cudaMemsetAsync(Hpp.p, 0, sizeof(T) * 36 * nP, stream));
 		if (nP) CUDA_TRY(cudaMemsetAsync(bp.p, 0, sizeof(T) * 6 * nP, stream));
-		ntiles = (int)S.tileLm.size() - 1;
 		nPoseBlocks = (S.numP + RED_BLOCK - 1) / RED_BLOCK;
 		nChiBlocks = std::max(1, std::min((eL + RED_BLOCK - 1) / RED_BLOCK, numSMs * 8));
 		CUDA_TRY(chiPartial.alloc((size_t)std::max(ntiles, nChiBlocks) + 1));
 		CUDA_TRY(scalePartialL.alloc((size_t)std::max(ntiles, (S.numL + RED_BLOCK - 1) / RED_BLOCK) + 1));
 		CUDA_TRY(scalePartialP.alloc((size_t)nPoseBlocks + 1));
 		CUDA_TRY(chiSq.alloc((size_t)S.E));
-		// cooperative grid of the PCG kernel
+		// cooperative grid of the first-generation PCG kernel
 		{
 			int perSM = 0;
 			CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_pcg<T>, PCG_BLOCK, 0));
@@ -305,28 +520,13 @@ struct Engine : EngineBase {
 			CUDA_TRY(pcgPartial.alloc(2 * (size_t)pcgGrid));
 		}
 		if (S.numP > 0) { int rc = setup_pcg2(); if (rc) return rc; }
-		CUDA_TRY(cudaStreamSynchronize(stream));
-		cur = 0; trialValid = false;
-		resolveProfile();   // drop the events of earlier problems
-		for (int i = 0; i < CUBA_PROF_NUM; i++) prof[i] = 0;
-		const auto t1 = std::chrono::steady_clock::now();
-		prof[CUBA_PROF_BUILD_STRUCTURE] += std::chrono::duration<double>(t1 - t0).count();
-		haveProblem = true;
 		return CUBA_OK;
 	}
 
 	int set_state(const double* q, const double* t, const double* X) override
 	{
 		if (!haveProblem) return fail(CUBA_ERR_STATE, "set_state before set_problem");
-		std::vector<T> hp((size_t)S.Pall * 8, T(0)), hx((size_t)S.Lall * 4, T(0));
-		for (int i = 0; i < S.Pall; i++) {
-			for (int k = 0; k < 4; k++) hp[8 * (size_t)i + k] = (T)q[4 * (size_t)i + k];
-			for (int k = 0; k < 3; k++) hp[8 * (size_t)i + 4 + k] = (T)t[3 * (size_t)i + k];
-		}
-		for (int i = 0; i < S.Lall; i++) for (int k = 0; k < 3; k++) hx[4 * (size_t)i + k] = (T)X[3 * (size_t)i + k];
-		for (int b = 0; b < 2; b++) { CUDA_TRY(pose[b].upload(hp, stream)); CUDA_TRY(Xw[b].upload(hx, stream)); }
-		CUDA_TRY(pose0.upload(hp, stream)); CUDA_TRY(Xw0.upload(hx, stream));
-		CUDA_TRY(cudaStreamSynchronize(stream));
+		const int rc = upload_state(q, t, nullptr, X); if (rc) return rc;
 		trialValid = false;
 		return CUBA_OK;
 	}
@@ -805,6 +1005,7 @@ struct Engine : EngineBase {
 	int dbg_hpl_structure(int32_t* colPtr, int32_t* rowInd, int32_t* e2h) override
 	{
 		if (!haveProblem) return fail(CUBA_ERR_STATE, "no problem");
+		{ const int rc0 = ensureHostStructure(); if (rc0) return rc0; }
 		if (colPtr) memcpy(colPtr, S.hplColPtr.data(), sizeof(int) * S.hplColPtr.size());
 		if (rowInd) memcpy(rowInd, S.hplRowInd.data(), sizeof(int) * S.hplRowInd.size());
 		if (e2h) memcpy(e2h, S.edge2Hpl.data(), sizeof(int) * S.edge2Hpl.size());
@@ -813,6 +1014,7 @@ struct Engine : EngineBase {
 	int dbg_hsc_structure(int32_t* rowPtr, int32_t* colInd) override
 	{
 		if (!haveProblem) return fail(CUBA_ERR_STATE, "no problem");
+		{ const int rc0 = ensureHostStructure(); if (rc0) return rc0; }
 		if (rowPtr) memcpy(rowPtr, S.hscRowPtr.data(), sizeof(int) * S.hscRowPtr.size());
 		if (colInd) memcpy(colInd, S.hscColInd.data(), sizeof(int) * S.hscColInd.size());
 		return CUBA_OK;
@@ -844,6 +1046,7 @@ struct Engine : EngineBase {
 	{
 		if (!haveProblem) return fail(CUBA_ERR_STATE, "no problem");
 		int rc;
+		if ((rc = ensureHostStructure())) return rc;
 		if (oHsc) {
 			std::vector<double> full(36 * (size_t)S.nfull);
 			if ((rc = download(fVal, full.size(), full.data()))) return rc;

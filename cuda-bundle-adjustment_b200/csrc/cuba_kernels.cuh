@@ -361,6 +361,7 @@ __global__ void __launch_bounds__(SCHUR_BLOCK) k_schur(const SchurArgs<T> a)
 	for (int i = 0; i < 6; i++) v[i] = T(0);
 	for (int n = n0 + lane; n < n1; n += 32) {
 		const int i = a.prodI[n], j = a.prodJ[n];
+		if (i < 0) continue;   // diagonal placeholder / product of a landmark owned by another rank
 		const int l = a.hplLm[i];
 		T Ai[18], Aj[18], inv[6];
 		const T* pi = a.Hpl + 18 * (size_t)i;

@@ -74,7 +74,9 @@ typedef struct cuba_config {
 	double pcg_tol;        /* stop when sqrt(r'z / r0'z0) <= pcg_tol; <=0: default 1e-13           */
 	int deterministic;     /* 1 (default): fixed-order reductions, bit-reproducible run to run     */
 	int reserved[7];       /* reserved[0]: PCG kernel, 0 = k_pcg2 (shared-memory resident, one barrier per
-	                          iteration; default), 1 = k_pcg (first generation, two cooperative-groups syncs) */
+	                          iteration; default), 1 = k_pcg (first generation, two cooperative-groups syncs)
+	                          reserved[1]: 1 = build the index structures on the host (cuba_structure.cpp) instead of
+	                          on the device (cuba_structure_gpu.cuh, default); both give identical structures */
 } cuba_config;
 
 /* Flat problem: exactly what CudaBlockSolver::initialize produces (cpp:115-261).

@@ -181,6 +181,35 @@ def test_fixed_vertices_pose_only_landmark_only(pkg, oracle, problems):
         eng.close()
 
 
+@pytest.mark.parametrize("name", ["small", "kitti07_shaped"])
+def test_device_and_host_structure_builders_agree(pkg, problems, name):
+    """cuba_structure_gpu.cuh (default) and cuba_structure.cpp give identical index structures and the same
+    optimisation bit for bit (tiles only change the grouping of the chi2 partial sums)"""
+    prob = problems(name); rk = KERNELS["huber"]
+    a = make_engine(pkg, prob, rk); b = make_engine(pkg, prob, rk, structure_on_host=True)
+    assert a.sizes == b.sizes
+    for x, y in zip(a.hpl_structure() + a.hsc_structure(), b.hpl_structure() + b.hsc_structure()):
+        assert np.array_equal(x, y)
+    ca, cb = a.linearize(), b.linearize()
+    assert ca == pytest.approx(cb, rel=1e-13)
+    for x, y in zip(a.system(), b.system()):
+        assert np.array_equal(x, y)
+    lam = 1e-5 * a.max_diagonal()
+    assert a.solve(lam) == b.solve(lam)
+    for x, y in zip(a.schur() + a.delta(), b.schur() + b.delta()):
+        assert np.array_equal(x, y)
+    a.close(); b.close()
+
+
+def test_rejects_bad_problems(pkg, problems):
+    p = problems("tiny").copy()
+    p.idx3 = p.idx3.copy(); p.idx3[5, 1] = p.Lall + 3
+    eng = pkg.Engine(device=0)
+    with pytest.raises(pkg.CubaError, match="out of range"):
+        eng.initialize(p)
+    eng.close()
+
+
 def test_bitwise_reproducible(pkg, problems):
     """fixed-order reductions everywhere: two runs give identical bits (the reference's atomics do not)"""
     prob = problems("small")
