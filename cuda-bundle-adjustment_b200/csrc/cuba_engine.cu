@@ -140,6 +140,7 @@ struct Engine : EngineBase {
 	DBuf<T> pose[2], Xw[2], cam, pose0, Xw0;
 	// edge streams
 	DBuf<T> e_mx, e_my, e_mz, e_om, p_mx, p_my, p_mz, p_om;
+	DBuf<int> tilePtr;   // run pointers seen by the landmark tiles (see k_tile_ptr)
 	DBuf<int> e_ip, e_il, e_hpl, e_user, lmPtr, tileLm, hplLm, posePtr, p_il;
 	// system
 	DBuf<T> Hpp, bp, Hll, bl, Hpl, invHll, fVal, bsc, xp, xl;
@@ -299,7 +300,8 @@ struct Engine : EngineBase {
 		CUDA_TRY(e_mx.upload(mx, stream)); CUDA_TRY(e_my.upload(my, stream)); CUDA_TRY(e_mz.upload(mz, stream)); CUDA_TRY(e_om.upload(om, stream));
 		CUDA_TRY(e_ip.upload(S.e_ip, stream)); CUDA_TRY(e_il.upload(S.e_il, stream)); CUDA_TRY(e_hpl.upload(S.e_hpl, stream));
 		CUDA_TRY(e_user.upload(S.order, stream));
-		CUDA_TRY(lmPtr.upload(S.lmPtr, stream)); CUDA_TRY(tileLm.upload(S.tileLm, stream)); CUDA_TRY(hplLm.upload(S.hplLm, stream));
+		CUDA_TRY(lmPtr.upload(S.lmPtr, stream)); CUDA_TRY(tilePtr.upload(S.lmPtr, stream));
+		CUDA_TRY(tileLm.upload(S.tileLm, stream)); CUDA_TRY(hplLm.upload(S.hplLm, stream));
 		const size_t nPe = S.p_src.size();
 		std::vector<T> qx(nPe), qy(nPe), qz(nPe), qo(nPe);
 		for (size_t k = 0; k < nPe; k++) { const int e = S.p_src[k]; qx[k] = mx[e]; qy[k] = my[e]; qz[k] = mz[e]; qo[k] = om[e]; }
@@ -353,7 +355,7 @@ struct Engine : EngineBase {
 		CUDA_TRY(cudaStreamSynchronize(stream));
 		if (hMeta->error == 1) return fail(CUBA_ERR_INVALID, "build_structure: edge index out of range");
 		if (hMeta->error == 2) return fail(CUBA_ERR_INVALID, "build_structure: edge with both ends fixed");
-		if (hMeta->error == 3) return fail(CUBA_ERR_INVALID, "build_structure: landmark without edges (the reference's initialize() drops such vertices)");
+		if (hMeta->error == 3) return fail(CUBA_ERR_INVALID, "build_structure: free landmark without edges (the reference's initialize() drops such vertices)");
 		return CUBA_OK;
 	}
 #define KLAUNCH(kernel, n, ...)                                                             \
@@ -383,7 +385,7 @@ struct Engine : EngineBase {
 		int rc = sortPairs(g_key.p, g_keyS.p, g_val.p, g_valS.p, E, 32 + bits_for((unsigned long long)std::max(Lall, 1))); if (rc) return rc;
 		CUDA_TRY(g_lmPtrG.alloc((size_t)Lall + 1));
 		KLAUNCH(k_ptr_from_high, Lall + 1, g_keyS.p, E, Lall, g_lmPtrG.p);
-		KLAUNCH(k_check_nonempty, Lall, g_lmPtrG.p, Lall, g_meta.p);
+		KLAUNCH(k_check_nonempty, numL, g_lmPtrG.p, numL, g_meta.p);
 		// 2. Hpl blocks = free-free edges in canonical order
 		CUDA_TRY(g_ff.alloc(E)); CUDA_TRY(g_hplG.alloc(E));
 		KLAUNCH(k_flag_freefree, E, g_keyS.p, E, numP, numL, g_ff.p);
@@ -407,9 +409,12 @@ struct Engine : EngineBase {
 		KLAUNCH(k_local_lmptr, Lall + 1, g_lmPtrG.p, Lall, kBeg, kEnd, lmPtr.p);
 		CUDA_TRY(hplLm.alloc(S.nhplLocal));
 		if (S.nhplLocal > 0) CUDA_TRY(cudaMemcpyAsync(hplLm.p, g_hplLmG.p + S.hplBase, sizeof(int) * (size_t)S.nhplLocal, cudaMemcpyDeviceToDevice, stream));
+		CUDA_TRY(tilePtr.alloc((size_t)numL + 2));
+		KLAUNCH(k_tile_ptr, numL + 2, lmPtr.p, numL, eL, tilePtr.p);
+		const int tb = std::min(S.lmBeg, numL), te = std::min(S.lmEnd, numL) + (S.lmEnd > numL ? 1 : 0);
 		const int nt = (eL + TILE - 1) / TILE;
 		CUDA_TRY(tileLm.alloc((size_t)nt + 1));
-		KLAUNCH(k_tiles, nt + 1, lmPtr.p, S.lmBeg, S.lmEnd, TILE, nt, tileLm.p);
+		KLAUNCH(k_tiles, nt + 1, tilePtr.p, tb, te, TILE, nt, tileLm.p);
 		ntiles = nt;
 		// 4. pose-major stream (free poses only)
 		CUDA_TRY(g_k32.alloc(eL)); CUDA_TRY(g_k32S.alloc(eL)); CUDA_TRY(g_pval.alloc(eL)); CUDA_TRY(g_psrc.alloc(eL));
@@ -576,7 +581,7 @@ struct Engine : EngineBase {
 		LinLmArgs<T> a;
 		a.pose = pose[cur]; a.cam = cam; a.Xw = Xw[cur];
 		a.mx = e_mx; a.my = e_my; a.mz = e_mz; a.om = e_om; a.ip = e_ip; a.il = e_il; a.hpl = e_hpl;
-		a.lmPtr = lmPtr; a.tileLm = tileLm; a.numP = S.numP; a.numL = S.numL;
+		a.lmPtr = tilePtr; a.tileLm = tileLm; a.numP = S.numP; a.numL = S.numL;
 		a.Hpl = Hpl; a.Hll = Hll; a.bl = bl; a.chiPartial = chiPartial; a.rk = rkParams();
 		k_linearize_landmark<T><<<ntiles, TILE, 0, stream>>>(a);
 		launches++;
@@ -819,7 +824,7 @@ struct Engine : EngineBase {
 		ProfScope ps(this, CUBA_PROF_SCHUR_COMPLEMENT);
 		if (ntiles > 0 && S.numL > 0) {
 			BacksubArgs<T> a;
-			a.Hpl = Hpl; a.invHll = invHll; a.bl = bl; a.xp = xp; a.ip = e_ip; a.hpl = e_hpl; a.lmPtr = lmPtr; a.tileLm = tileLm;
+			a.Hpl = Hpl; a.invHll = invHll; a.bl = bl; a.xp = xp; a.ip = e_ip; a.hpl = e_hpl; a.lmPtr = tilePtr; a.tileLm = tileLm;
 			a.numL = S.numL; a.lambda = lambda; a.XwCur = Xw[cur]; a.XwTrial = Xw[cur ^ 1]; a.xl = xl; a.scalePartial = scalePartialL;
 			k_backsub<T><<<ntiles, TILE, 0, stream>>>(a);
 			launches++;

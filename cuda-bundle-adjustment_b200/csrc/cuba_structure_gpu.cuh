@@ -63,10 +63,21 @@ __global__ void k_ptr_from_u32(const unsigned int* __restrict__ keys, int nkeys,
 	ptr[i] = lo;
 }
 
-__global__ void k_check_nonempty(const int* __restrict__ lmPtrG, int Lall, Meta* meta)
+// every FREE landmark must have an edge; fixed landmarks may have none (all their observers fixed: the
+// reference keeps such vertices, src/cuda_bundle_adjustment.cpp:163-178, and drops only the edges, :212,233)
+__global__ void k_check_nonempty(const int* __restrict__ lmPtrG, int numL, Meta* meta)
 {
 	const int l = blockIdx.x * blockDim.x + threadIdx.x;
-	if (l < Lall && lmPtrG[l + 1] == lmPtrG[l]) atomicMax(&meta->error, 3);
+	if (l < numL && lmPtrG[l + 1] == lmPtrG[l]) atomicMax(&meta->error, 3);
+}
+
+// run pointers used by the landmark tiles: the free landmarks one by one, then ALL fixed landmarks of the
+// shard as one pseudo-landmark numL (its edges only contribute chi2 there; Hpp comes from the pose pass)
+__global__ void k_tile_ptr(const int* __restrict__ lmPtr, int numL, int eLocal, int* tilePtr)
+{
+	const int l = blockIdx.x * blockDim.x + threadIdx.x;
+	if (l > numL + 1) return;
+	tilePtr[l] = l <= numL ? lmPtr[l] : eLocal;
 }
 
 __global__ void k_flag_freefree(const unsigned long long* __restrict__ keys, int E, int numP, int numL, int* ff)
