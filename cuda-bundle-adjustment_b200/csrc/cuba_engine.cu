@@ -17,6 +17,7 @@
 #include "../../include/cuba_b200.h"
 #include "cuba_kernels.cuh"
 #include "cuba_pcg2.cuh"
+#include "cuba_pcg3.cuh"
 #include "cuba_structure.h"
 #include "cuba_structure_gpu.cuh"
 
@@ -154,6 +155,7 @@ struct Engine : EngineBase {
 	DBuf<int> fLocal, ctaRow, needPtr, needCol;
 	DBuf<double> pcg2Partial;
 	DBuf<GridBar> gridBar;
+	DBuf<unsigned long long> llFlags;   // k_pcg3: [wFlag 2*6numP*2 | pFlag 2*2G*2 | abort word]
 	int pcg2Grid = 0, pcg2Cap = 0, pcg2NeedMax = 0, pcg2MaxRows = 0;
 	size_t pcg2Smem = 0;
 	// reductions
@@ -763,12 +765,15 @@ struct Engine : EngineBase {
 			blkMax = std::max(blkMax, S.fRowPtr[rows[c + 1]] - S.fRowPtr[rows[c]]);
 		}
 		nptr[G] = (int)ncol.size();
-		const size_t needBytes = (size_t)needMax * (6 * sizeof(T) + 4) + ((size_t)maxRows + 1) * 4;
+		// fixed shared-memory footprint of k_pcg3 (a superset of k_pcg2's): r,s per needed column, p,y per own row, index lists
+		const size_t needBytes = (size_t)needMax * (12 * sizeof(T) + 8) + (size_t)maxRows * 12 * sizeof(T) + ((size_t)maxRows + 1) * 4;
 		size_t cap = budget > needBytes ? (budget - needBytes) / (36 * sizeof(T) + 4) : 0;
 		cap = std::min<size_t>(cap, (size_t)blkMax);
 		pcg2Grid = G; pcg2Cap = (int)cap; pcg2NeedMax = needMax; pcg2MaxRows = maxRows;
 		pcg2Smem = (size_t)cap * 36 * sizeof(T) + needBytes + (size_t)cap * 4 + 16;
 		CUDA_TRY(cudaFuncSetAttribute(k_pcg2<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pcg2Smem));
+		CUDA_TRY(cudaFuncSetAttribute(k_pcg3<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pcg2Smem));
+		CUDA_TRY(llFlags.alloc(2 * (2 * 6 * (size_t)numP) + 2 * (2 * 2 * (size_t)G) + 2));
 		int perSM = 0;
 		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_pcg2<T>, PCG2_BLOCK, pcg2Smem));
 		if (perSM < 1) return fail(CUBA_ERR_CUDA, "k_pcg2 cannot be resident with the requested shared memory");
@@ -784,7 +789,7 @@ struct Engine : EngineBase {
 		return CUBA_OK;
 	}
 
-	int launch_pcg2()
+	int launch_pcg2(bool flagged)
 	{
 		ProfScope ps(this, CUBA_PROF_DECOMP_NUMERICAL);
 		Pcg2Args<T> a;
@@ -796,6 +801,18 @@ struct Engine : EngineBase {
 		const double tol = cfg.pcg_tol > 0 ? cfg.pcg_tol : (sizeof(T) == 8 ? 1e-13 : 1e-6);
 		a.tol2 = tol * tol;
 		a.status = &dScal.p->pcg;
+		if (flagged) {
+			Pcg3Args<T> b;
+			b.base = a;
+			b.wFlag = llFlags.p;
+			b.pFlag = llFlags.p + 2 * (2 * 6 * (size_t)S.numP);
+			b.abortFlag = (int*)(b.pFlag + 2 * (2 * 2 * (size_t)pcg2Grid));
+			CUDA_TRY(cudaMemsetAsync(llFlags.p, 0, sizeof(unsigned long long) * llFlags.n, stream));
+			void* args3[] = { (void*)&b };
+			CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_pcg3<T>, dim3(pcg2Grid), dim3(PCG2_BLOCK), args3, pcg2Smem, stream));
+			launches++;
+			return CUBA_OK;
+		}
 		void* args[] = { (void*)&a };
 		CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_pcg2<T>, dim3(pcg2Grid), dim3(PCG2_BLOCK), args, pcg2Smem, stream));
 		launches++;
@@ -804,7 +821,8 @@ struct Engine : EngineBase {
 
 	int launch_pcg()
 	{
-		if (cfg.reserved[0] != 1) return launch_pcg2();   // reserved[0] == 1 selects the first-generation kernel
+		if (cfg.reserved[0] == 0) return launch_pcg2(true);    // k_pcg3: flag-synchronised exchange (default)
+		if (cfg.reserved[0] == 2) return launch_pcg2(false);   // k_pcg2: one grid barrier per iteration
 		ProfScope ps(this, CUBA_PROF_DECOMP_NUMERICAL);
 		PcgArgs<T> a;
 		a.fRowPtr = fRowPtr; a.fColInd = fColInd; a.fVal = fVal; a.b = bsc; a.numP = S.numP;

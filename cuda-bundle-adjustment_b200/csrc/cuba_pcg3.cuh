@@ -1,0 +1,300 @@
+// cuba_pcg3.cuh -- third-generation block-Jacobi PCG: k_pcg2 without grid barriers inside the iteration.
+//
+// Same algorithm and data placement as k_pcg2 (split-preconditioned Chronopoulos-Gear CG, A^ resident in
+// shared memory, one CTA per SM).  What changes is the exchange between CTAs: every value another CTA needs
+// (the six entries of w = A^ r per owned row, and the two partial inner products per CTA) is published as
+// "low-latency" words -- each fp64 is split in two 32-bit halves, each half travels in an 8-byte word next
+// to a 32-bit sequence tag (the pass number) -- so a consumer simply polls the payload in L2 until both tags
+// match.  8-byte stores are single-copy atomic, hence no __threadfence / MEMBAR / L1 invalidation and no
+// barrier: an iteration costs one L2 store->load hop instead of a GPU-wide barrier (~2 us on B200).
+// r and s of the needed columns are kept in shared memory by every consumer and advanced locally.
+// Buffers are double-buffered by pass parity; a CTA can never run more than one pass ahead of any other,
+// because it needs everybody's partial sums of pass k-1 to start pass k.
+#pragma once
+
+#include "cuba_pcg2.cuh"
+
+namespace cuba_b200 {
+
+constexpr unsigned int PCG3_SPIN_LIMIT = 1u << 24;   // ~1 s of polling: a lost peer aborts the solve instead of hanging
+
+__device__ __forceinline__ void ll_store(unsigned long long* slot, double v, unsigned int tag)
+{
+	const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+	const unsigned long long lo = (b & 0xffffffffull) | ((unsigned long long)tag << 32);
+	const unsigned long long hi = (b >> 32) | ((unsigned long long)tag << 32);
+	asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" :: "l"(slot), "l"(lo), "l"(hi) : "memory");
+}
+__device__ __forceinline__ bool ll_try_load(const unsigned long long* slot, unsigned int tag, double& v)
+{
+	unsigned long long lo, hi;
+	asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(slot) : "memory");
+	if ((unsigned int)(lo >> 32) != tag || (unsigned int)(hi >> 32) != tag) return false;
+	v = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+	return true;
+}
+// polls until the tag matches; returns false when the solve was aborted (or this thread gave up and aborts it)
+__device__ __forceinline__ bool ll_wait(const unsigned long long* slot, unsigned int tag, double& v, int* abortFlag)
+{
+	for (unsigned int spin = 0;; spin++) {
+		if (ll_try_load(slot, tag, v)) return true;
+		if ((spin & 1023u) == 1023u) {
+			if (*(volatile int*)abortFlag) return false;
+			if (spin >= PCG3_SPIN_LIMIT) { atomicExch(abortFlag, 1); return false; }
+		}
+	}
+}
+
+template <typename T>
+struct Pcg3Args {
+	Pcg2Args<T> base;
+	unsigned long long* wFlag;   // [2][6*numP][2]  published w entries
+	unsigned long long* pFlag;   // [2][2*G][2]     published partial inner products
+	int* abortFlag;              // zeroed before the launch together with wFlag/pFlag
+};
+
+template <typename T>
+__global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
+{
+	const Pcg2Args<T>& a = aa.base;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	T* s_blk = reinterpret_cast<T*>(smem_raw);                          // [36][capBlocks] element-major A^ cache
+	T* s_r = s_blk + (size_t)a.capBlocks * 36;                          // [needMax][6] residual of the needed columns
+	T* s_s = s_r + (size_t)a.needMax * 6;                               // [needMax][6] s = w + beta s
+	T* s_p = s_s + (size_t)a.needMax * 6;                               // [maxRows][6] search direction of the own rows
+	T* s_y = s_p + (size_t)a.maxRows * 6;                               // [maxRows][6] iterate (hat space) of the own rows
+	int* s_loc = reinterpret_cast<int*>(s_y + (size_t)a.maxRows * 6);   // [capBlocks]  need index of a block's column (<0: diagonal)
+	int* s_rowPtr = s_loc + a.capBlocks;                                // [maxRows+1]
+	int* s_need = s_rowPtr + a.maxRows + 1;                             // [needMax] global column of each need entry
+	int* s_own = s_need + a.needMax;                                    // [needMax] local own row of a need entry, or -1
+	__shared__ double s_red[PCG2_BLOCK / 32][2];
+	__shared__ double s_bc[2];
+	__shared__ unsigned int s_gen;
+	__shared__ int s_abort;
+
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const int G = gridDim.x, cta = blockIdx.x;
+	const int row0 = a.ctaRow[cta], row1 = a.ctaRow[cta + 1], nrows = row1 - row0;
+	const int need0 = a.needPtr[cta], nneed = a.needPtr[cta + 1] - need0;
+	const int blk0 = a.fRowPtr[row0], nblkCta = a.fRowPtr[row1] - blk0;
+	const int ncached = nblkCta < a.capBlocks ? nblkCta : a.capBlocks;
+	const size_t n6 = 6 * (size_t)a.numP;
+	if (tid == 0) { s_gen = ld_acquire_u32(&a.bar->gen); s_abort = 0; }
+	for (int i = tid; i <= nrows; i += PCG2_BLOCK) s_rowPtr[i] = a.fRowPtr[row0 + i] - blk0;
+	for (int i = tid; i < nneed; i += PCG2_BLOCK) {
+		const int j = a.needCol[need0 + i];
+		s_need[i] = j;
+		s_own[i] = (j >= row0 && j < row1) ? j - row0 : -1;
+	}
+	for (int i = tid; i < nrows * 6; i += PCG2_BLOCK) { s_p[i] = T(0); s_y[i] = T(0); }
+	__syncthreads();
+	unsigned int gen = s_gen;
+
+	// ---- S1: factor the diagonal blocks of the own rows, b^ = L^-1 b ------------------------------------
+	int bad = 0;
+	for (int i = row0 + tid; i < row1; i += PCG2_BLOCK) {
+		int d = -1;
+		for (int n = a.fRowPtr[i]; n < a.fRowPtr[i + 1]; n++) if (a.fColInd[n] == i) { d = n; break; }
+		T Li[36];
+		bool ok = d >= 0 && chol6_inverse_factor(a.fVal + 36 * (size_t)d, Li);
+		if (!ok) { bad = 1; for (int e = 0; e < 36; e++) Li[e] = (e % 7) == 0 ? T(1) : T(0); }
+		for (int e = 0; e < 36; e++) a.Linv[36 * (size_t)i + e] = Li[e];
+		for (int r = 0; r < 6; r++) {
+			T s = T(0);
+			for (int c = 0; c <= r; c++) s += Li[c * 6 + r] * a.b[6 * (size_t)i + c];
+			a.R0[6 * (size_t)i + r] = s;
+		}
+	}
+	{
+		const int anyBad = __syncthreads_or(bad);
+		if (tid == 0) a.partial[(size_t)cta * 2] = (double)anyBad;
+	}
+	grid_barrier(a.bar, G, gen);
+	double nbad = 0;
+	if (tid < 32) {
+		for (int i = tid; i < G; i += 32) nbad += __ldcg(a.partial + (size_t)i * 2);
+		nbad = warp_sum(nbad);
+		if (tid == 0) s_bc[0] = nbad;
+	}
+	__syncthreads();
+	nbad = s_bc[0];
+	__syncthreads();
+
+	// ---- S2: A^_ij = L_i^-1 S_ij L_j^-T for the own rows -> shared memory; r0 of the needed columns --------
+	for (int n = tid; n < nblkCta; n += PCG2_BLOCK) {
+		const int g = blk0 + n;
+		int lo = 0, hi = nrows - 1;
+		while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_rowPtr[mid] <= n) lo = mid; else hi = mid - 1; }
+		const int i = row0 + lo, j = a.fColInd[g];
+		const T* B = a.fVal + 36 * (size_t)g;
+		const T* Li = a.Linv + 36 * (size_t)i;
+		const T* Lj = a.Linv + 36 * (size_t)j;
+		T tmp[36], out[36];
+		for (int c = 0; c < 6; c++)
+			for (int r = 0; r < 6; r++) {
+				T s = T(0);
+				for (int k = 0; k <= r; k++) s += Li[k * 6 + r] * B[c * 6 + k];
+				tmp[c * 6 + r] = s;
+			}
+		for (int c = 0; c < 6; c++)
+			for (int r = 0; r < 6; r++) {
+				T s = T(0);
+				for (int k = 0; k <= c; k++) s += tmp[k * 6 + r] * __ldcg(Lj + k * 6 + c);
+				out[c * 6 + r] = s;
+			}
+		if (n < ncached) {
+			for (int e = 0; e < 36; e++) s_blk[(size_t)e * a.capBlocks + n] = out[e];
+			s_loc[n] = a.fLocal[g];
+		} else {
+			for (int e = 0; e < 36; e++) a.fHat[36 * (size_t)g + e] = out[e];
+		}
+	}
+	for (int wi = tid; wi < nneed * 6; wi += PCG2_BLOCK) {
+		const int c = wi / 6, comp = wi - 6 * c;
+		s_r[wi] = __ldcg(a.R0 + 6 * (size_t)s_need[c] + comp);
+		s_s[wi] = T(0);
+	}
+	__syncthreads();
+
+	int status = 1, it = 0;
+	double gamma = 0, gamma0 = 0, alpha = 0, beta = 0;
+	if (nbad > 0) status = 2;
+	else {
+		// pass k = -1: w0 = A^ r0 and the first inner products; pass k >= 0: CG iteration k.
+		// Values published at the end of pass k-1 carry the tag k+1 and live in parity (k+1)&1.
+		for (int k = -1;; k++) {
+			if (k >= 0) {
+				const unsigned int tag = (unsigned int)(k + 1);
+				const int par = (k + 1) & 1;
+				bool ok = true;
+				// ---- poll w_k of the needed columns (first item per thread now, the rest below) ----
+				double wv0 = 0;
+				if (tid < nneed * 6) {
+					const int c = tid / 6, comp = tid - 6 * c;
+					ok = ll_wait(aa.wFlag + 2 * ((size_t)par * n6 + 6 * (size_t)s_need[c] + comp), tag, wv0, aa.abortFlag);
+				}
+				// ---- scalars from everybody's partial inner products of pass k-1 ----
+				if (tid < 32) {
+					double g2 = 0, d2 = 0;
+					for (int i = tid; i < G && ok; i += 32) {
+						double x0 = 0, x1 = 0;
+						ok = ll_wait(aa.pFlag + 2 * ((size_t)par * 2 * G + 2 * (size_t)i), tag, x0, aa.abortFlag)
+							&& ll_wait(aa.pFlag + 2 * ((size_t)par * 2 * G + 2 * (size_t)i + 1), tag, x1, aa.abortFlag);
+						g2 += x0; d2 += x1;
+					}
+					g2 = warp_sum(g2); d2 = warp_sum(d2);
+					if (tid == 0) { s_bc[0] = g2; s_bc[1] = d2; }
+				}
+				if (!ok) s_abort = 1;
+				__syncthreads();
+				if (s_abort) { status = 3; break; }
+				const double gnew = s_bc[0], delta = s_bc[1];
+				if (!(gnew == gnew) || !(delta == delta)) { status = 2; break; }
+				if (k == 0) {
+					gamma0 = gamma = gnew;
+					if (gamma0 <= 0) { status = 0; break; }
+					if (!(delta > 0)) { status = 2; break; }
+					alpha = gamma / delta; beta = 0;
+				} else {
+					it = k;
+					if (gnew <= a.tol2 * gamma0) { gamma = gnew; status = 0; break; }
+					beta = gnew / gamma;
+					const double den = delta - beta * gnew / alpha;
+					gamma = gnew;
+					if (!(den > 0)) { status = 2; break; }
+					alpha = gnew / den;
+				}
+				if (k >= a.maxIters) { status = 1; break; }
+				// ---- advance s, r (all needed columns) and p, y (own rows) in shared memory ----
+				for (int wi = tid; wi < nneed * 6; wi += PCG2_BLOCK) {
+					double wv = wv0;
+					if (wi >= PCG2_BLOCK) {
+						const int c = wi / 6, comp = wi - 6 * c;
+						if (!ll_wait(aa.wFlag + 2 * ((size_t)par * n6 + 6 * (size_t)s_need[c] + comp), tag, wv, aa.abortFlag)) { s_abort = 1; wv = 0; }
+					}
+					const T rold = s_r[wi];
+					const T snew = (T)wv + (T)beta * s_s[wi];
+					s_s[wi] = snew;
+					s_r[wi] = rold - (T)alpha * snew;
+					const int own = s_own[wi / 6];
+					if (own >= 0) {
+						const int o = own * 6 + (wi % 6);
+						const T p = rold + (T)beta * s_p[o];
+						s_p[o] = p;
+						s_y[o] += (T)alpha * p;
+					}
+				}
+				__syncthreads();
+				if (s_abort) { status = 3; break; }
+			}
+			// ---- w_{k+1} = A^ r_{k+1} for the own rows (warp per row); publish w and the partial products ----
+			const unsigned int otag = (unsigned int)(k + 2);
+			const int opar = (k + 2) & 1;
+			double pg = 0, pd = 0;
+			for (int li = wid; li < nrows; li += PCG2_BLOCK / 32) {
+				T acc[6] = { T(0), T(0), T(0), T(0), T(0), T(0) };
+				const int n0 = s_rowPtr[li], n1 = s_rowPtr[li + 1];
+				int selfLoc = -1;
+				for (int n = n0 + lane; n < n1; n += 32) {
+					const bool cached = n < ncached;
+					const int loc = cached ? s_loc[n] : a.fLocal[blk0 + n];
+					if (loc < 0) { selfLoc = -1 - loc; continue; }
+					const T* rj = s_r + 6 * (size_t)loc;
+					if (cached) {
+						const T* B = s_blk + n;
+						const size_t st = (size_t)a.capBlocks;
+#pragma unroll
+						for (int c = 0; c < 6; c++) {
+							const T rc = rj[c];
+#pragma unroll
+							for (int r = 0; r < 6; r++) acc[r] += B[(c * 6 + r) * st] * rc;
+						}
+					} else {
+						const T* B = a.fHat + 36 * (size_t)(blk0 + n);
+#pragma unroll
+						for (int c = 0; c < 6; c++) {
+							const T rc = rj[c];
+#pragma unroll
+							for (int r = 0; r < 6; r++) acc[r] += B[c * 6 + r] * rc;
+						}
+					}
+				}
+#pragma unroll
+				for (int c = 0; c < 6; c++) acc[c] = warp_sum(acc[c]);
+				selfLoc = __reduce_max_sync(0xffffffffu, selfLoc);
+				if (lane < 6) {
+					T wv = acc[0];
+#pragma unroll
+					for (int c = 1; c < 6; c++) if (lane == c) wv = acc[c];
+					const T ri = s_r[6 * (size_t)selfLoc + lane];
+					wv += ri;                                   // A^_ii = I
+					ll_store(aa.wFlag + 2 * ((size_t)opar * n6 + 6 * (size_t)(row0 + li) + lane), (double)wv, otag);
+					pg += (double)ri * (double)ri;
+					pd += (double)wv * (double)ri;
+				}
+			}
+			pg = warp_sum(pg); pd = warp_sum(pd);
+			if (lane == 0) { s_red[wid][0] = pg; s_red[wid][1] = pd; }
+			__syncthreads();
+			if (tid == 0) {
+				double g2 = 0, d2 = 0;
+				for (int w = 0; w < PCG2_BLOCK / 32; w++) { g2 += s_red[w][0]; d2 += s_red[w][1]; }
+				ll_store(aa.pFlag + 2 * ((size_t)opar * 2 * G + 2 * (size_t)cta), g2, otag);
+				ll_store(aa.pFlag + 2 * ((size_t)opar * 2 * G + 2 * (size_t)cta + 1), d2, otag);
+			}
+			// s_red is rewritten only after the next pass's __syncthreads
+		}
+	}
+	// ---- x = L^-T y for the own rows ----
+	__syncthreads();
+	for (int wi = tid; wi < nrows * 6; wi += PCG2_BLOCK) {
+		const int li = wi / 6, r = wi % 6;
+		const T* Li = a.Linv + 36 * (size_t)(row0 + li);
+		T s = T(0);
+		for (int c = r; c < 6; c++) s += Li[r * 6 + c] * s_y[6 * li + c];   // (L^-T)(r,c) = Li(c,r)
+		a.x[6 * (size_t)(row0 + li) + r] = s;
+	}
+	if (cta == 0 && tid == 0) { a.status->iters = it; a.status->status = status; a.status->rz0 = gamma0; a.status->rz = gamma; }
+}
+
+}  // namespace cuba_b200

@@ -73,8 +73,9 @@ typedef struct cuba_config {
 	int pcg_max_iters;     /* <=0: default                                         */
 	double pcg_tol;        /* stop when sqrt(r'z / r0'z0) <= pcg_tol; <=0: default 1e-13           */
 	int deterministic;     /* 1 (default): fixed-order reductions, bit-reproducible run to run     */
-	int reserved[7];       /* reserved[0]: PCG kernel, 0 = k_pcg2 (shared-memory resident, one barrier per
-	                          iteration; default), 1 = k_pcg (first generation, two cooperative-groups syncs)
+	int reserved[7];       /* reserved[0]: PCG kernel, 0 = k_pcg3 (shared-memory resident, flag-synchronised exchange,
+	                          no barrier in the iteration; default), 2 = k_pcg2 (same, one grid barrier per iteration),
+	                          1 = k_pcg (first generation, two cooperative-groups syncs)
 	                          reserved[1]: 1 = build the index structures on the host (cuba_structure.cpp) instead of
 	                          on the device (cuba_structure_gpu.cuh, default); both give identical structures */
 } cuba_config;

@@ -143,9 +143,9 @@ def test_against_compiled_reference(pkg, problems, name, kernel):
     eng.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1])
-def test_both_pcg_kernels_solve_the_same_system(pkg, oracle, problems, variant):
-    """k_pcg2 (shared-memory resident, single barrier) and k_pcg (first generation) against the direct solve"""
+@pytest.mark.parametrize("variant", [0, 2, 1])
+def test_all_pcg_kernels_solve_the_same_system(pkg, oracle, problems, variant):
+    """k_pcg3 (flag-synchronised), k_pcg2 (single barrier) and k_pcg (first generation) against the direct solve"""
     prob = problems("kitti07_shaped"); rk = KERNELS["huber"]
     eng = make_engine(pkg, prob, rk, pcg_variant=variant)
     o = oracle.Oracle(prob, *rk)
