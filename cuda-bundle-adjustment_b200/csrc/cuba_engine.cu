@@ -724,7 +724,7 @@ struct Engine : EngineBase {
 		int dev = 0, smemMax = 0;
 		CUDA_TRY(cudaGetDevice(&dev));
 		CUDA_TRY(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-		const size_t budget = (size_t)smemMax > 4096 ? (size_t)smemMax - 2048 : 0;   // leave room for the static arrays
+		const size_t budget = (size_t)smemMax > 8192 ? (size_t)smemMax - 6144 : 0;   // leave room for the static arrays (4.4 KB in k_pcg3)
 		const size_t matBytes = (size_t)S.nfull * (36 * sizeof(T) + 4);
 		int G = std::max((numP + 7) / 8, (int)((matBytes + budget - 1) / std::max<size_t>(budget, 1)));
 		G = std::max(1, std::min(G, std::min(numSMs, numP)));

@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 	int* s_own = s_need + a.needMax;                                    // [needMax] local own row of a need entry, or -1
 	__shared__ double s_red[PCG2_BLOCK / 32][2];
 	__shared__ double s_bc[2];
+	__shared__ double s_part[PCG2_BLOCK];   // 2*G <= 2*numSMs partial products
 	__shared__ unsigned int s_gen;
 	__shared__ int s_abort;
 
@@ -166,26 +167,31 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 			if (k >= 0) {
 				const unsigned int tag = (unsigned int)(k + 1);
 				const int par = (k + 1) & 1;
-				bool ok = true;
-				// ---- poll w_k of the needed columns (first item per thread now, the rest below) ----
-				double wv0 = 0;
-				if (tid < nneed * 6) {
-					const int c = tid / 6, comp = tid - 6 * c;
-					ok = ll_wait(aa.wFlag + 2 * ((size_t)par * n6 + 6 * (size_t)s_need[c] + comp), tag, wv0, aa.abortFlag);
+				// ---- one polling round per thread: its first w item and one partial product, loads in flight together ----
+				double wv0 = 0, pv = 0;
+				const bool needW = tid < nneed * 6, needP = tid < 2 * G;
+				const unsigned long long* wslot = aa.wFlag;
+				if (needW) { const int c = tid / 6, comp = tid - 6 * c; wslot = aa.wFlag + 2 * ((size_t)par * n6 + 6 * (size_t)s_need[c] + comp); }
+				const unsigned long long* pslot = aa.pFlag + 2 * ((size_t)par * 2 * G + (size_t)(needP ? tid : 0));
+				bool gotW = !needW, gotP = !needP, ok = true;
+				for (unsigned int spin = 0; !(gotW && gotP); spin++) {
+					if (!gotW) gotW = ll_try_load(wslot, tag, wv0);
+					if (!gotP) gotP = ll_try_load(pslot, tag, pv);
+					if ((spin & 1023u) == 1023u) {
+						if (*(volatile int*)aa.abortFlag) { ok = false; break; }
+						if (spin >= PCG3_SPIN_LIMIT) { atomicExch(aa.abortFlag, 1); ok = false; break; }
+					}
 				}
-				// ---- scalars from everybody's partial inner products of pass k-1 ----
+				if (needP) s_part[tid] = pv;
+				if (!ok) s_abort = 1;
+				__syncthreads();
+				// ---- scalars: fixed-order sum of everybody's partial inner products of pass k-1 ----
 				if (tid < 32) {
 					double g2 = 0, d2 = 0;
-					for (int i = tid; i < G && ok; i += 32) {
-						double x0 = 0, x1 = 0;
-						ok = ll_wait(aa.pFlag + 2 * ((size_t)par * 2 * G + 2 * (size_t)i), tag, x0, aa.abortFlag)
-							&& ll_wait(aa.pFlag + 2 * ((size_t)par * 2 * G + 2 * (size_t)i + 1), tag, x1, aa.abortFlag);
-						g2 += x0; d2 += x1;
-					}
+					for (int i = tid; i < G; i += 32) { g2 += s_part[2 * i]; d2 += s_part[2 * i + 1]; }
 					g2 = warp_sum(g2); d2 = warp_sum(d2);
 					if (tid == 0) { s_bc[0] = g2; s_bc[1] = d2; }
 				}
-				if (!ok) s_abort = 1;
 				__syncthreads();
 				if (s_abort) { status = 3; break; }
 				const double gnew = s_bc[0], delta = s_bc[1];
