@@ -127,6 +127,7 @@ struct EngineBase {
 	virtual int dbg_schur(double* Hsc, double* bsc, double* invHll) = 0;
 	virtual int dbg_delta(double* xp, double* xl) = 0;
 	virtual int bench_stage(int stage, int reps, int flush, double lambda, double* ms) = 0;
+	virtual int dbg_pcg_timing(long long* out, int maxCtas) = 0;
 };
 
 template <typename T>
@@ -155,6 +156,7 @@ struct Engine : EngineBase {
 	DBuf<int> fLocal, ctaRow, needPtr, needCol;
 	DBuf<double> pcg2Partial;
 	DBuf<GridBar> gridBar;
+	DBuf<long long> pcgTiming;
 	DBuf<unsigned long long> llFlags;   // k_pcg3: [wFlag 2*6numP*2 | pFlag 2*2G*2 | abort word]
 	int pcg2Grid = 0, pcg2Cap = 0, pcg2NeedMax = 0, pcg2MaxRows = 0;
 	size_t pcg2Smem = 0;
@@ -807,6 +809,11 @@ struct Engine : EngineBase {
 			b.wFlag = llFlags.p;
 			b.pFlag = llFlags.p + 2 * (2 * 6 * (size_t)S.numP);
 			b.abortFlag = (int*)(b.pFlag + 2 * (2 * 2 * (size_t)pcg2Grid));
+			b.timing = nullptr;
+#ifdef CUBA_PCG_TIMING
+			CUDA_TRY(pcgTiming.alloc(8 * (size_t)pcg2Grid));
+			b.timing = pcgTiming.p;
+#endif
 			CUDA_TRY(cudaMemsetAsync(llFlags.p, 0, sizeof(unsigned long long) * llFlags.n, stream));
 			void* args3[] = { (void*)&b };
 			CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_pcg3<T>, dim3(pcg2Grid), dim3(PCG2_BLOCK), args3, pcg2Smem, stream));
@@ -1088,6 +1095,15 @@ struct Engine : EngineBase {
 		return CUBA_OK;
 	}
 
+	int dbg_pcg_timing(long long* out, int maxCtas) override
+	{
+		const int n = std::min(maxCtas, pcg2Grid);
+		if (!pcgTiming.p || n <= 0) return 0;
+		cudaMemcpyAsync(out, pcgTiming.p, sizeof(long long) * 8 * (size_t)n, cudaMemcpyDeviceToHost, stream);
+		cudaStreamSynchronize(stream);
+		return n;
+	}
+
 	// ---- micro-benchmarks --------------------------------------------------------------------------------
 	int bench_stage(int stage, int reps, int flush, double lambda, double* ms) override
 	{
@@ -1221,6 +1237,12 @@ int cuba_engine_optimize(cuba_engine* e, int niter, cuba_iter_stat* stats, int* 
 int cuba_engine_get_state(cuba_engine* e, double* q, double* t, double* Xw) { ENGINE_OR_FAIL(e); return e->impl->get_state(q, t, Xw); }
 int cuba_engine_get_chi2(cuba_engine* e, double* per_edge) { ENGINE_OR_FAIL(e); if (!per_edge) return fail(CUBA_ERR_INVALID, "null out"); return e->impl->get_chi2(per_edge); }
 int cuba_engine_get_profile(cuba_engine* e, double* sec) { ENGINE_OR_FAIL(e); if (!sec) return fail(CUBA_ERR_INVALID, "null out"); return e->impl->get_profile(sec); }
+// debug: per-CTA phase timings of the last k_pcg3 launch (library built with -DCUBA_PCG_TIMING); returns the CTA count
+int cuba_debug_get_pcg_timing(cuba_engine* e, long long* out, int maxCtas)
+{
+	if (!e || !e->impl) return -1;
+	return e->impl->dbg_pcg_timing(out, maxCtas);
+}
 int cuba_get_transfer_bytes(long long* h2d, long long* d2h) { if (h2d) *h2d = g_h2dBytes; if (d2h) *d2h = g_d2hBytes; return CUBA_OK; }
 int cuba_engine_get_launch_count(cuba_engine* e, long long* count) { ENGINE_OR_FAIL(e); if (count) *count = e->impl->launches; return CUBA_OK; }
 

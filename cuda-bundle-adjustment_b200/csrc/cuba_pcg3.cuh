@@ -16,6 +16,14 @@
 
 namespace cuba_b200 {
 
+#ifdef CUBA_PCG_TIMING
+#define PCG_T(var) const long long var = clock64()
+#define PCG_ACC(slot, a, b) do { if (threadIdx.x == 0) tacc[slot] += (b) - (a); } while (0)
+#else
+#define PCG_T(var)
+#define PCG_ACC(slot, a, b)
+#endif
+
 constexpr unsigned int PCG3_SPIN_LIMIT = 1u << 24;   // ~1 s of polling: a lost peer aborts the solve instead of hanging
 
 __device__ __forceinline__ void ll_store(unsigned long long* slot, double v, unsigned int tag)
@@ -51,6 +59,7 @@ struct Pcg3Args {
 	unsigned long long* wFlag;   // [2][6*numP][2]  published w entries
 	unsigned long long* pFlag;   // [2][2*G][2]     published partial inner products
 	int* abortFlag;              // zeroed before the launch together with wFlag/pFlag
+	long long* timing;           // [G][8] per-phase clock64 sums (only with -DCUBA_PCG_TIMING)
 };
 
 template <typename T>
@@ -159,6 +168,9 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 
 	int status = 1, it = 0;
 	double gamma = 0, gamma0 = 0, alpha = 0, beta = 0;
+#ifdef CUBA_PCG_TIMING
+	long long tacc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+#endif
 	if (nbad > 0) status = 2;
 	else {
 		// pass k = -1: w0 = A^ r0 and the first inner products; pass k >= 0: CG iteration k.
@@ -167,6 +179,7 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 			if (k >= 0) {
 				const unsigned int tag = (unsigned int)(k + 1);
 				const int par = (k + 1) & 1;
+				PCG_T(t0);
 				// ---- one polling round per thread: its first w item and one partial product, loads in flight together ----
 				double wv0 = 0, pv = 0;
 				const bool needW = tid < nneed * 6, needP = tid < 2 * G;
@@ -182,9 +195,12 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 						if (spin >= PCG3_SPIN_LIMIT) { atomicExch(aa.abortFlag, 1); ok = false; break; }
 					}
 				}
+				PCG_T(t1);
 				if (needP) s_part[tid] = pv;
 				if (!ok) s_abort = 1;
 				__syncthreads();
+				PCG_T(t2);
+				PCG_ACC(0, t0, t1); PCG_ACC(1, t1, t2);
 				// ---- scalars: fixed-order sum of everybody's partial inner products of pass k-1 ----
 				if (tid < 32) {
 					double g2 = 0, d2 = 0;
@@ -211,6 +227,8 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 					alpha = gnew / den;
 				}
 				if (k >= a.maxIters) { status = 1; break; }
+				PCG_T(t3);
+				PCG_ACC(2, t2, t3);
 				// ---- advance s, r (all needed columns) and p, y (own rows) in shared memory ----
 				for (int wi = tid; wi < nneed * 6; wi += PCG2_BLOCK) {
 					double wv = wv0;
@@ -232,7 +250,10 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 				}
 				__syncthreads();
 				if (s_abort) { status = 3; break; }
+				PCG_T(t4);
+				PCG_ACC(3, t3, t4);
 			}
+			PCG_T(t5);
 			// ---- w_{k+1} = A^ r_{k+1} for the own rows (warp per row); publish w and the partial products ----
 			const unsigned int otag = (unsigned int)(k + 2);
 			const int opar = (k + 2) & 1;
@@ -279,15 +300,19 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 					pd += (double)wv * (double)ri;
 				}
 			}
+			PCG_T(t6);
 			pg = warp_sum(pg); pd = warp_sum(pd);
 			if (lane == 0) { s_red[wid][0] = pg; s_red[wid][1] = pd; }
 			__syncthreads();
+			PCG_T(t7);
 			if (tid == 0) {
 				double g2 = 0, d2 = 0;
 				for (int w = 0; w < PCG2_BLOCK / 32; w++) { g2 += s_red[w][0]; d2 += s_red[w][1]; }
 				ll_store(aa.pFlag + 2 * ((size_t)opar * 2 * G + 2 * (size_t)cta), g2, otag);
 				ll_store(aa.pFlag + 2 * ((size_t)opar * 2 * G + 2 * (size_t)cta + 1), d2, otag);
 			}
+			PCG_T(t8);
+			PCG_ACC(4, t5, t6); PCG_ACC(5, t6, t7); PCG_ACC(6, t7, t8);
 			// s_red is rewritten only after the next pass's __syncthreads
 		}
 	}
@@ -300,6 +325,9 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 		for (int c = r; c < 6; c++) s += Li[r * 6 + c] * s_y[6 * li + c];   // (L^-T)(r,c) = Li(c,r)
 		a.x[6 * (size_t)(row0 + li) + r] = s;
 	}
+#ifdef CUBA_PCG_TIMING
+	if (tid == 0 && aa.timing) { for (int i = 0; i < 7; i++) aa.timing[(size_t)cta * 8 + i] = tacc[i]; aa.timing[(size_t)cta * 8 + 7] = it; }
+#endif
 	if (cta == 0 && tid == 0) { a.status->iters = it; a.status->status = status; a.status->rz0 = gamma0; a.status->rz = gamma; }
 }
 
