@@ -159,6 +159,7 @@ struct Engine : EngineBase {
 	DBuf<long long> pcgTiming;
 	DBuf<unsigned long long> llFlags;   // k_pcg3: [wFlag 2*6numP*2 | pFlag 2*2G*2 | abort word]
 	int pcg2Grid = 0, pcg2Cap = 0, pcg2NeedMax = 0, pcg2MaxRows = 0;
+	bool pcg3Ok = false;
 	size_t pcg2Smem = 0;
 	// reductions
 	DBuf<double> chiPartial, scalePartialL, scalePartialP, chiSq;
@@ -768,7 +769,9 @@ struct Engine : EngineBase {
 		}
 		nptr[G] = (int)ncol.size();
 		// fixed shared-memory footprint of k_pcg3 (a superset of k_pcg2's): r,s per needed column, p,y per own row, index lists
-		const size_t needBytes = (size_t)needMax * (12 * sizeof(T) + 8) + (size_t)maxRows * 12 * sizeof(T) + ((size_t)maxRows + 1) * 4;
+		const size_t needBytes = (size_t)needMax * (12 * sizeof(T) + 8) + (size_t)maxRows * (12 * sizeof(T) + 4) + ((size_t)maxRows + 1) * 4
+			+ (size_t)PCG3_CHUNK * 6 * sizeof(T);
+		pcg3Ok = maxRows * 6 <= PCG2_BLOCK && 2 * G <= PCG2_BLOCK;   // k_pcg3 keeps one (row,component) and one partial per thread
 		size_t cap = budget > needBytes ? (budget - needBytes) / (36 * sizeof(T) + 4) : 0;
 		cap = std::min<size_t>(cap, (size_t)blkMax);
 		pcg2Grid = G; pcg2Cap = (int)cap; pcg2NeedMax = needMax; pcg2MaxRows = maxRows;
@@ -828,7 +831,7 @@ struct Engine : EngineBase {
 
 	int launch_pcg()
 	{
-		if (cfg.reserved[0] == 0) return launch_pcg2(true);    // k_pcg3: flag-synchronised exchange (default)
+		if (cfg.reserved[0] == 0) return launch_pcg2(pcg3Ok);  // k_pcg3: flag-synchronised exchange (default; k_pcg2 beyond ~85 rows per CTA)
 		if (cfg.reserved[0] == 2) return launch_pcg2(false);   // k_pcg2: one grid barrier per iteration
 		ProfScope ps(this, CUBA_PROF_DECOMP_NUMERICAL);
 		PcgArgs<T> a;

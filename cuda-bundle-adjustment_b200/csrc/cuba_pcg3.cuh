@@ -62,6 +62,8 @@ struct Pcg3Args {
 	long long* timing;           // [G][8] per-phase clock64 sums (only with -DCUBA_PCG_TIMING)
 };
 
+constexpr int PCG3_CHUNK = PCG2_BLOCK;   // block products staged per round (one per thread)
+
 template <typename T>
 __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 {
@@ -72,11 +74,14 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 	T* s_s = s_r + (size_t)a.needMax * 6;                               // [needMax][6] s = w + beta s
 	T* s_p = s_s + (size_t)a.needMax * 6;                               // [maxRows][6] search direction of the own rows
 	T* s_y = s_p + (size_t)a.maxRows * 6;                               // [maxRows][6] iterate (hat space) of the own rows
-	int* s_loc = reinterpret_cast<int*>(s_y + (size_t)a.maxRows * 6);   // [capBlocks]  need index of a block's column (<0: diagonal)
+	T* s_c = s_y + (size_t)a.maxRows * 6;                               // [PCG3_CHUNK][6] block-product contributions
+	int* s_loc = reinterpret_cast<int*>(s_c + (size_t)PCG3_CHUNK * 6);  // [capBlocks]  need index of a block's column (<0: diagonal)
 	int* s_rowPtr = s_loc + a.capBlocks;                                // [maxRows+1]
 	int* s_need = s_rowPtr + a.maxRows + 1;                             // [needMax] global column of each need entry
 	int* s_own = s_need + a.needMax;                                    // [needMax] local own row of a need entry, or -1
+	int* s_diag = s_own + a.needMax;                                    // [maxRows] need index of each own row
 	__shared__ double s_red[PCG2_BLOCK / 32][2];
+	__shared__ double s_w2[PCG2_BLOCK / 32][2];
 	__shared__ double s_bc[2];
 	__shared__ double s_part[PCG2_BLOCK];   // 2*G <= 2*numSMs partial products
 	__shared__ unsigned int s_gen;
@@ -98,6 +103,7 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 	}
 	for (int i = tid; i < nrows * 6; i += PCG2_BLOCK) { s_p[i] = T(0); s_y[i] = T(0); }
 	__syncthreads();
+	for (int i = tid; i < nneed; i += PCG2_BLOCK) if (s_own[i] >= 0) s_diag[s_own[i]] = i;
 	unsigned int gen = s_gen;
 
 	// ---- S1: factor the diagonal blocks of the own rows, b^ = L^-1 b ------------------------------------
@@ -171,6 +177,7 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 #ifdef CUBA_PCG_TIMING
 	long long tacc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 #endif
+	const int nw2 = (2 * G + 31) >> 5;   // warps that reduce the polled partial products
 	if (nbad > 0) status = 2;
 	else {
 		// pass k = -1: w0 = A^ r0 and the first inner products; pass k >= 0: CG iteration k.
@@ -180,15 +187,18 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 				const unsigned int tag = (unsigned int)(k + 1);
 				const int par = (k + 1) & 1;
 				PCG_T(t0);
-				// ---- one polling round per thread: its first w item and one partial product, loads in flight together ----
-				double wv0 = 0, pv = 0;
-				const bool needW = tid < nneed * 6, needP = tid < 2 * G;
-				const unsigned long long* wslot = aa.wFlag;
-				if (needW) { const int c = tid / 6, comp = tid - 6 * c; wslot = aa.wFlag + 2 * ((size_t)par * n6 + 6 * (size_t)s_need[c] + comp); }
+				// ---- one polling round per thread: up to two w items and one partial product, all loads in flight together ----
+				double wv0 = 0, wv1 = 0, pv = 0;
+				const bool needW0 = tid < nneed * 6, needW1 = tid + PCG2_BLOCK < nneed * 6, needP = tid < 2 * G;
+				const unsigned long long* wslot0 = aa.wFlag;
+				const unsigned long long* wslot1 = aa.wFlag;
+				if (needW0) { const int c = tid / 6, comp = tid - 6 * c; wslot0 = aa.wFlag + 2 * ((size_t)par * n6 + 6 * (size_t)s_need[c] + comp); }
+				if (needW1) { const int w1 = tid + PCG2_BLOCK; const int c = w1 / 6, comp = w1 - 6 * c; wslot1 = aa.wFlag + 2 * ((size_t)par * n6 + 6 * (size_t)s_need[c] + comp); }
 				const unsigned long long* pslot = aa.pFlag + 2 * ((size_t)par * 2 * G + (size_t)(needP ? tid : 0));
-				bool gotW = !needW, gotP = !needP, ok = true;
-				for (unsigned int spin = 0; !(gotW && gotP); spin++) {
-					if (!gotW) gotW = ll_try_load(wslot, tag, wv0);
+				bool got0 = !needW0, got1 = !needW1, gotP = !needP, ok = true;
+				for (unsigned int spin = 0; !(got0 && got1 && gotP); spin++) {
+					if (!got0) got0 = ll_try_load(wslot0, tag, wv0);
+					if (!got1) got1 = ll_try_load(wslot1, tag, wv1);
 					if (!gotP) gotP = ll_try_load(pslot, tag, pv);
 					if ((spin & 1023u) == 1023u) {
 						if (*(volatile int*)aa.abortFlag) { ok = false; break; }
@@ -196,21 +206,24 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 					}
 				}
 				PCG_T(t1);
-				if (needP) s_part[tid] = pv;
+				s_part[tid] = needP ? pv : 0.0;
 				if (!ok) s_abort = 1;
 				__syncthreads();
 				PCG_T(t2);
 				PCG_ACC(0, t0, t1); PCG_ACC(1, t1, t2);
-				// ---- scalars: fixed-order sum of everybody's partial inner products of pass k-1 ----
-				if (tid < 32) {
-					double g2 = 0, d2 = 0;
-					for (int i = tid; i < G; i += 32) { g2 += s_part[2 * i]; d2 += s_part[2 * i + 1]; }
-					g2 = warp_sum(g2); d2 = warp_sum(d2);
-					if (tid == 0) { s_bc[0] = g2; s_bc[1] = d2; }
+				// ---- fixed-order sum of everybody's partial products: even slots gamma', odd slots delta ----
+				if (wid < nw2) {
+					double v = s_part[tid];
+					v += __shfl_xor_sync(0xffffffffu, v, 2);
+					v += __shfl_xor_sync(0xffffffffu, v, 4);
+					v += __shfl_xor_sync(0xffffffffu, v, 8);
+					v += __shfl_xor_sync(0xffffffffu, v, 16);
+					if (lane < 2) s_w2[wid][lane] = v;
 				}
 				__syncthreads();
 				if (s_abort) { status = 3; break; }
-				const double gnew = s_bc[0], delta = s_bc[1];
+				double gnew = 0, delta = 0;
+				for (int w = 0; w < nw2; w++) { gnew += s_w2[w][0]; delta += s_w2[w][1]; }
 				if (!(gnew == gnew) || !(delta == delta)) { status = 2; break; }
 				if (k == 0) {
 					gamma0 = gamma = gnew;
@@ -231,8 +244,8 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 				PCG_ACC(2, t2, t3);
 				// ---- advance s, r (all needed columns) and p, y (own rows) in shared memory ----
 				for (int wi = tid; wi < nneed * 6; wi += PCG2_BLOCK) {
-					double wv = wv0;
-					if (wi >= PCG2_BLOCK) {
+					double wv = wi < PCG2_BLOCK ? wv0 : wv1;
+					if (wi >= 2 * PCG2_BLOCK) {
 						const int c = wi / 6, comp = wi - 6 * c;
 						if (!ll_wait(aa.wFlag + 2 * ((size_t)par * n6 + 6 * (size_t)s_need[c] + comp), tag, wv, aa.abortFlag)) { s_abort = 1; wv = 0; }
 					}
@@ -254,53 +267,64 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 				PCG_ACC(3, t3, t4);
 			}
 			PCG_T(t5);
-			// ---- w_{k+1} = A^ r_{k+1} for the own rows (warp per row); publish w and the partial products ----
+			// ---- w_{k+1} = A^ r_{k+1} for the own rows: one block product per thread, then per-row sums ----
 			const unsigned int otag = (unsigned int)(k + 2);
 			const int opar = (k + 2) & 1;
-			double pg = 0, pd = 0;
-			for (int li = wid; li < nrows; li += PCG2_BLOCK / 32) {
-				T acc[6] = { T(0), T(0), T(0), T(0), T(0), T(0) };
-				const int n0 = s_rowPtr[li], n1 = s_rowPtr[li + 1];
-				int selfLoc = -1;
-				for (int n = n0 + lane; n < n1; n += 32) {
+			T wacc = T(0);                                       // thread (row li, component comp) for tid < nrows*6
+			for (int cs = 0; cs < nblkCta; cs += PCG3_CHUNK) {
+				const int n = cs + tid;
+				T y[6] = { T(0), T(0), T(0), T(0), T(0), T(0) };
+				if (n < nblkCta) {
 					const bool cached = n < ncached;
 					const int loc = cached ? s_loc[n] : a.fLocal[blk0 + n];
-					if (loc < 0) { selfLoc = -1 - loc; continue; }
-					const T* rj = s_r + 6 * (size_t)loc;
-					if (cached) {
-						const T* B = s_blk + n;
-						const size_t st = (size_t)a.capBlocks;
+					if (loc >= 0) {
+						const T* rj = s_r + 6 * (size_t)loc;
+						if (cached) {
+							const T* B = s_blk + n;
+							const size_t st = (size_t)a.capBlocks;
 #pragma unroll
-						for (int c = 0; c < 6; c++) {
-							const T rc = rj[c];
+							for (int c = 0; c < 6; c++) {
+								const T rc = rj[c];
 #pragma unroll
-							for (int r = 0; r < 6; r++) acc[r] += B[(c * 6 + r) * st] * rc;
-						}
-					} else {
-						const T* B = a.fHat + 36 * (size_t)(blk0 + n);
+								for (int r = 0; r < 6; r++) y[r] += B[(c * 6 + r) * st] * rc;
+							}
+						} else {
+							const T* B = a.fHat + 36 * (size_t)(blk0 + n);
 #pragma unroll
-						for (int c = 0; c < 6; c++) {
-							const T rc = rj[c];
+							for (int c = 0; c < 6; c++) {
+								const T rc = rj[c];
 #pragma unroll
-							for (int r = 0; r < 6; r++) acc[r] += B[c * 6 + r] * rc;
+								for (int r = 0; r < 6; r++) y[r] += B[c * 6 + r] * rc;
+							}
 						}
 					}
 				}
+				if (cs > 0) __syncthreads();                     // the previous chunk's row sums are done
 #pragma unroll
-				for (int c = 0; c < 6; c++) acc[c] = warp_sum(acc[c]);
-				selfLoc = __reduce_max_sync(0xffffffffu, selfLoc);
-				if (lane < 6) {
-					T wv = acc[0];
-#pragma unroll
-					for (int c = 1; c < 6; c++) if (lane == c) wv = acc[c];
-					const T ri = s_r[6 * (size_t)selfLoc + lane];
-					wv += ri;                                   // A^_ii = I
-					ll_store(aa.wFlag + 2 * ((size_t)opar * n6 + 6 * (size_t)(row0 + li) + lane), (double)wv, otag);
-					pg += (double)ri * (double)ri;
-					pd += (double)wv * (double)ri;
+				for (int r = 0; r < 6; r++) s_c[tid * 6 + r] = y[r];
+				__syncthreads();
+				if (tid < nrows * 6) {                               // nrows*6 <= PCG2_BLOCK (checked on the host)
+					const int li = tid / 6, comp = tid - 6 * li;
+					int n0 = s_rowPtr[li], n1 = s_rowPtr[li + 1];
+					n0 = (n0 > cs ? n0 : cs) - cs;
+					n1 = (n1 < cs + PCG3_CHUNK ? n1 : cs + PCG3_CHUNK) - cs;
+					T s0 = T(0), s1 = T(0);
+					int q = n0;
+					for (; q + 1 < n1; q += 2) { s0 += s_c[q * 6 + comp]; s1 += s_c[(q + 1) * 6 + comp]; }
+					if (q < n1) s0 += s_c[q * 6 + comp];
+					wacc += s0 + s1;
 				}
 			}
 			PCG_T(t6);
+			double pg = 0, pd = 0;
+			if (tid < nrows * 6) {
+				const int li = tid / 6, comp = tid - 6 * li;
+				const T ri = s_r[6 * (size_t)s_diag[li] + comp];
+				const T wv = wacc + ri;                             // A^_ii = I
+				ll_store(aa.wFlag + 2 * ((size_t)opar * n6 + 6 * (size_t)(row0 + li) + comp), (double)wv, otag);
+				pg = (double)ri * (double)ri;
+				pd = (double)wv * (double)ri;
+			}
 			pg = warp_sum(pg); pd = warp_sum(pd);
 			if (lane == 0) { s_red[wid][0] = pg; s_red[wid][1] = pd; }
 			__syncthreads();
@@ -313,7 +337,7 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 			}
 			PCG_T(t8);
 			PCG_ACC(4, t5, t6); PCG_ACC(5, t6, t7); PCG_ACC(6, t7, t8);
-			// s_red is rewritten only after the next pass's __syncthreads
+			// s_red / s_c are rewritten only after the next pass's __syncthreads
 		}
 	}
 	// ---- x = L^-T y for the own rows ----
