@@ -57,7 +57,8 @@ template <typename T>
 struct Pcg3Args {
 	Pcg2Args<T> base;
 	unsigned long long* wFlag;   // [2][6*numP][2]  published w entries
-	unsigned long long* pFlag;   // [2][2*G][2]     published partial inner products
+	unsigned long long* pFlag;   // [2][2*G][2]     published partial inner products (read by CTA 0 only)
+	unsigned long long* tFlag;   // [2][2][2]       their totals, published by CTA 0
 	int* abortFlag;              // zeroed before the launch together with wFlag/pFlag
 	long long* timing;           // [G][8] per-phase clock64 sums (only with -DCUBA_PCG_TIMING)
 };
@@ -92,7 +93,8 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 	const int row0 = a.ctaRow[cta], row1 = a.ctaRow[cta + 1], nrows = row1 - row0;
 	const int need0 = a.needPtr[cta], nneed = a.needPtr[cta + 1] - need0;
 	const int blk0 = a.fRowPtr[row0], nblkCta = a.fRowPtr[row1] - blk0;
-	const int ncached = nblkCta < a.capBlocks ? nblkCta : a.capBlocks;
+	// shared-memory cache for the blocks past the register-resident first PCG2_BLOCK ones
+	const int ncached = nblkCta - PCG2_BLOCK < a.capBlocks ? (nblkCta > PCG2_BLOCK ? nblkCta - PCG2_BLOCK : 0) : a.capBlocks;
 	const size_t n6 = 6 * (size_t)a.numP;
 	if (tid == 0) { s_gen = ld_acquire_u32(&a.bar->gen); s_abort = 0; }
 	for (int i = tid; i <= nrows; i += PCG2_BLOCK) s_rowPtr[i] = a.fRowPtr[row0 + i] - blk0;
@@ -136,7 +138,13 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 	nbad = s_bc[0];
 	__syncthreads();
 
-	// ---- S2: A^_ij = L_i^-1 S_ij L_j^-T for the own rows -> shared memory; r0 of the needed columns --------
+	// ---- S2: A^_ij = L_i^-1 S_ij L_j^-T for the own rows; r0 of the needed columns.
+	//      Block n < PCG2_BLOCK stays in the REGISTERS of thread n for the whole solve (36 fp64), blocks beyond
+	//      that go to shared memory (element-major) and, past its capacity, to the global copy.
+	T breg[36];
+	int myLoc = -1;                                            // need index of the register block's column (<0: diagonal / none)
+#pragma unroll
+	for (int e = 0; e < 36; e++) breg[e] = T(0);
 	for (int n = tid; n < nblkCta; n += PCG2_BLOCK) {
 		const int g = blk0 + n;
 		int lo = 0, hi = nrows - 1;
@@ -158,9 +166,13 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 				for (int k = 0; k <= c; k++) s += tmp[k * 6 + r] * __ldcg(Lj + k * 6 + c);
 				out[c * 6 + r] = s;
 			}
-		if (n < ncached) {
-			for (int e = 0; e < 36; e++) s_blk[(size_t)e * a.capBlocks + n] = out[e];
-			s_loc[n] = a.fLocal[g];
+		if (n < PCG2_BLOCK) {
+#pragma unroll
+			for (int e = 0; e < 36; e++) breg[e] = out[e];
+			myLoc = a.fLocal[g];
+		} else if (n - PCG2_BLOCK < ncached) {
+			for (int e = 0; e < 36; e++) s_blk[(size_t)e * a.capBlocks + (n - PCG2_BLOCK)] = out[e];
+			s_loc[n - PCG2_BLOCK] = a.fLocal[g];
 		} else {
 			for (int e = 0; e < 36; e++) a.fHat[36 * (size_t)g + e] = out[e];
 		}
@@ -189,12 +201,17 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 				PCG_T(t0);
 				// ---- one polling round per thread: up to two w items and one partial product, all loads in flight together ----
 				double wv0 = 0, wv1 = 0, pv = 0;
-				const bool needW0 = tid < nneed * 6, needW1 = tid + PCG2_BLOCK < nneed * 6, needP = tid < 2 * G;
+				const bool needW0 = tid < nneed * 6, needW1 = tid + PCG2_BLOCK < nneed * 6;
+				// the partial products are gathered by CTA 0 only (all-to-all polling of 2G slots by G CTAs costs
+				// ~2.5 us on B200); everybody else waits for the two totals CTA 0 publishes
+				const bool root = cta == 0;
+				const bool needP = root ? (tid < 2 * G) : (tid < 2);
 				const unsigned long long* wslot0 = aa.wFlag;
 				const unsigned long long* wslot1 = aa.wFlag;
 				if (needW0) { const int c = tid / 6, comp = tid - 6 * c; wslot0 = aa.wFlag + 2 * ((size_t)par * n6 + 6 * (size_t)s_need[c] + comp); }
 				if (needW1) { const int w1 = tid + PCG2_BLOCK; const int c = w1 / 6, comp = w1 - 6 * c; wslot1 = aa.wFlag + 2 * ((size_t)par * n6 + 6 * (size_t)s_need[c] + comp); }
-				const unsigned long long* pslot = aa.pFlag + 2 * ((size_t)par * 2 * G + (size_t)(needP ? tid : 0));
+				const unsigned long long* pslot = root ? aa.pFlag + 2 * ((size_t)par * 2 * G + (size_t)(needP ? tid : 0))
+				                                       : aa.tFlag + 2 * ((size_t)par * 2 + (size_t)(needP ? tid : 0));
 				bool got0 = !needW0, got1 = !needW1, gotP = !needP, ok = true;
 				for (unsigned int spin = 0; !(got0 && got1 && gotP); spin++) {
 					if (!got0) got0 = ll_try_load(wslot0, tag, wv0);
@@ -211,19 +228,24 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 				__syncthreads();
 				PCG_T(t2);
 				PCG_ACC(0, t0, t1); PCG_ACC(1, t1, t2);
-				// ---- fixed-order sum of everybody's partial products: even slots gamma', odd slots delta ----
-				if (wid < nw2) {
-					double v = s_part[tid];
-					v += __shfl_xor_sync(0xffffffffu, v, 2);
-					v += __shfl_xor_sync(0xffffffffu, v, 4);
-					v += __shfl_xor_sync(0xffffffffu, v, 8);
-					v += __shfl_xor_sync(0xffffffffu, v, 16);
-					if (lane < 2) s_w2[wid][lane] = v;
-				}
-				__syncthreads();
-				if (s_abort) { status = 3; break; }
 				double gnew = 0, delta = 0;
-				for (int w = 0; w < nw2; w++) { gnew += s_w2[w][0]; delta += s_w2[w][1]; }
+				if (root) {
+					// ---- fixed-order sum of everybody's partial products: even slots gamma', odd slots delta ----
+					if (wid < nw2) {
+						double v = s_part[tid];
+						v += __shfl_xor_sync(0xffffffffu, v, 2);
+						v += __shfl_xor_sync(0xffffffffu, v, 4);
+						v += __shfl_xor_sync(0xffffffffu, v, 8);
+						v += __shfl_xor_sync(0xffffffffu, v, 16);
+						if (lane < 2) s_w2[wid][lane] = v;
+					}
+					__syncthreads();
+					for (int w = 0; w < nw2; w++) { gnew += s_w2[w][0]; delta += s_w2[w][1]; }
+					if (tid < 2) ll_store(aa.tFlag + 2 * ((size_t)par * 2 + tid), tid == 0 ? gnew : delta, tag);
+				} else {
+					gnew = s_part[0]; delta = s_part[1];
+				}
+				if (s_abort) { status = 3; break; }
 				if (!(gnew == gnew) || !(delta == delta)) { status = 2; break; }
 				if (k == 0) {
 					gamma0 = gamma = gnew;
@@ -274,13 +296,24 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 			for (int cs = 0; cs < nblkCta; cs += PCG3_CHUNK) {
 				const int n = cs + tid;
 				T y[6] = { T(0), T(0), T(0), T(0), T(0), T(0) };
-				if (n < nblkCta) {
-					const bool cached = n < ncached;
-					const int loc = cached ? s_loc[n] : a.fLocal[blk0 + n];
+				if (cs == 0) {
+					if (myLoc >= 0) {                                // register-resident block of this thread
+						const T* rj = s_r + 6 * (size_t)myLoc;
+#pragma unroll
+						for (int c = 0; c < 6; c++) {
+							const T rc = rj[c];
+#pragma unroll
+							for (int r = 0; r < 6; r++) y[r] += breg[c * 6 + r] * rc;
+						}
+					}
+				} else if (n < nblkCta) {
+					const int m = n - PCG2_BLOCK;
+					const bool cached = m < ncached;
+					const int loc = cached ? s_loc[m] : a.fLocal[blk0 + n];
 					if (loc >= 0) {
 						const T* rj = s_r + 6 * (size_t)loc;
 						if (cached) {
-							const T* B = s_blk + n;
+							const T* B = s_blk + m;
 							const size_t st = (size_t)a.capBlocks;
 #pragma unroll
 							for (int c = 0; c < 6; c++) {
