@@ -771,7 +771,7 @@ struct Engine : EngineBase {
 		// fixed shared-memory footprint of k_pcg3 (a superset of k_pcg2's): r,s per needed column, p,y per own row, index lists
 		const size_t needBytes = (size_t)needMax * (12 * sizeof(T) + 8) + (size_t)maxRows * (12 * sizeof(T) + 4) + ((size_t)maxRows + 1) * 4
 			+ (size_t)PCG3_CHUNK * 6 * sizeof(T);
-		pcg3Ok = maxRows * 6 <= PCG2_BLOCK && 2 * G <= PCG2_BLOCK;   // k_pcg3 keeps one (row,component) and one partial per thread
+		pcg3Ok = maxRows * 6 <= PCG3_BLOCK && 2 * G <= 2 * PCG3_BLOCK;   // k_pcg3: one (row,component) pair per thread, two partial words per thread
 		size_t cap = budget > needBytes ? (budget - needBytes) / (36 * sizeof(T) + 4) : 0;
 		cap = std::min<size_t>(cap, (size_t)blkMax);
 		pcg2Grid = G; pcg2Cap = (int)cap; pcg2NeedMax = needMax; pcg2MaxRows = maxRows;
@@ -820,7 +820,7 @@ struct Engine : EngineBase {
 #endif
 			CUDA_TRY(cudaMemsetAsync(llFlags.p, 0, sizeof(unsigned long long) * llFlags.n, stream));
 			void* args3[] = { (void*)&b };
-			CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_pcg3<T>, dim3(pcg2Grid), dim3(PCG2_BLOCK), args3, pcg2Smem, stream));
+			CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_pcg3<T>, dim3(pcg2Grid), dim3(PCG3_BLOCK), args3, pcg2Smem, stream));
 			launches++;
 			return CUBA_OK;
 		}

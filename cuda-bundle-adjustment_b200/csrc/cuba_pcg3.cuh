@@ -63,28 +63,32 @@ struct Pcg3Args {
 	long long* timing;           // [G][8] per-phase clock64 sums (only with -DCUBA_PCG_TIMING)
 };
 
-constexpr int PCG3_CHUNK = PCG2_BLOCK;   // block products staged per round (one per thread)
+constexpr int PCG3_BLOCK = 256;                 // threads per CTA: 255 registers each, enough for two 6x6 fp64 blocks
+constexpr int PCG3_BPT = 2;                     // register-resident A^ blocks per thread
+constexpr int PCG3_REGBLK = PCG3_BLOCK * PCG3_BPT;
+constexpr int PCG3_CHUNK = PCG3_REGBLK;         // block products staged per round
+constexpr int PCG3_WPT = 4;                     // polled w items per thread (need list up to 170 columns without extra rounds)
 
 template <typename T>
-__global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
+__global__ void __launch_bounds__(PCG3_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 {
 	const Pcg2Args<T>& a = aa.base;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	T* s_blk = reinterpret_cast<T*>(smem_raw);                          // [36][capBlocks] element-major A^ cache
+	T* s_blk = reinterpret_cast<T*>(smem_raw);                          // [36][capBlocks] element-major cache of the blocks past the registers
 	T* s_r = s_blk + (size_t)a.capBlocks * 36;                          // [needMax][6] residual of the needed columns
 	T* s_s = s_r + (size_t)a.needMax * 6;                               // [needMax][6] s = w + beta s
 	T* s_p = s_s + (size_t)a.needMax * 6;                               // [maxRows][6] search direction of the own rows
 	T* s_y = s_p + (size_t)a.maxRows * 6;                               // [maxRows][6] iterate (hat space) of the own rows
 	T* s_c = s_y + (size_t)a.maxRows * 6;                               // [PCG3_CHUNK][6] block-product contributions
-	int* s_loc = reinterpret_cast<int*>(s_c + (size_t)PCG3_CHUNK * 6);  // [capBlocks]  need index of a block's column (<0: diagonal)
+	int* s_loc = reinterpret_cast<int*>(s_c + (size_t)PCG3_CHUNK * 6);  // [capBlocks]  need index of a cached block's column (<0: diagonal)
 	int* s_rowPtr = s_loc + a.capBlocks;                                // [maxRows+1]
 	int* s_need = s_rowPtr + a.maxRows + 1;                             // [needMax] global column of each need entry
 	int* s_own = s_need + a.needMax;                                    // [needMax] local own row of a need entry, or -1
 	int* s_diag = s_own + a.needMax;                                    // [maxRows] need index of each own row
-	__shared__ double s_red[PCG2_BLOCK / 32][2];
-	__shared__ double s_w2[PCG2_BLOCK / 32][2];
+	__shared__ double s_red[PCG3_BLOCK / 32][2];
+	__shared__ double s_w2[16][2];
 	__shared__ double s_bc[2];
-	__shared__ double s_part[PCG2_BLOCK];   // 2*G <= 2*numSMs partial products
+	__shared__ double s_part[512];          // 2*G <= 512 partial products (CTA 0)
 	__shared__ unsigned int s_gen;
 	__shared__ int s_abort;
 
@@ -93,24 +97,24 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 	const int row0 = a.ctaRow[cta], row1 = a.ctaRow[cta + 1], nrows = row1 - row0;
 	const int need0 = a.needPtr[cta], nneed = a.needPtr[cta + 1] - need0;
 	const int blk0 = a.fRowPtr[row0], nblkCta = a.fRowPtr[row1] - blk0;
-	// shared-memory cache for the blocks past the register-resident first PCG2_BLOCK ones
-	const int ncached = nblkCta - PCG2_BLOCK < a.capBlocks ? (nblkCta > PCG2_BLOCK ? nblkCta - PCG2_BLOCK : 0) : a.capBlocks;
+	// shared-memory cache for the blocks past the register-resident first PCG3_REGBLK ones
+	const int ncached = nblkCta > PCG3_REGBLK ? (nblkCta - PCG3_REGBLK < a.capBlocks ? nblkCta - PCG3_REGBLK : a.capBlocks) : 0;
 	const size_t n6 = 6 * (size_t)a.numP;
 	if (tid == 0) { s_gen = ld_acquire_u32(&a.bar->gen); s_abort = 0; }
-	for (int i = tid; i <= nrows; i += PCG2_BLOCK) s_rowPtr[i] = a.fRowPtr[row0 + i] - blk0;
-	for (int i = tid; i < nneed; i += PCG2_BLOCK) {
+	for (int i = tid; i <= nrows; i += PCG3_BLOCK) s_rowPtr[i] = a.fRowPtr[row0 + i] - blk0;
+	for (int i = tid; i < nneed; i += PCG3_BLOCK) {
 		const int j = a.needCol[need0 + i];
 		s_need[i] = j;
 		s_own[i] = (j >= row0 && j < row1) ? j - row0 : -1;
 	}
-	for (int i = tid; i < nrows * 6; i += PCG2_BLOCK) { s_p[i] = T(0); s_y[i] = T(0); }
+	for (int i = tid; i < nrows * 6; i += PCG3_BLOCK) { s_p[i] = T(0); s_y[i] = T(0); }
 	__syncthreads();
-	for (int i = tid; i < nneed; i += PCG2_BLOCK) if (s_own[i] >= 0) s_diag[s_own[i]] = i;
+	for (int i = tid; i < nneed; i += PCG3_BLOCK) if (s_own[i] >= 0) s_diag[s_own[i]] = i;
 	unsigned int gen = s_gen;
 
 	// ---- S1: factor the diagonal blocks of the own rows, b^ = L^-1 b ------------------------------------
 	int bad = 0;
-	for (int i = row0 + tid; i < row1; i += PCG2_BLOCK) {
+	for (int i = row0 + tid; i < row1; i += PCG3_BLOCK) {
 		int d = -1;
 		for (int n = a.fRowPtr[i]; n < a.fRowPtr[i + 1]; n++) if (a.fColInd[n] == i) { d = n; break; }
 		T Li[36];
@@ -139,45 +143,63 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 	__syncthreads();
 
 	// ---- S2: A^_ij = L_i^-1 S_ij L_j^-T for the own rows; r0 of the needed columns.
-	//      Block n < PCG2_BLOCK stays in the REGISTERS of thread n for the whole solve (36 fp64), blocks beyond
-	//      that go to shared memory (element-major) and, past its capacity, to the global copy.
-	T breg[36];
-	int myLoc = -1;                                            // need index of the register block's column (<0: diagonal / none)
+	//      Blocks n < PCG3_REGBLK stay in REGISTERS for the whole solve (thread n % PCG3_BLOCK, slot n / PCG3_BLOCK),
+	//      later ones go to shared memory (element-major) and, past its capacity, to the global copy.
+	T breg[PCG3_BPT][36];
+	int myLoc[PCG3_BPT];
 #pragma unroll
-	for (int e = 0; e < 36; e++) breg[e] = T(0);
-	for (int n = tid; n < nblkCta; n += PCG2_BLOCK) {
-		const int g = blk0 + n;
-		int lo = 0, hi = nrows - 1;
-		while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_rowPtr[mid] <= n) lo = mid; else hi = mid - 1; }
-		const int i = row0 + lo, j = a.fColInd[g];
-		const T* B = a.fVal + 36 * (size_t)g;
-		const T* Li = a.Linv + 36 * (size_t)i;
-		const T* Lj = a.Linv + 36 * (size_t)j;
-		T tmp[36], out[36];
-		for (int c = 0; c < 6; c++)
-			for (int r = 0; r < 6; r++) {
-				T s = T(0);
-				for (int k = 0; k <= r; k++) s += Li[k * 6 + r] * B[c * 6 + k];
-				tmp[c * 6 + r] = s;
-			}
-		for (int c = 0; c < 6; c++)
-			for (int r = 0; r < 6; r++) {
-				T s = T(0);
-				for (int k = 0; k <= c; k++) s += tmp[k * 6 + r] * __ldcg(Lj + k * 6 + c);
-				out[c * 6 + r] = s;
-			}
-		if (n < PCG2_BLOCK) {
+	for (int u = 0; u < PCG3_BPT; u++) {
+		myLoc[u] = -1;
 #pragma unroll
-			for (int e = 0; e < 36; e++) breg[e] = out[e];
-			myLoc = a.fLocal[g];
-		} else if (n - PCG2_BLOCK < ncached) {
-			for (int e = 0; e < 36; e++) s_blk[(size_t)e * a.capBlocks + (n - PCG2_BLOCK)] = out[e];
-			s_loc[n - PCG2_BLOCK] = a.fLocal[g];
-		} else {
-			for (int e = 0; e < 36; e++) a.fHat[36 * (size_t)g + e] = out[e];
+		for (int e = 0; e < 36; e++) breg[u][e] = T(0);
+	}
+	{
+		auto transform = [&](int n, T* out) {
+			const int g = blk0 + n;
+			int lo = 0, hi = nrows - 1;
+			while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_rowPtr[mid] <= n) lo = mid; else hi = mid - 1; }
+			const int i = row0 + lo, j = a.fColInd[g];
+			const T* B = a.fVal + 36 * (size_t)g;
+			const T* Li = a.Linv + 36 * (size_t)i;
+			const T* Lj = a.Linv + 36 * (size_t)j;
+			T tmp[36];
+			for (int c = 0; c < 6; c++)
+				for (int r = 0; r < 6; r++) {
+					T s = T(0);
+					for (int k = 0; k <= r; k++) s += Li[k * 6 + r] * B[c * 6 + k];
+					tmp[c * 6 + r] = s;
+				}
+			for (int c = 0; c < 6; c++)
+				for (int r = 0; r < 6; r++) {
+					T s = T(0);
+					for (int k = 0; k <= c; k++) s += tmp[k * 6 + r] * __ldcg(Lj + k * 6 + c);
+					out[c * 6 + r] = s;
+				}
+		};
+#pragma unroll
+		for (int u = 0; u < PCG3_BPT; u++) {
+			const int n = u * PCG3_BLOCK + tid;
+			if (n < nblkCta) {
+				T out[36];
+				transform(n, out);
+#pragma unroll
+				for (int e = 0; e < 36; e++) breg[u][e] = out[e];
+				myLoc[u] = a.fLocal[blk0 + n];
+			}
+		}
+		for (int n = PCG3_REGBLK + tid; n < nblkCta; n += PCG3_BLOCK) {
+			T out[36];
+			transform(n, out);
+			const int m = n - PCG3_REGBLK;
+			if (m < ncached) {
+				for (int e = 0; e < 36; e++) s_blk[(size_t)e * a.capBlocks + m] = out[e];
+				s_loc[m] = a.fLocal[blk0 + n];
+			} else {
+				for (int e = 0; e < 36; e++) a.fHat[36 * (size_t)(blk0 + n) + e] = out[e];
+			}
 		}
 	}
-	for (int wi = tid; wi < nneed * 6; wi += PCG2_BLOCK) {
+	for (int wi = tid; wi < nneed * 6; wi += PCG3_BLOCK) {
 		const int c = wi / 6, comp = wi - 6 * c;
 		s_r[wi] = __ldcg(a.R0 + 6 * (size_t)s_need[c] + comp);
 		s_s[wi] = T(0);
@@ -189,7 +211,11 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 #ifdef CUBA_PCG_TIMING
 	long long tacc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 #endif
-	const int nw2 = (2 * G + 31) >> 5;   // warps that reduce the polled partial products
+	const int nw2 = (2 * G + 31) >> 5;       // warps' worth of polled partial products (CTA 0)
+	const bool root = cta == 0;
+	// row sums: tpp threads per (row, component) pair, a power of two
+	int tpp = 1;
+	while (tpp < 8 && nrows * 6 * tpp * 2 <= PCG3_BLOCK) tpp *= 2;
 	if (nbad > 0) status = 2;
 	else {
 		// pass k = -1: w0 = A^ r0 and the first inner products; pass k >= 0: CG iteration k.
@@ -199,31 +225,45 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 				const unsigned int tag = (unsigned int)(k + 1);
 				const int par = (k + 1) & 1;
 				PCG_T(t0);
-				// ---- one polling round per thread: up to two w items and one partial product, all loads in flight together ----
-				double wv0 = 0, wv1 = 0, pv = 0;
-				const bool needW0 = tid < nneed * 6, needW1 = tid + PCG2_BLOCK < nneed * 6;
-				// the partial products are gathered by CTA 0 only (all-to-all polling of 2G slots by G CTAs costs
-				// ~2.5 us on B200); everybody else waits for the two totals CTA 0 publishes
-				const bool root = cta == 0;
-				const bool needP = root ? (tid < 2 * G) : (tid < 2);
-				const unsigned long long* wslot0 = aa.wFlag;
-				const unsigned long long* wslot1 = aa.wFlag;
-				if (needW0) { const int c = tid / 6, comp = tid - 6 * c; wslot0 = aa.wFlag + 2 * ((size_t)par * n6 + 6 * (size_t)s_need[c] + comp); }
-				if (needW1) { const int w1 = tid + PCG2_BLOCK; const int c = w1 / 6, comp = w1 - 6 * c; wslot1 = aa.wFlag + 2 * ((size_t)par * n6 + 6 * (size_t)s_need[c] + comp); }
-				const unsigned long long* pslot = root ? aa.pFlag + 2 * ((size_t)par * 2 * G + (size_t)(needP ? tid : 0))
-				                                       : aa.tFlag + 2 * ((size_t)par * 2 + (size_t)(needP ? tid : 0));
-				bool got0 = !needW0, got1 = !needW1, gotP = !needP, ok = true;
-				for (unsigned int spin = 0; !(got0 && got1 && gotP); spin++) {
-					if (!got0) got0 = ll_try_load(wslot0, tag, wv0);
-					if (!got1) got1 = ll_try_load(wslot1, tag, wv1);
-					if (!gotP) gotP = ll_try_load(pslot, tag, pv);
+				// ---- one polling round per thread: up to PCG3_WPT w items and up to two partial / total words, loads in flight together.
+				//      The partial products are gathered by CTA 0 only (all-to-all polling of 2G slots by G CTAs costs ~2.5 us on
+				//      B200); everybody else waits for the two totals CTA 0 publishes.
+				double wv[PCG3_WPT], pv[2];
+				const unsigned long long* wslot[PCG3_WPT];
+				const unsigned long long* pslot[2];
+				unsigned int pend = 0;                             // bit i: w item i pending; bits 8,9: partial words pending
+#pragma unroll
+				for (int u = 0; u < PCG3_WPT; u++) {
+					const int wi = u * PCG3_BLOCK + tid;
+					wv[u] = 0; wslot[u] = aa.wFlag;
+					if (wi < nneed * 6) {
+						const int c = wi / 6, comp = wi - 6 * c;
+						wslot[u] = aa.wFlag + 2 * ((size_t)par * n6 + 6 * (size_t)s_need[c] + comp);
+						pend |= 1u << u;
+					}
+				}
+#pragma unroll
+				for (int u = 0; u < 2; u++) {
+					const int pi = u * PCG3_BLOCK + tid;
+					pv[u] = 0; pslot[u] = aa.tFlag;
+					if (root ? (pi < 2 * G) : (u == 0 && tid < 2)) {
+						pslot[u] = root ? aa.pFlag + 2 * ((size_t)par * 2 * G + (size_t)pi) : aa.tFlag + 2 * ((size_t)par * 2 + (size_t)pi);
+						pend |= 0x100u << u;
+					}
+				}
+				bool ok = true;
+				for (unsigned int spin = 0; pend; spin++) {
+#pragma unroll
+					for (int u = 0; u < PCG3_WPT; u++) if ((pend >> u) & 1u) { if (ll_try_load(wslot[u], tag, wv[u])) pend &= ~(1u << u); }
+#pragma unroll
+					for (int u = 0; u < 2; u++) if ((pend >> (8 + u)) & 1u) { if (ll_try_load(pslot[u], tag, pv[u])) pend &= ~(0x100u << u); }
 					if ((spin & 1023u) == 1023u) {
 						if (*(volatile int*)aa.abortFlag) { ok = false; break; }
 						if (spin >= PCG3_SPIN_LIMIT) { atomicExch(aa.abortFlag, 1); ok = false; break; }
 					}
 				}
 				PCG_T(t1);
-				s_part[tid] = needP ? pv : 0.0;
+				s_part[tid] = pv[0]; s_part[tid + PCG3_BLOCK] = pv[1];
 				if (!ok) s_abort = 1;
 				__syncthreads();
 				PCG_T(t2);
@@ -231,13 +271,13 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 				double gnew = 0, delta = 0;
 				if (root) {
 					// ---- fixed-order sum of everybody's partial products: even slots gamma', odd slots delta ----
-					if (wid < nw2) {
-						double v = s_part[tid];
+					for (int w = wid; w < nw2; w += PCG3_BLOCK / 32) {
+						double v = s_part[w * 32 + lane];
 						v += __shfl_xor_sync(0xffffffffu, v, 2);
 						v += __shfl_xor_sync(0xffffffffu, v, 4);
 						v += __shfl_xor_sync(0xffffffffu, v, 8);
 						v += __shfl_xor_sync(0xffffffffu, v, 16);
-						if (lane < 2) s_w2[wid][lane] = v;
+						if (lane < 2) s_w2[w][lane] = v;
 					}
 					__syncthreads();
 					for (int w = 0; w < nw2; w++) { gnew += s_w2[w][0]; delta += s_w2[w][1]; }
@@ -265,14 +305,17 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 				PCG_T(t3);
 				PCG_ACC(2, t2, t3);
 				// ---- advance s, r (all needed columns) and p, y (own rows) in shared memory ----
-				for (int wi = tid; wi < nneed * 6; wi += PCG2_BLOCK) {
-					double wv = wi < PCG2_BLOCK ? wv0 : wv1;
-					if (wi >= 2 * PCG2_BLOCK) {
+				for (int wi = tid, u = 0; wi < nneed * 6; wi += PCG3_BLOCK, u++) {
+					double wvv = 0;
+					if (u < PCG3_WPT) {
+#pragma unroll
+						for (int q = 0; q < PCG3_WPT; q++) if (q == u) wvv = wv[q];
+					} else {
 						const int c = wi / 6, comp = wi - 6 * c;
-						if (!ll_wait(aa.wFlag + 2 * ((size_t)par * n6 + 6 * (size_t)s_need[c] + comp), tag, wv, aa.abortFlag)) { s_abort = 1; wv = 0; }
+						if (!ll_wait(aa.wFlag + 2 * ((size_t)par * n6 + 6 * (size_t)s_need[c] + comp), tag, wvv, aa.abortFlag)) { s_abort = 1; wvv = 0; }
 					}
 					const T rold = s_r[wi];
-					const T snew = (T)wv + (T)beta * s_s[wi];
+					const T snew = (T)wvv + (T)beta * s_s[wi];
 					s_s[wi] = snew;
 					s_r[wi] = rold - (T)alpha * snew;
 					const int own = s_own[wi / 6];
@@ -289,74 +332,83 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 				PCG_ACC(3, t3, t4);
 			}
 			PCG_T(t5);
-			// ---- w_{k+1} = A^ r_{k+1} for the own rows: one block product per thread, then per-row sums ----
+			// ---- w_{k+1} = A^ r_{k+1} for the own rows: block products from registers, then per-row sums ----
 			const unsigned int otag = (unsigned int)(k + 2);
 			const int opar = (k + 2) & 1;
-			T wacc = T(0);                                       // thread (row li, component comp) for tid < nrows*6
+			T wacc = T(0);                                       // (row, component) partial of this thread's slice
 			for (int cs = 0; cs < nblkCta; cs += PCG3_CHUNK) {
-				const int n = cs + tid;
-				T y[6] = { T(0), T(0), T(0), T(0), T(0), T(0) };
-				if (cs == 0) {
-					if (myLoc >= 0) {                                // register-resident block of this thread
-						const T* rj = s_r + 6 * (size_t)myLoc;
-#pragma unroll
-						for (int c = 0; c < 6; c++) {
-							const T rc = rj[c];
-#pragma unroll
-							for (int r = 0; r < 6; r++) y[r] += breg[c * 6 + r] * rc;
-						}
-					}
-				} else if (n < nblkCta) {
-					const int m = n - PCG2_BLOCK;
-					const bool cached = m < ncached;
-					const int loc = cached ? s_loc[m] : a.fLocal[blk0 + n];
-					if (loc >= 0) {
-						const T* rj = s_r + 6 * (size_t)loc;
-						if (cached) {
-							const T* B = s_blk + m;
-							const size_t st = (size_t)a.capBlocks;
-#pragma unroll
-							for (int c = 0; c < 6; c++) {
-								const T rc = rj[c];
-#pragma unroll
-								for (int r = 0; r < 6; r++) y[r] += B[(c * 6 + r) * st] * rc;
-							}
-						} else {
-							const T* B = a.fHat + 36 * (size_t)(blk0 + n);
-#pragma unroll
-							for (int c = 0; c < 6; c++) {
-								const T rc = rj[c];
-#pragma unroll
-								for (int r = 0; r < 6; r++) y[r] += B[c * 6 + r] * rc;
-							}
-						}
-					}
-				}
 				if (cs > 0) __syncthreads();                     // the previous chunk's row sums are done
 #pragma unroll
-				for (int r = 0; r < 6; r++) s_c[tid * 6 + r] = y[r];
+				for (int u = 0; u < PCG3_BPT; u++) {
+					const int n = cs + u * PCG3_BLOCK + tid;
+					T y[6] = { T(0), T(0), T(0), T(0), T(0), T(0) };
+					if (cs == 0) {
+						if (myLoc[u] >= 0) {
+							const T* rj = s_r + 6 * (size_t)myLoc[u];
+#pragma unroll
+							for (int c = 0; c < 6; c++) {
+								const T rc = rj[c];
+#pragma unroll
+								for (int r = 0; r < 6; r++) y[r] += breg[u][c * 6 + r] * rc;
+							}
+						}
+					} else if (n < nblkCta) {
+						const int m = n - PCG3_REGBLK;
+						const bool cached = m < ncached;
+						const int loc = cached ? s_loc[m] : a.fLocal[blk0 + n];
+						if (loc >= 0) {
+							const T* rj = s_r + 6 * (size_t)loc;
+							if (cached) {
+								const T* B = s_blk + m;
+								const size_t st = (size_t)a.capBlocks;
+#pragma unroll
+								for (int c = 0; c < 6; c++) {
+									const T rc = rj[c];
+#pragma unroll
+									for (int r = 0; r < 6; r++) y[r] += B[(c * 6 + r) * st] * rc;
+								}
+							} else {
+								const T* B = a.fHat + 36 * (size_t)(blk0 + n);
+#pragma unroll
+								for (int c = 0; c < 6; c++) {
+									const T rc = rj[c];
+#pragma unroll
+									for (int r = 0; r < 6; r++) y[r] += B[c * 6 + r] * rc;
+								}
+							}
+						}
+					}
+					// component-major staging: the row sums read consecutive blocks of one component
+#pragma unroll
+					for (int r = 0; r < 6; r++) s_c[r * PCG3_CHUNK + u * PCG3_BLOCK + tid] = y[r];
+				}
 				__syncthreads();
-				if (tid < nrows * 6) {                               // nrows*6 <= PCG2_BLOCK (checked on the host)
-					const int li = tid / 6, comp = tid - 6 * li;
+				if (tid < nrows * 6 * tpp) {                     // nrows*6 <= PCG3_BLOCK (checked on the host)
+					const int pair = tid / tpp, sub = tid - pair * tpp;
+					const int li = pair / 6, comp = pair - 6 * li;
 					int n0 = s_rowPtr[li], n1 = s_rowPtr[li + 1];
 					n0 = (n0 > cs ? n0 : cs) - cs;
 					n1 = (n1 < cs + PCG3_CHUNK ? n1 : cs + PCG3_CHUNK) - cs;
 					T s0 = T(0), s1 = T(0);
-					int q = n0;
-					for (; q + 1 < n1; q += 2) { s0 += s_c[q * 6 + comp]; s1 += s_c[(q + 1) * 6 + comp]; }
-					if (q < n1) s0 += s_c[q * 6 + comp];
+					const T* col = s_c + comp * PCG3_CHUNK;
+					int q = n0 + sub;
+					for (; q + tpp < n1; q += 2 * tpp) { s0 += col[q]; s1 += col[q + tpp]; }
+					if (q < n1) s0 += col[q];
 					wacc += s0 + s1;
 				}
 			}
+			// combine the tpp slices of each (row, component) pair: lanes of one pair are adjacent
+			for (int o = 1; o < tpp; o <<= 1) wacc += __shfl_xor_sync(0xffffffffu, wacc, o);
 			PCG_T(t6);
 			double pg = 0, pd = 0;
-			if (tid < nrows * 6) {
-				const int li = tid / 6, comp = tid - 6 * li;
+			if (tid < nrows * 6 * tpp && (tid % tpp) == 0) {
+				const int pair = tid / tpp;
+				const int li = pair / 6, comp = pair - 6 * li;
 				const T ri = s_r[6 * (size_t)s_diag[li] + comp];
-				const T wv = wacc + ri;                             // A^_ii = I
-				ll_store(aa.wFlag + 2 * ((size_t)opar * n6 + 6 * (size_t)(row0 + li) + comp), (double)wv, otag);
+				const T wv1 = wacc + ri;                            // A^_ii = I
+				ll_store(aa.wFlag + 2 * ((size_t)opar * n6 + 6 * (size_t)(row0 + li) + comp), (double)wv1, otag);
 				pg = (double)ri * (double)ri;
-				pd = (double)wv * (double)ri;
+				pd = (double)wv1 * (double)ri;
 			}
 			pg = warp_sum(pg); pd = warp_sum(pd);
 			if (lane == 0) { s_red[wid][0] = pg; s_red[wid][1] = pd; }
@@ -364,7 +416,7 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 			PCG_T(t7);
 			if (tid == 0) {
 				double g2 = 0, d2 = 0;
-				for (int w = 0; w < PCG2_BLOCK / 32; w++) { g2 += s_red[w][0]; d2 += s_red[w][1]; }
+				for (int w = 0; w < PCG3_BLOCK / 32; w++) { g2 += s_red[w][0]; d2 += s_red[w][1]; }
 				ll_store(aa.pFlag + 2 * ((size_t)opar * 2 * G + 2 * (size_t)cta), g2, otag);
 				ll_store(aa.pFlag + 2 * ((size_t)opar * 2 * G + 2 * (size_t)cta + 1), d2, otag);
 			}
@@ -375,7 +427,7 @@ __global__ void __launch_bounds__(PCG2_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 	}
 	// ---- x = L^-T y for the own rows ----
 	__syncthreads();
-	for (int wi = tid; wi < nrows * 6; wi += PCG2_BLOCK) {
+	for (int wi = tid; wi < nrows * 6; wi += PCG3_BLOCK) {
 		const int li = wi / 6, r = wi % 6;
 		const T* Li = a.Linv + 36 * (size_t)(row0 + li);
 		T s = T(0);
