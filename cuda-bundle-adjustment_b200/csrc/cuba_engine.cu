@@ -778,7 +778,7 @@ struct Engine : EngineBase {
 		pcg2Smem = (size_t)cap * 36 * sizeof(T) + needBytes + (size_t)cap * 4 + 16;
 		CUDA_TRY(cudaFuncSetAttribute(k_pcg2<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pcg2Smem));
 		CUDA_TRY(cudaFuncSetAttribute(k_pcg3<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pcg2Smem));
-		CUDA_TRY(llFlags.alloc(2 * (2 * 6 * (size_t)numP) + 2 * (2 * 2 * (size_t)G) + 2 * (2 * 2) + 2));
+		CUDA_TRY(llFlags.alloc(2 * (2 * 6 * (size_t)numP) + 2 * (2 * PCG3_REPL * 2 * (size_t)G) + 2));
 		int perSM = 0;
 		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_pcg2<T>, PCG2_BLOCK, pcg2Smem));
 		if (perSM < 1) return fail(CUBA_ERR_CUDA, "k_pcg2 cannot be resident with the requested shared memory");
@@ -811,8 +811,7 @@ struct Engine : EngineBase {
 			b.base = a;
 			b.wFlag = llFlags.p;
 			b.pFlag = llFlags.p + 2 * (2 * 6 * (size_t)S.numP);
-			b.tFlag = b.pFlag + 2 * (2 * 2 * (size_t)pcg2Grid);
-			b.abortFlag = (int*)(b.tFlag + 2 * (2 * 2));
+			b.abortFlag = (int*)(b.pFlag + 2 * (2 * PCG3_REPL * 2 * (size_t)pcg2Grid));
 			b.timing = nullptr;
 #ifdef CUBA_PCG_TIMING
 			CUDA_TRY(pcgTiming.alloc(8 * (size_t)pcg2Grid));

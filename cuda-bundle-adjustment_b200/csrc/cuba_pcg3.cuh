@@ -57,8 +57,7 @@ template <typename T>
 struct Pcg3Args {
 	Pcg2Args<T> base;
 	unsigned long long* wFlag;   // [2][6*numP][2]  published w entries
-	unsigned long long* pFlag;   // [2][2*G][2]     published partial inner products (read by CTA 0 only)
-	unsigned long long* tFlag;   // [2][2][2]       their totals, published by CTA 0
+	unsigned long long* pFlag;   // [2][PCG3_REPL][2*G][2]  published partial inner products (replicated board)
 	int* abortFlag;              // zeroed before the launch together with wFlag/pFlag
 	long long* timing;           // [G][8] per-phase clock64 sums (only with -DCUBA_PCG_TIMING)
 };
@@ -67,6 +66,7 @@ constexpr int PCG3_BLOCK = 256;                 // threads per CTA: 255 register
 constexpr int PCG3_BPT = 2;                     // register-resident A^ blocks per thread
 constexpr int PCG3_REGBLK = PCG3_BLOCK * PCG3_BPT;
 constexpr int PCG3_CHUNK = PCG3_REGBLK;         // block products staged per round
+constexpr int PCG3_REPL = 8;                    // replicas of the partial-product board (readers per L2 line / 8)
 constexpr int PCG3_WPT = 4;                     // polled w items per thread (need list up to 170 columns without extra rounds)
 
 template <typename T>
@@ -212,7 +212,6 @@ __global__ void __launch_bounds__(PCG3_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 	long long tacc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 #endif
 	const int nw2 = (2 * G + 31) >> 5;       // warps' worth of polled partial products (CTA 0)
-	const bool root = cta == 0;
 	// row sums: tpp threads per (row, component) pair, a power of two
 	int tpp = 1;
 	while (tpp < 8 && nrows * 6 * tpp * 2 <= PCG3_BLOCK) tpp *= 2;
@@ -226,8 +225,9 @@ __global__ void __launch_bounds__(PCG3_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 				const int par = (k + 1) & 1;
 				PCG_T(t0);
 				// ---- one polling round per thread: up to PCG3_WPT w items and up to two partial / total words, loads in flight together.
-				//      The partial products are gathered by CTA 0 only (all-to-all polling of 2G slots by G CTAs costs ~2.5 us on
-				//      B200); everybody else waits for the two totals CTA 0 publishes.
+				//      Every CTA sums everybody's partial products itself, in the same fixed order (one L2 hop).  With all G CTAs
+				//      polling the same 2G slots the hot L2 lines cost ~2.5 us per round on B200 (tools/microbench), so the board
+				//      is published in PCG3_REPL replicas and CTA c reads replica c % PCG3_REPL.
 				double wv[PCG3_WPT], pv[2];
 				const unsigned long long* wslot[PCG3_WPT];
 				const unsigned long long* pslot[2];
@@ -245,9 +245,9 @@ __global__ void __launch_bounds__(PCG3_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 #pragma unroll
 				for (int u = 0; u < 2; u++) {
 					const int pi = u * PCG3_BLOCK + tid;
-					pv[u] = 0; pslot[u] = aa.tFlag;
-					if (root ? (pi < 2 * G) : (u == 0 && tid < 2)) {
-						pslot[u] = root ? aa.pFlag + 2 * ((size_t)par * 2 * G + (size_t)pi) : aa.tFlag + 2 * ((size_t)par * 2 + (size_t)pi);
+					pv[u] = 0; pslot[u] = aa.pFlag;
+					if (pi < 2 * G) {
+						pslot[u] = aa.pFlag + 2 * (((size_t)par * PCG3_REPL + (size_t)(cta % PCG3_REPL)) * 2 * G + (size_t)pi);
 						pend |= 0x100u << u;
 					}
 				}
@@ -269,22 +269,17 @@ __global__ void __launch_bounds__(PCG3_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 				PCG_T(t2);
 				PCG_ACC(0, t0, t1); PCG_ACC(1, t1, t2);
 				double gnew = 0, delta = 0;
-				if (root) {
-					// ---- fixed-order sum of everybody's partial products: even slots gamma', odd slots delta ----
-					for (int w = wid; w < nw2; w += PCG3_BLOCK / 32) {
-						double v = s_part[w * 32 + lane];
-						v += __shfl_xor_sync(0xffffffffu, v, 2);
-						v += __shfl_xor_sync(0xffffffffu, v, 4);
-						v += __shfl_xor_sync(0xffffffffu, v, 8);
-						v += __shfl_xor_sync(0xffffffffu, v, 16);
-						if (lane < 2) s_w2[w][lane] = v;
-					}
-					__syncthreads();
-					for (int w = 0; w < nw2; w++) { gnew += s_w2[w][0]; delta += s_w2[w][1]; }
-					if (tid < 2) ll_store(aa.tFlag + 2 * ((size_t)par * 2 + tid), tid == 0 ? gnew : delta, tag);
-				} else {
-					gnew = s_part[0]; delta = s_part[1];
+				// ---- fixed-order sum of everybody's partial products: even slots gamma', odd slots delta ----
+				for (int w = wid; w < nw2; w += PCG3_BLOCK / 32) {
+					double v = s_part[w * 32 + lane];
+					v += __shfl_xor_sync(0xffffffffu, v, 2);
+					v += __shfl_xor_sync(0xffffffffu, v, 4);
+					v += __shfl_xor_sync(0xffffffffu, v, 8);
+					v += __shfl_xor_sync(0xffffffffu, v, 16);
+					if (lane < 2) s_w2[w][lane] = v;
 				}
+				__syncthreads();
+				for (int w = 0; w < nw2; w++) { gnew += s_w2[w][0]; delta += s_w2[w][1]; }
 				if (s_abort) { status = 3; break; }
 				if (!(gnew == gnew) || !(delta == delta)) { status = 2; break; }
 				if (k == 0) {
@@ -414,11 +409,11 @@ __global__ void __launch_bounds__(PCG3_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 			if (lane == 0) { s_red[wid][0] = pg; s_red[wid][1] = pd; }
 			__syncthreads();
 			PCG_T(t7);
-			if (tid == 0) {
-				double g2 = 0, d2 = 0;
-				for (int w = 0; w < PCG3_BLOCK / 32; w++) { g2 += s_red[w][0]; d2 += s_red[w][1]; }
-				ll_store(aa.pFlag + 2 * ((size_t)opar * 2 * G + 2 * (size_t)cta), g2, otag);
-				ll_store(aa.pFlag + 2 * ((size_t)opar * 2 * G + 2 * (size_t)cta + 1), d2, otag);
+			if (tid < 2 * PCG3_REPL) {                           // thread (replica, word): every replica gets both words
+				const int rep = tid >> 1, word = tid & 1;
+				double v = 0;
+				for (int w = 0; w < PCG3_BLOCK / 32; w++) v += s_red[w][word];
+				ll_store(aa.pFlag + 2 * (((size_t)opar * PCG3_REPL + rep) * 2 * G + 2 * (size_t)cta + word), v, otag);
 			}
 			PCG_T(t8);
 			PCG_ACC(4, t5, t6); PCG_ACC(5, t6, t7); PCG_ACC(6, t7, t8);
