@@ -88,7 +88,6 @@ __global__ void __launch_bounds__(PCG3_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 	__shared__ double s_red[PCG3_BLOCK / 32][2];
 	__shared__ double s_w2[16][2];
 	__shared__ double s_bc[2];
-	__shared__ double s_part[512];          // 2*G <= 512 partial products (CTA 0)
 	__shared__ unsigned int s_gen;
 	__shared__ int s_abort;
 
@@ -263,20 +262,20 @@ __global__ void __launch_bounds__(PCG3_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 					}
 				}
 				PCG_T(t1);
-				s_part[tid] = pv[0]; s_part[tid + PCG3_BLOCK] = pv[1];
 				if (!ok) s_abort = 1;
-				__syncthreads();
 				PCG_T(t2);
 				PCG_ACC(0, t0, t1); PCG_ACC(1, t1, t2);
 				double gnew = 0, delta = 0;
-				// ---- fixed-order sum of everybody's partial products: even slots gamma', odd slots delta ----
-				for (int w = wid; w < nw2; w += PCG3_BLOCK / 32) {
-					double v = s_part[w * 32 + lane];
+				// ---- fixed-order sum of everybody's partial products (slot = u*PCG3_BLOCK + tid; even slots gamma', odd delta):
+				//      parity-preserving butterfly inside each warp straight from the polled registers, then 16 warp partials ----
+#pragma unroll
+				for (int u = 0; u < 2; u++) {
+					double v = pv[u];
 					v += __shfl_xor_sync(0xffffffffu, v, 2);
 					v += __shfl_xor_sync(0xffffffffu, v, 4);
 					v += __shfl_xor_sync(0xffffffffu, v, 8);
 					v += __shfl_xor_sync(0xffffffffu, v, 16);
-					if (lane < 2) s_w2[w][lane] = v;
+					if (lane < 2) s_w2[u * (PCG3_BLOCK / 32) + wid][lane] = v;
 				}
 				__syncthreads();
 				for (int w = 0; w < nw2; w++) { gnew += s_w2[w][0]; delta += s_w2[w][1]; }
