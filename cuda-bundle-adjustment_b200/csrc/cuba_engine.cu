@@ -136,6 +136,8 @@ struct Engine : EngineBase {
 	cudaStream_t stream = nullptr;
 	int numSMs = 0;
 	int ntiles = 0, nPoseBlocks = 0, nChiBlocks = 0;
+	int tileSize = TILE;    // 256 or 128, from cfg.reserved[2]
+	int jhMinBlocks = 2;
 	int cur = 0;            // current state buffer
 	bool trialValid = false;
 	// state
@@ -274,6 +276,13 @@ struct Engine : EngineBase {
 		const auto t0 = std::chrono::steady_clock::now();
 		haveProblem = false;
 		hostStructureValid = false;
+		// landmark-tile variant: 0/1 = 256 edges, 2 CTAs/SM; 2 = 256, 3 CTAs/SM; 3 = 128, 4 CTAs/SM; 4 = 128, 6 CTAs/SM
+		switch (cfg.reserved[2]) {
+		case 2: tileSize = 256; jhMinBlocks = 3; break;
+		case 3: tileSize = 128; jhMinBlocks = 4; break;
+		case 4: tileSize = 128; jhMinBlocks = 6; break;
+		default: tileSize = 256; jhMinBlocks = 2; break;
+		}
 		int rc = (cfg.reserved[1] == 1) ? build_on_host(p) : build_on_gpu(p);
 		if (rc) return rc;
 		rc = upload_state(p->q, p->t, p->cam, p->Xw); if (rc) return rc;
@@ -292,7 +301,7 @@ struct Engine : EngineBase {
 	int build_on_host(const cuba_problem* p)
 	{
 		const char* err = "";
-		if (!build_structure(p->Pall, p->numP, p->Lall, p->numL, p->E2, p->idx2, p->E3, p->idx3, rank, world, TILE, S, &err))
+		if (!build_structure(p->Pall, p->numP, p->Lall, p->numL, p->E2, p->idx2, p->E3, p->idx3, rank, world, tileSize, S, &err))
 			return fail(CUBA_ERR_INVALID, err);
 		hostStructureValid = true;
 		const int eL = S.eLocal;
@@ -417,9 +426,9 @@ struct Engine : EngineBase {
 		CUDA_TRY(tilePtr.alloc((size_t)numL + 2));
 		KLAUNCH(k_tile_ptr, numL + 2, lmPtr.p, numL, eL, tilePtr.p);
 		const int tb = std::min(S.lmBeg, numL), te = std::min(S.lmEnd, numL) + (S.lmEnd > numL ? 1 : 0);
-		const int nt = (eL + TILE - 1) / TILE;
+		const int nt = (eL + tileSize - 1) / tileSize;
 		CUDA_TRY(tileLm.alloc((size_t)nt + 1));
-		KLAUNCH(k_tiles, nt + 1, tilePtr.p, tb, te, TILE, nt, tileLm.p);
+		KLAUNCH(k_tiles, nt + 1, tilePtr.p, tb, te, tileSize, nt, tileLm.p);
 		ntiles = nt;
 		// 4. pose-major stream (free poses only)
 		CUDA_TRY(g_k32.alloc(eL)); CUDA_TRY(g_k32S.alloc(eL)); CUDA_TRY(g_pval.alloc(eL)); CUDA_TRY(g_psrc.alloc(eL));
@@ -588,7 +597,10 @@ struct Engine : EngineBase {
 		a.mx = e_mx; a.my = e_my; a.mz = e_mz; a.om = e_om; a.ip = e_ip; a.il = e_il; a.hpl = e_hpl;
 		a.lmPtr = tilePtr; a.tileLm = tileLm; a.numP = S.numP; a.numL = S.numL;
 		a.Hpl = Hpl; a.Hll = Hll; a.bl = bl; a.chiPartial = chiPartial; a.rk = rkParams();
-		k_linearize_landmark<T><<<ntiles, TILE, 0, stream>>>(a);
+		if (tileSize == 128 && jhMinBlocks >= 6) k_linearize_landmark<T, 128, 6><<<ntiles, 128, 0, stream>>>(a);
+		else if (tileSize == 128) k_linearize_landmark<T, 128, 4><<<ntiles, 128, 0, stream>>>(a);
+		else if (jhMinBlocks >= 3) k_linearize_landmark<T, 256, 3><<<ntiles, 256, 0, stream>>>(a);
+		else k_linearize_landmark<T, 256, 2><<<ntiles, 256, 0, stream>>>(a);
 		launches++;
 		CUDA_TRY(cudaGetLastError());
 		return CUBA_OK;
@@ -854,7 +866,8 @@ struct Engine : EngineBase {
 			BacksubArgs<T> a;
 			a.Hpl = Hpl; a.invHll = invHll; a.bl = bl; a.xp = xp; a.ip = e_ip; a.hpl = e_hpl; a.lmPtr = tilePtr; a.tileLm = tileLm;
 			a.numL = S.numL; a.lambda = lambda; a.XwCur = Xw[cur]; a.XwTrial = Xw[cur ^ 1]; a.xl = xl; a.scalePartial = scalePartialL;
-			k_backsub<T><<<ntiles, TILE, 0, stream>>>(a);
+			if (tileSize == 128) k_backsub<T, 128><<<ntiles, 128, 0, stream>>>(a);
+			else k_backsub<T, 256><<<ntiles, 256, 0, stream>>>(a);
 			launches++;
 			CUDA_TRY(cudaGetLastError());
 		}

@@ -19,7 +19,7 @@ namespace cuba_b200 {
 
 namespace cg = cooperative_groups;
 
-constexpr int TILE = 256;        // edges per landmark tile == threads per CTA of the landmark kernels
+constexpr int TILE = 256;        // largest landmark tile (edges per tile == threads per CTA of the landmark kernels)
 constexpr int POSE_BLOCK = 128;  // threads per CTA of the pose pass
 constexpr int SCHUR_BLOCK = 128; // 4 warps, one destination block per warp
 constexpr int PCG_BLOCK = 256;
@@ -107,24 +107,24 @@ struct LinLmArgs {
 	RobustParams rk;
 };
 
-template <typename T>
-__global__ void __launch_bounds__(TILE) k_linearize_landmark(const LinLmArgs<T> a)
+template <typename T, int TL, int MINB>
+__global__ void __launch_bounds__(TL, MINB) k_linearize_landmark(const LinLmArgs<T> a)
 {
-	__shared__ T s_val[9][TILE + 1];
-	__shared__ T s_acc[TILE * 9];
-	__shared__ int s_ptr[TILE + 1];
-	__shared__ double s_red[TILE / 32];
+	__shared__ T s_val[9][TL + 1];
+	__shared__ T s_acc[TL * 9];
+	__shared__ int s_ptr[TL + 1];
+	__shared__ double s_red[TL / 32];
 
 	const int tid = threadIdx.x;
 	const int l0 = a.tileLm[blockIdx.x], l1 = a.tileLm[blockIdx.x + 1];
 	const int nl = l1 - l0;
-	for (int i = tid; i <= nl; i += TILE) s_ptr[i] = a.lmPtr[l0 + i];
-	for (int i = tid; i < nl * 9; i += TILE) s_acc[i] = T(0);
+	for (int i = tid; i <= nl; i += TL) s_ptr[i] = a.lmPtr[l0 + i];
+	for (int i = tid; i < nl * 9; i += TL) s_acc[i] = T(0);
 	__syncthreads();
 	const int e0 = s_ptr[0], e1 = s_ptr[nl];
 
 	double chi = 0;
-	for (int cs = e0; cs < e1; cs += TILE) {
+	for (int cs = e0; cs < e1; cs += TL) {
 		const int e = cs + tid;
 		T v[9];
 #pragma unroll
@@ -183,11 +183,11 @@ __global__ void __launch_bounds__(TILE) k_linearize_landmark(const LinLmArgs<T> 
 #pragma unroll
 		for (int i = 0; i < 9; i++) s_val[i][tid] = v[i];
 		__syncthreads();
-		for (int wi = tid; wi < nl * 9; wi += TILE) {
+		for (int wi = tid; wi < nl * 9; wi += TL) {
 			const int j = wi / 9, cc = wi - 9 * j;
 			int s = s_ptr[j], t = s_ptr[j + 1];
 			s = (s > cs ? s : cs) - cs;
-			t = (t < cs + TILE ? t : cs + TILE) - cs;
+			t = (t < cs + TL ? t : cs + TL) - cs;
 			if (t > s) {
 				T sum = T(0);
 				for (int k = s; k < t; k++) sum += s_val[cc][k];
@@ -199,11 +199,11 @@ __global__ void __launch_bounds__(TILE) k_linearize_landmark(const LinLmArgs<T> 
 	// write Hll (full symmetric 3x3, column-major) and bl of the tile's free landmarks, coalesced
 	{
 		const int map9[9] = { 0, 1, 2, 1, 3, 4, 2, 4, 5 };
-		for (int wi = tid; wi < nl * 9; wi += TILE) {
+		for (int wi = tid; wi < nl * 9; wi += TL) {
 			const int j = wi / 9, cc = wi - 9 * j;
 			if (l0 + j < a.numL) a.Hll[9 * (size_t)l0 + wi] = s_acc[j * 9 + map9[cc]];
 		}
-		for (int wi = tid; wi < nl * 3; wi += TILE) {
+		for (int wi = tid; wi < nl * 3; wi += TL) {
 			const int j = wi / 3, cc = wi - 3 * j;
 			if (l0 + j < a.numL) a.bl[3 * (size_t)l0 + wi] = s_acc[j * 9 + 6 + cc];
 		}
@@ -567,23 +567,23 @@ struct BacksubArgs {
 	double* scalePartial;
 };
 
-template <typename T>
-__global__ void __launch_bounds__(TILE) k_backsub(const BacksubArgs<T> a)
+template <typename T, int TL>
+__global__ void __launch_bounds__(TL) k_backsub(const BacksubArgs<T> a)
 {
-	__shared__ T s_val[3][TILE + 1];
-	__shared__ T s_acc[TILE * 3];
-	__shared__ int s_ptr[TILE + 1];
-	__shared__ double s_red[TILE / 32];
+	__shared__ T s_val[3][TL + 1];
+	__shared__ T s_acc[TL * 3];
+	__shared__ int s_ptr[TL + 1];
+	__shared__ double s_red[TL / 32];
 	const int tid = threadIdx.x;
 	const int l0 = a.tileLm[blockIdx.x], l1 = a.tileLm[blockIdx.x + 1];
 	const int nl = l1 - l0;
 	double sc = 0;
 	if (l0 < a.numL) {   // tiles of fixed landmarks have nothing to solve (uniform branch)
-		for (int i = tid; i <= nl; i += TILE) s_ptr[i] = a.lmPtr[l0 + i];
-		for (int i = tid; i < nl * 3; i += TILE) s_acc[i] = T(0);
+		for (int i = tid; i <= nl; i += TL) s_ptr[i] = a.lmPtr[l0 + i];
+		for (int i = tid; i < nl * 3; i += TL) s_acc[i] = T(0);
 		__syncthreads();
 		const int e0 = s_ptr[0], e1 = s_ptr[nl];
-		for (int cs = e0; cs < e1; cs += TILE) {
+		for (int cs = e0; cs < e1; cs += TL) {
 			const int e = cs + tid;
 			T v0 = T(0), v1 = T(0), v2 = T(0);
 			if (e < e1) {
@@ -603,11 +603,11 @@ __global__ void __launch_bounds__(TILE) k_backsub(const BacksubArgs<T> a)
 			}
 			s_val[0][tid] = v0; s_val[1][tid] = v1; s_val[2][tid] = v2;
 			__syncthreads();
-			for (int wi = tid; wi < nl * 3; wi += TILE) {
+			for (int wi = tid; wi < nl * 3; wi += TL) {
 				const int j = wi / 3, cc = wi - 3 * j;
 				int s = s_ptr[j], t = s_ptr[j + 1];
 				s = (s > cs ? s : cs) - cs;
-				t = (t < cs + TILE ? t : cs + TILE) - cs;
+				t = (t < cs + TL ? t : cs + TL) - cs;
 				if (t > s) {
 					T sum = T(0);
 					for (int k = s; k < t; k++) sum += s_val[cc][k];
@@ -616,7 +616,7 @@ __global__ void __launch_bounds__(TILE) k_backsub(const BacksubArgs<T> a)
 			}
 			__syncthreads();
 		}
-		for (int j = tid; j < nl; j += TILE) {
+		for (int j = tid; j < nl; j += TL) {
 			const int l = l0 + j;
 			if (l < a.numL) {
 				const T* bl = a.bl + 3 * (size_t)l;
