@@ -138,6 +138,8 @@ struct Engine : EngineBase {
 	int ntiles = 0, nPoseBlocks = 0, nChiBlocks = 0;
 	int tileSize = TILE;    // 256 or 128, from cfg.reserved[2]
 	int jhMinBlocks = 2;
+	bool jhV2 = true;       // k_linearize_landmark2 (pose window in smem + TMA bulk store of Hpl)
+	DBuf<int> tilePose0, tilePoseN;
 	int cur = 0;            // current state buffer
 	bool trialValid = false;
 	// state
@@ -281,8 +283,10 @@ struct Engine : EngineBase {
 		case 2: tileSize = 256; jhMinBlocks = 3; break;
 		case 3: tileSize = 128; jhMinBlocks = 4; break;
 		case 4: tileSize = 128; jhMinBlocks = 6; break;
-		default: tileSize = 256; jhMinBlocks = 2; break;
+		case 1: tileSize = 256; jhMinBlocks = 2; break;
+		default: tileSize = JH2_TL; jhMinBlocks = 4; break;
 		}
+		jhV2 = cfg.reserved[2] == 0;
 		int rc = (cfg.reserved[1] == 1) ? build_on_host(p) : build_on_gpu(p);
 		if (rc) return rc;
 		rc = upload_state(p->q, p->t, p->cam, p->Xw); if (rc) return rc;
@@ -522,6 +526,12 @@ struct Engine : EngineBase {
 		if (nP) CUDA_TRY(cudaMemsetAsync(xp.p, 0, sizeof(T) * 6 * nP, stream));
 		if (nP) CUDA_TRY(cudaMemsetAsync(Hpp.p, 0, sizeof(T) * 36 * nP, stream));
 		if (nP) CUDA_TRY(cudaMemsetAsync(bp.p, 0, sizeof(T) * 6 * nP, stream));
+		CUDA_TRY(tilePose0.alloc((size_t)std::max(ntiles, 1))); CUDA_TRY(tilePoseN.alloc((size_t)std::max(ntiles, 1)));
+		if (ntiles > 0) {
+			k_tile_info<<<ntiles, 128, 0, stream>>>(tilePtr.p, tileLm.p, e_ip.p, ntiles, tilePose0.p, tilePoseN.p);
+			launches++;
+			CUDA_TRY(cudaGetLastError());
+		}
 		nPoseBlocks = (S.numP + RED_BLOCK - 1) / RED_BLOCK;
 		nChiBlocks = std::max(1, std::min((eL + RED_BLOCK - 1) / RED_BLOCK, numSMs * 8));
 		CUDA_TRY(chiPartial.alloc((size_t)std::max(ntiles, nChiBlocks) + 1));
@@ -597,7 +607,12 @@ struct Engine : EngineBase {
 		a.mx = e_mx; a.my = e_my; a.mz = e_mz; a.om = e_om; a.ip = e_ip; a.il = e_il; a.hpl = e_hpl;
 		a.lmPtr = tilePtr; a.tileLm = tileLm; a.numP = S.numP; a.numL = S.numL;
 		a.Hpl = Hpl; a.Hll = Hll; a.bl = bl; a.chiPartial = chiPartial; a.rk = rkParams();
-		if (tileSize == 128 && jhMinBlocks >= 6) k_linearize_landmark<T, 128, 6><<<ntiles, 128, 0, stream>>>(a);
+		if (jhV2) {
+			LinLm2Args<T> b;
+			b.base = a; b.tilePose0 = tilePose0; b.tilePoseN = tilePoseN; b.eLocal = S.eLocal; b.nhplLocal = S.nhplLocal;
+			k_linearize_landmark2<T><<<ntiles, JH2_TL, 0, stream>>>(b);
+		}
+		else if (tileSize == 128 && jhMinBlocks >= 6) k_linearize_landmark<T, 128, 6><<<ntiles, 128, 0, stream>>>(a);
 		else if (tileSize == 128) k_linearize_landmark<T, 128, 4><<<ntiles, 128, 0, stream>>>(a);
 		else if (jhMinBlocks >= 3) k_linearize_landmark<T, 256, 3><<<ntiles, 256, 0, stream>>>(a);
 		else k_linearize_landmark<T, 256, 2><<<ntiles, 256, 0, stream>>>(a);

@@ -212,6 +212,178 @@ __global__ void __launch_bounds__(TL, MINB) k_linearize_landmark(const LinLmArgs
 	if (tid == 0) a.chiPartial[blockIdx.x] = tot;
 }
 
+// per-tile pose window [pose0, pose0 + poseN): lets the v2 landmark kernel cache the tile's poses in shared memory
+__global__ void k_tile_info(const int* __restrict__ tilePtr, const int* __restrict__ tileLm, const int* __restrict__ ip, int ntiles, int* pose0, int* poseN)
+{
+	__shared__ int s_min, s_max;
+	if (threadIdx.x == 0) { s_min = 0x7fffffff; s_max = -1; }
+	__syncthreads();
+	const int e0 = tilePtr[tileLm[blockIdx.x]], e1 = tilePtr[tileLm[blockIdx.x + 1]];
+	int mn = 0x7fffffff, mx = -1;
+	for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) { const int p = ip[e] & 0x7fffffff; mn = p < mn ? p : mn; mx = p > mx ? p : mx; }
+	atomicMin(&s_min, mn); atomicMax(&s_max, mx);
+	__syncthreads();
+	if (threadIdx.x == 0) { pose0[blockIdx.x] = s_max >= 0 ? s_min : 0; poseN[blockIdx.x] = s_max >= 0 ? s_max - s_min + 1 : 0; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Landmark pass, second generation (the default).  Same outputs and the same per-landmark summation order as
+// k_linearize_landmark; what changes is how the data moves, because the first version was bound by L1/LSU
+// transactions, not by HBM or the fp64 pipe (profiles/r01_*):
+//   * the poses a tile needs form a short window (edges are sorted by (iL,iP) and a landmark is seen by
+//     neighbouring poses): the window's pose+camera records are staged once in shared memory (coalesced) and
+//     every edge reads them from there instead of gathering 13 doubles through 7 scattered LDG per thread;
+//   * the 144-byte Hpl blocks of a tile are contiguous in HBM (block index = rank of the free-free edge in the
+//     canonical order): each thread writes its block to a shared-memory staging buffer with conflict-free
+//     16-byte stores and ONE bulk-async (TMA) copy per chunk streams the whole range out
+//     (cp.async.bulk.global.shared::cta -> SASS UBLKCP), instead of 9 strided STG.128 per thread.
+// ------------------------------------------------------------------------------------------------
+constexpr int JH2_TL = 128;          // edges per tile / threads per CTA
+constexpr int JH2_POSES = 48;        // pose-window capacity of the shared-memory cache
+constexpr int JH2_PSTRIDE = 17;      // doubles per cached pose record (13 used; odd stride spreads the banks)
+
+template <typename T>
+struct LinLm2Args {
+	LinLmArgs<T> base;
+	const int* tilePose0; const int* tilePoseN;
+	int eLocal, nhplLocal;   // hpl[e] = rank of edge e among the free-free edges (>= 0: has a block, else -1-rank)
+};
+
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+
+template <typename T>
+__global__ void __launch_bounds__(JH2_TL, 4) k_linearize_landmark2(const LinLm2Args<T> aa)
+{
+	const LinLmArgs<T>& a = aa.base;
+	constexpr int TL = JH2_TL;
+	__shared__ __align__(16) T s_hpl[TL * 18];            // Hpl staging of one chunk, global layout
+	__shared__ T s_val[9][TL + 1];
+	__shared__ T s_acc[TL * 9];
+	__shared__ T s_pose[JH2_POSES * JH2_PSTRIDE];
+	__shared__ int s_ptr[TL + 1];
+	__shared__ double s_red[TL / 32];
+
+	const int tid = threadIdx.x;
+	const int l0 = a.tileLm[blockIdx.x], l1 = a.tileLm[blockIdx.x + 1];
+	const int nl = l1 - l0;
+	const int p0 = aa.tilePose0[blockIdx.x], pn = aa.tilePoseN[blockIdx.x];
+	const bool cachePoses = pn <= JH2_POSES;
+	for (int i = tid; i <= nl; i += TL) s_ptr[i] = a.lmPtr[l0 + i];
+	for (int i = tid; i < nl * 9; i += TL) s_acc[i] = T(0);
+	if (cachePoses) {
+		for (int i = tid; i < pn * 16; i += TL) {
+			const int p = i >> 4, k = i & 15;
+			if (k < 13) s_pose[p * JH2_PSTRIDE + k] = k < 8 ? a.pose[8 * (size_t)(p0 + p) + k] : a.cam[8 * (size_t)(p0 + p) + (k - 8)];
+		}
+	}
+	__syncthreads();
+	const int e0 = s_ptr[0], e1 = s_ptr[nl];
+	// rank of an edge position among the free-free edges of the shard (Hpl block index of the next such edge)
+	auto rankAt = [&](int e) { if (e >= aa.eLocal) return aa.nhplLocal; const int x = a.hpl[e]; return x >= 0 ? x : -1 - x; };
+
+	double chi = 0;
+	for (int cs = e0; cs < e1; cs += TL) {
+		const int e = cs + tid;
+		T v[9];
+#pragma unroll
+		for (int i = 0; i < 9; i++) v[i] = T(0);
+		const int cend = cs + TL < e1 ? cs + TL : e1;
+		const int hbase = rankAt(cs), hcount = rankAt(cend) - hbase;   // the chunk's Hpl blocks: [hbase, hbase + hcount)
+		if (e < e1) {
+			const int ipf = a.ip[e];
+			const bool stereo = ipf < 0;
+			const int ip = ipf & 0x7fffffff;
+			const int il = a.il[e];
+			T q[4], t[3], c[5], X[3], m[3], Xc[3], r[3];
+			if (cachePoses) {
+				const T* sp = s_pose + (ip - p0) * JH2_PSTRIDE;
+				q[0] = sp[0]; q[1] = sp[1]; q[2] = sp[2]; q[3] = sp[3]; t[0] = sp[4]; t[1] = sp[5]; t[2] = sp[6];
+				c[0] = sp[8]; c[1] = sp[9]; c[2] = sp[10]; c[3] = sp[11]; c[4] = sp[12];
+			} else load_pose(a.pose, a.cam, ip, q, t, c);
+			load_xw(a.Xw, il, X);
+			m[0] = a.mx[e]; m[1] = a.my[e]; m[2] = stereo ? a.mz[e] : T(0);
+			const T om = a.om[e];
+			edge_residual(q, t, c, X, m, stereo, Xc, r);
+			const T e2 = om * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+			T rho, drho;
+			robust<T>(a.rk.type[stereo ? 1 : 0], (T)a.rk.delta[stereo ? 1 : 0], e2, rho, drho);
+			chi += (double)rho;
+			const T w = om * drho;
+			if (il < a.numL) {
+				T JP[3][6], JL[3][3];
+				edge_jacobians(q, c, Xc, stereo, JP, JL);
+				T wJL[3][3], wr[3];
+#pragma unroll
+				for (int mm = 0; mm < 3; mm++) {
+					wr[mm] = w * r[mm];
+#pragma unroll
+					for (int n = 0; n < 3; n++) wJL[mm][n] = w * JL[mm][n];
+				}
+				v[0] = JL[0][0] * wJL[0][0] + JL[1][0] * wJL[1][0] + JL[2][0] * wJL[2][0];
+				v[1] = JL[0][0] * wJL[0][1] + JL[1][0] * wJL[1][1] + JL[2][0] * wJL[2][1];
+				v[2] = JL[0][0] * wJL[0][2] + JL[1][0] * wJL[1][2] + JL[2][0] * wJL[2][2];
+				v[3] = JL[0][1] * wJL[0][1] + JL[1][1] * wJL[1][1] + JL[2][1] * wJL[2][1];
+				v[4] = JL[0][1] * wJL[0][2] + JL[1][1] * wJL[1][2] + JL[2][1] * wJL[2][2];
+				v[5] = JL[0][2] * wJL[0][2] + JL[1][2] * wJL[1][2] + JL[2][2] * wJL[2][2];
+				v[6] = JL[0][0] * wr[0] + JL[1][0] * wr[1] + JL[2][0] * wr[2];
+				v[7] = JL[0][1] * wr[0] + JL[1][1] * wr[1] + JL[2][1] * wr[2];
+				v[8] = JL[0][2] * wr[0] + JL[1][2] * wr[1] + JL[2][2] * wr[2];
+				const int hp = a.hpl[e];
+				if (hp >= 0) {
+					T* dst = s_hpl + 18 * (hp - hbase);              // blocks of a chunk are consecutive: hp - hbase < TL
+#pragma unroll
+					for (int n = 0; n < 3; n++) {
+#pragma unroll
+						for (int l = 0; l < 6; l += 2) {
+							const T h0 = JP[0][l] * wJL[0][n] + JP[1][l] * wJL[1][n] + JP[2][l] * wJL[2][n];
+							const T h1 = JP[0][l + 1] * wJL[0][n] + JP[1][l + 1] * wJL[1][n] + JP[2][l + 1] * wJL[2][n];
+							st2(dst + n * 6 + l, h0, h1);
+						}
+					}
+				}
+			}
+		}
+#pragma unroll
+		for (int i = 0; i < 9; i++) s_val[i][tid] = v[i];
+		// make the staging writes visible to the async (TMA) proxy before the barrier
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		__syncthreads();
+		// one thread streams the chunk's whole Hpl range out while the others reduce Hll/bl
+		if (tid == 0 && hcount > 0) {
+			const unsigned int bytes = (unsigned int)(hcount * 18 * sizeof(T));
+			T* gdst = a.Hpl + 18 * (size_t)hbase;
+			asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(smem_u32(s_hpl)), "r"(bytes) : "memory");
+			asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+		}
+		for (int wi = tid; wi < nl * 9; wi += TL) {
+			const int j = wi / 9, cc = wi - 9 * j;
+			int s = s_ptr[j], t = s_ptr[j + 1];
+			s = (s > cs ? s : cs) - cs;
+			t = (t < cs + TL ? t : cs + TL) - cs;
+			if (t > s) {
+				T sum = T(0);
+				for (int k = s; k < t; k++) sum += s_val[cc][k];
+				s_acc[wi] += sum;
+			}
+		}
+		if (tid == 0 && hcount > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging buffer may be rewritten
+		__syncthreads();
+	}
+	{
+		const int map9[9] = { 0, 1, 2, 1, 3, 4, 2, 4, 5 };
+		for (int wi = tid; wi < nl * 9; wi += TL) {
+			const int j = wi / 9, cc = wi - 9 * j;
+			if (l0 + j < a.numL) a.Hll[9 * (size_t)l0 + wi] = s_acc[j * 9 + map9[cc]];
+		}
+		for (int wi = tid; wi < nl * 3; wi += TL) {
+			const int j = wi / 3, cc = wi - 3 * j;
+			if (l0 + j < a.numL) a.bl[3 * (size_t)l0 + wi] = s_acc[j * 9 + 6 + cc];
+		}
+	}
+	const double tot = block_sum(chi, s_red);
+	if (tid == 0) a.chiPartial[blockIdx.x] = tot;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Pose pass of the Jacobian+Hessian stage: one CTA per free pose over its pose-major edge list.
 // Each thread accumulates the 21 upper entries of JP^T w JP and the 6 of JP^T w r in registers;

@@ -71,12 +71,16 @@ bool build_structure(int Pall, int numP, int Lall, int numL, int E2, const int32
 	S.hplBase = hplAt(S.lmBeg);
 	S.nhplLocal = hplAt(S.lmEnd) - S.hplBase;
 	S.order.resize(S.eLocal); S.e_ip.resize(S.eLocal); S.e_il.resize(S.eLocal); S.e_hpl.resize(S.eLocal);
-	for (int k = kBeg; k < kEnd; k++) {
-		const int u = orderG[k], e = k - kBeg;
-		S.order[e] = u;
-		S.e_ip[e] = IP(u) | (u >= E2 ? (int)0x80000000u : 0);
-		S.e_il[e] = IL(u);
-		S.e_hpl[e] = S.edge2Hpl[u] >= 0 ? S.edge2Hpl[u] - S.hplBase : -1;
+	{
+		int rankFF = 0;   // rank among the shard's free-free edges; edges without a block store -1-rank
+		for (int k = kBeg; k < kEnd; k++) {
+			const int u = orderG[k], e = k - kBeg;
+			S.order[e] = u;
+			S.e_ip[e] = IP(u) | (u >= E2 ? (int)0x80000000u : 0);
+			S.e_il[e] = IL(u);
+			if (S.edge2Hpl[u] >= 0) { S.e_hpl[e] = S.edge2Hpl[u] - S.hplBase; rankFF = S.e_hpl[e] + 1; }
+			else S.e_hpl[e] = -1 - rankFF;
+		}
 	}
 	S.lmPtr.resize(Lall + 1);
 	for (int l = 0; l <= Lall; l++) S.lmPtr[l] = std::min(std::max(lmPtrG[l], kBeg), kEnd) - kBeg;

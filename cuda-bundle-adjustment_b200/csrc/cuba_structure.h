@@ -40,7 +40,7 @@ struct Structure {
 	std::vector<int> order;       // [eLocal] user edge id of each stream slot
 	std::vector<int> e_ip;        // bit31 = stereo
 	std::vector<int> e_il;
-	std::vector<int> e_hpl;       // LOCAL Hpl index or -1
+	std::vector<int> e_hpl;       // LOCAL Hpl index, or -1-rank (rank among the shard's free-free edges) if no block
 	std::vector<int> lmPtr;       // [Lall+1] stream offsets; landmarks outside the shard have empty runs
 	std::vector<int> tileLm;      // [ntiles+1] first landmark of each tile
 	std::vector<int> hplLm;       // [nhplLocal] landmark of each local Hpl block

@@ -144,7 +144,7 @@ __global__ void k_edge_stream(const unsigned long long* __restrict__ keys, const
 	e_user[e] = u;
 	e_ip[e] = (int)(keys[k] & 0xffffffffu) | (stereo ? (int)0x80000000u : 0);
 	e_il[e] = (int)(keys[k] >> 32);
-	e_hpl[e] = ff[k] ? hplG[k] - hplBase : -1;
+	e_hpl[e] = ff[k] ? hplG[k] - hplBase : -1 - (hplG[k] - hplBase);   // rank among the free-free edges; negative: no block
 	if (!stereo) { mx[e] = (T)meas2[2 * (size_t)u]; my[e] = (T)meas2[2 * (size_t)u + 1]; mz[e] = T(0); om[e] = (T)om2[u]; }
 	else { const size_t s = (size_t)(u - E2); mx[e] = (T)meas3[3 * s]; my[e] = (T)meas3[3 * s + 1]; mz[e] = (T)meas3[3 * s + 2]; om[e] = (T)om3[s]; }
 }
