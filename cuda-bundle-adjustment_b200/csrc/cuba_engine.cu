@@ -286,7 +286,8 @@ struct Engine : EngineBase {
 		case 1: tileSize = 256; jhMinBlocks = 2; break;
 		default: tileSize = JH2_TL; jhMinBlocks = 4; break;
 		}
-		jhV2 = cfg.reserved[2] == 0;
+		jhV2 = cfg.reserved[2] == 0 && sizeof(T) == 8;   // the bulk copy needs 16-byte multiples: 144-byte fp64 blocks qualify, 72-byte fp32 blocks do not
+		if (cfg.reserved[2] == 0 && !jhV2) { tileSize = 128; jhMinBlocks = 6; }
 		int rc = (cfg.reserved[1] == 1) ? build_on_host(p) : build_on_gpu(p);
 		if (rc) return rc;
 		rc = upload_state(p->q, p->t, p->cam, p->Xw); if (rc) return rc;
