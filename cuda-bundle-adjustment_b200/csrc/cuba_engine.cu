@@ -139,6 +139,9 @@ struct Engine : EngineBase {
 	int tileSize = TILE;    // 256 or 128, from cfg.reserved[2]
 	int jhMinBlocks = 2;
 	bool jhV2 = true;       // k_linearize_landmark2 (pose window in smem + TMA bulk store of Hpl)
+	bool jhV3 = true;       // k_linearize_landmark3 (v2 + persistent CTAs with a cp.async double-buffered input stage)
+	int jh3Grid = 0, nChiLin = 0;
+	DBuf<TileInfo> tileInfo;
 	DBuf<int> tilePose0, tilePoseN;
 	int cur = 0;            // current state buffer
 	bool trialValid = false;
@@ -286,8 +289,11 @@ struct Engine : EngineBase {
 		case 1: tileSize = 256; jhMinBlocks = 2; break;
 		default: tileSize = JH2_TL; jhMinBlocks = 4; break;
 		}
-		jhV2 = cfg.reserved[2] == 0 && sizeof(T) == 8;   // the bulk copy needs 16-byte multiples: 144-byte fp64 blocks qualify, 72-byte fp32 blocks do not
-		if (cfg.reserved[2] == 0 && !jhV2) { tileSize = 128; jhMinBlocks = 6; }
+		jhV3 = cfg.reserved[2] == 0 && sizeof(T) == 8;
+		jhV2 = (cfg.reserved[2] == 5 || cfg.reserved[2] == 0) && sizeof(T) == 8 && !jhV3;
+		if (cfg.reserved[2] == 5) { tileSize = JH2_TL; jhMinBlocks = 4; }
+		// (the bulk copy needs 16-byte multiples: 144-byte fp64 blocks qualify, 72-byte fp32 blocks do not)
+		if (cfg.reserved[2] == 0 && sizeof(T) != 8) { tileSize = 128; jhMinBlocks = 6; }
 		int rc = (cfg.reserved[1] == 1) ? build_on_host(p) : build_on_gpu(p);
 		if (rc) return rc;
 		rc = upload_state(p->q, p->t, p->cam, p->Xw); if (rc) return rc;
@@ -431,9 +437,11 @@ struct Engine : EngineBase {
 		CUDA_TRY(tilePtr.alloc((size_t)numL + 2));
 		KLAUNCH(k_tile_ptr, numL + 2, lmPtr.p, numL, eL, tilePtr.p);
 		const int tb = std::min(S.lmBeg, numL), te = std::min(S.lmEnd, numL) + (S.lmEnd > numL ? 1 : 0);
-		const int nt = (eL + tileSize - 1) / tileSize;
+		// windows a little shorter than the CTA so that the tail of a tile's last landmark usually still fits one chunk
+		const int window = tileSize == 128 ? JH3_WINDOW : tileSize - 16;
+		const int nt = (eL + window - 1) / window;
 		CUDA_TRY(tileLm.alloc((size_t)nt + 1));
-		KLAUNCH(k_tiles, nt + 1, tilePtr.p, tb, te, tileSize, nt, tileLm.p);
+		KLAUNCH(k_tiles, nt + 1, tilePtr.p, tb, te, window, nt, tileLm.p);
 		ntiles = nt;
 		// 4. pose-major stream (free poses only)
 		CUDA_TRY(g_k32.alloc(eL)); CUDA_TRY(g_k32S.alloc(eL)); CUDA_TRY(g_pval.alloc(eL)); CUDA_TRY(g_psrc.alloc(eL));
@@ -532,7 +540,14 @@ struct Engine : EngineBase {
 			k_tile_info<<<ntiles, 128, 0, stream>>>(tilePtr.p, tileLm.p, e_ip.p, ntiles, tilePose0.p, tilePoseN.p);
 			launches++;
 			CUDA_TRY(cudaGetLastError());
+			CUDA_TRY(tileInfo.alloc((size_t)ntiles));
+			k_tile_info3<<<ntiles, 128, 0, stream>>>(tilePtr.p, tileLm.p, e_ip.p, e_hpl.p, S.eLocal, S.nhplLocal, ntiles, tileInfo.p);
+			launches++;
+			CUDA_TRY(cudaGetLastError());
 		}
+		CUDA_TRY(cudaFuncSetAttribute(k_linearize_landmark3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Jh3Smem)));
+		jh3Grid = std::max(1, std::min(ntiles, numSMs * 3));
+		nChiLin = jhV3 ? jh3Grid : ntiles;
 		nPoseBlocks = (S.numP + RED_BLOCK - 1) / RED_BLOCK;
 		nChiBlocks = std::max(1, std::min((eL + RED_BLOCK - 1) / RED_BLOCK, numSMs * 8));
 		CUDA_TRY(chiPartial.alloc((size_t)std::max(ntiles, nChiBlocks) + 1));
@@ -608,7 +623,14 @@ struct Engine : EngineBase {
 		a.mx = e_mx; a.my = e_my; a.mz = e_mz; a.om = e_om; a.ip = e_ip; a.il = e_il; a.hpl = e_hpl;
 		a.lmPtr = tilePtr; a.tileLm = tileLm; a.numP = S.numP; a.numL = S.numL;
 		a.Hpl = Hpl; a.Hll = Hll; a.bl = bl; a.chiPartial = chiPartial; a.rk = rkParams();
-		if (jhV2) {
+		if (jhV3) {
+			if constexpr (sizeof(T) == 8) {
+				LinLm3Args b;
+				b.base = a; b.info = tileInfo; b.ntiles = ntiles;
+				k_linearize_landmark3<<<jh3Grid, JH3_TL, sizeof(Jh3Smem), stream>>>(b);
+			}
+		}
+		else if (jhV2) {
 			LinLm2Args<T> b;
 			b.base = a; b.tilePose0 = tilePose0; b.tilePoseN = tilePoseN; b.eLocal = S.eLocal; b.nhplLocal = S.nhplLocal;
 			k_linearize_landmark2<T><<<ntiles, JH2_TL, 0, stream>>>(b);
@@ -661,7 +683,7 @@ struct Engine : EngineBase {
 				rc = allreduce(Hpp.p, 36 * (size_t)S.numP, true); if (rc) return rc;
 				rc = allreduce(bp.p, 6 * (size_t)S.numP, true); if (rc) return rc;
 			}
-			rc = launch_sum(chiPartial, ntiles, nullptr, 0, nullptr, 0, 0); if (rc) return rc;
+			rc = launch_sum(chiPartial, ntiles > 0 ? nChiLin : 0, nullptr, 0, nullptr, 0, 0); if (rc) return rc;
 			if (world > 1) { rc = allreduce(&dScal.p->v[0], 1, false); if (rc) return rc; }
 		}
 		int rc = fetchScalars(); if (rc) return rc;

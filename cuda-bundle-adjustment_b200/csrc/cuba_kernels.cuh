@@ -385,6 +385,244 @@ __global__ void __launch_bounds__(JH2_TL, 4) k_linearize_landmark2(const LinLm2A
 }
 
 // ------------------------------------------------------------------------------------------------
+// Landmark pass, third generation: k_linearize_landmark2 made latency tolerant.
+// ncu on v1/v2 (profiles/): fp64 pipe 13 %, LSU 14 %, DRAM 13 % -- the warps sit on long-scoreboard stalls,
+// i.e. on a chain of dependent global loads (tile -> run pointers -> edge stream -> landmark gather) with only
+// 16 warps per SM to hide it.  Here a persistent CTA walks tiles b, b+G, b+2G, ... and every global input of
+// tile i+1 -- edge stream, run pointers, pose window, landmark window (the landmarks of a tile are a contiguous
+// range, so nothing is gathered by index any more) -- is copied into the other half of a double-buffered
+// shared-memory stage with cp.async (LDGSTS) while tile i is being computed from shared memory.
+// Output path unchanged: Hpl through the staging buffer + one TMA bulk store per tile, Hll/bl coalesced.
+// ------------------------------------------------------------------------------------------------
+struct TileInfo { int l0, l1, e0, e1, pose0, poseN, h0, h1; };   // h0/h1: Hpl block index at e0 / e1
+
+__global__ void k_tile_info3(const int* __restrict__ tilePtr, const int* __restrict__ tileLm, const int* __restrict__ ip,
+	const int* __restrict__ hpl, int eLocal, int nhplLocal, int ntiles, TileInfo* info)
+{
+	__shared__ int s_min, s_max;
+	if (threadIdx.x == 0) { s_min = 0x7fffffff; s_max = -1; }
+	__syncthreads();
+	const int l0 = tileLm[blockIdx.x], l1 = tileLm[blockIdx.x + 1];
+	const int e0 = tilePtr[l0], e1 = tilePtr[l1];
+	int mn = 0x7fffffff, mx = -1;
+	for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) { const int p = ip[e] & 0x7fffffff; mn = p < mn ? p : mn; mx = p > mx ? p : mx; }
+	atomicMin(&s_min, mn); atomicMax(&s_max, mx);
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		auto rankAt = [&](int e) { if (e >= eLocal) return nhplLocal; const int x = hpl[e]; return x >= 0 ? x : -1 - x; };
+		TileInfo ti;
+		ti.l0 = l0; ti.l1 = l1; ti.e0 = e0; ti.e1 = e1;
+		ti.pose0 = s_max >= 0 ? s_min : 0; ti.poseN = s_max >= 0 ? s_max - s_min + 1 : 0;
+		ti.h0 = rankAt(e0); ti.h1 = rankAt(e1);
+		info[blockIdx.x] = ti;
+	}
+}
+
+__device__ __forceinline__ void cp_async8(void* smem, const void* gptr)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem_u32(smem)), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gptr)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(smem)), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gptr)
+{
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(smem)), "l"(gptr) : "memory");
+}
+
+constexpr int JH3_TL = 128;          // threads per CTA == edges of a tile's first chunk
+constexpr int JH3_WINDOW = 112;      // edges per tile window (structure builder): leaves 16 slots for the last landmark's tail
+constexpr int JH3_POSES = 48;
+
+struct alignas(16) Jh3Stage {
+	double xw[JH3_TL * 4];            // landmark window (32-byte records)
+	double mx[JH3_TL], my[JH3_TL], mz[JH3_TL], om[JH3_TL];
+	double pose[JH3_POSES * JH2_PSTRIDE];
+	int ip[JH3_TL], il[JH3_TL], hpl[JH3_TL];
+	int ptr[JH3_TL + 4];
+};
+
+struct alignas(16) Jh3Smem {
+	Jh3Stage stage[2];
+	double hpl[JH3_TL * 18];
+	double val[9][JH3_TL + 1];
+	double acc[JH3_TL * 9];
+	double red[JH3_TL / 32];
+};
+
+struct LinLm3Args {
+	LinLmArgs<double> base;
+	const TileInfo* info;
+	int ntiles;
+};
+
+__device__ __forceinline__ void jh3_issue_loads(const LinLmArgs<double>& a, const TileInfo& ti, Jh3Stage& st, int tid)
+{
+	const int ne = ti.e1 - ti.e0, nl = ti.l1 - ti.l0;
+	if (tid < ne) {                                   // first chunk of the edge stream (tid < JH3_TL)
+		const size_t e = (size_t)ti.e0 + tid;
+		cp_async8(&st.mx[tid], a.mx + e); cp_async8(&st.my[tid], a.my + e); cp_async8(&st.mz[tid], a.mz + e); cp_async8(&st.om[tid], a.om + e);
+		cp_async4(&st.ip[tid], a.ip + e); cp_async4(&st.il[tid], a.il + e); cp_async4(&st.hpl[tid], a.hpl + e);
+	}
+	for (int i = tid; i <= nl; i += JH3_TL) cp_async4(&st.ptr[i], a.lmPtr + ti.l0 + i);
+	// landmark window: rows l0 .. l0+nl-1 of Xw (the pseudo-landmark of the fixed ones maps to a real row, harmless)
+	for (int i = tid; i < nl * 2; i += JH3_TL) cp_async16(&st.xw[2 * i], a.Xw + 4 * (size_t)ti.l0 + 2 * i);
+	if (ti.poseN <= JH3_POSES) {
+		for (int i = tid; i < ti.poseN * 16; i += JH3_TL) {
+			const int p = i >> 4, k = i & 15;
+			if (k < 13) cp_async8(&st.pose[p * JH2_PSTRIDE + k], k < 8 ? a.pose + 8 * (size_t)(ti.pose0 + p) + k : a.cam + 8 * (size_t)(ti.pose0 + p) + (k - 8));
+		}
+	}
+}
+
+__global__ void __launch_bounds__(JH3_TL, 3) k_linearize_landmark3(const LinLm3Args aa)
+{
+	typedef double T;
+	const LinLmArgs<T>& a = aa.base;
+	constexpr int TL = JH3_TL;
+	extern __shared__ __align__(16) unsigned char jh3_smem_raw[];
+	Jh3Smem& sm = *reinterpret_cast<Jh3Smem*>(jh3_smem_raw);
+	Jh3Stage* s_stage = sm.stage;
+	T* s_hpl = sm.hpl;
+	T (*s_val)[JH3_TL + 1] = sm.val;
+	T* s_acc = sm.acc;
+	double* s_red = sm.red;
+
+	const int tid = threadIdx.x, G = gridDim.x;
+	int t = blockIdx.x;
+	TileInfo cur = {}, nxt = {};
+	if (t < aa.ntiles) cur = aa.info[t];
+	if (t + G < aa.ntiles) nxt = aa.info[t + G];
+	if (t < aa.ntiles) jh3_issue_loads(a, cur, s_stage[0], tid);
+	asm volatile("cp.async.commit_group;" ::: "memory");
+
+	double chi = 0;
+	for (int it = 0; t < aa.ntiles; t += G, it++) {
+		Jh3Stage& st = s_stage[it & 1];
+		// prefetch the next tile into the other stage and the descriptor after it into registers
+		if (t + G < aa.ntiles) jh3_issue_loads(a, nxt, s_stage[(it & 1) ^ 1], tid);
+		asm volatile("cp.async.commit_group;" ::: "memory");
+		TileInfo nn = {};
+		if (t + 2 * G < aa.ntiles) nn = aa.info[t + 2 * G];
+		asm volatile("cp.async.wait_group 1;" ::: "memory");      // everything but the group just committed has landed
+		__syncthreads();
+
+		const int l0 = cur.l0, nl = cur.l1 - cur.l0, e0 = cur.e0, e1 = cur.e1, p0 = cur.pose0;
+		const bool cachePoses = cur.poseN <= JH3_POSES;
+		for (int i = tid; i < nl * 9; i += TL) s_acc[i] = T(0);
+		// Hpl blocks of the tile: [h0, h1); per chunk they are consecutive
+		int hdone = 0;
+		for (int cs = e0; cs < e1; cs += TL) {
+			const bool first = cs == e0;
+			const int e = cs + tid;
+			const int cend = cs + TL < e1 ? cs + TL : e1;
+			T v[9];
+#pragma unroll
+			for (int i = 0; i < 9; i++) v[i] = T(0);
+			// number of Hpl blocks in this chunk: count of hpl >= 0
+			int hp = -1;
+			if (e < e1) {
+				const int ipf = first ? st.ip[tid] : a.ip[e];
+				const bool stereo = ipf < 0;
+				const int ip = ipf & 0x7fffffff;
+				const int il = first ? st.il[tid] : a.il[e];
+				hp = first ? st.hpl[tid] : a.hpl[e];
+				T q[4], tt[3], c[5], X[3], m[3], Xc[3], r[3];
+				if (cachePoses) {
+					const T* sp = st.pose + (ip - p0) * JH2_PSTRIDE;
+					q[0] = sp[0]; q[1] = sp[1]; q[2] = sp[2]; q[3] = sp[3]; tt[0] = sp[4]; tt[1] = sp[5]; tt[2] = sp[6];
+					c[0] = sp[8]; c[1] = sp[9]; c[2] = sp[10]; c[3] = sp[11]; c[4] = sp[12];
+				} else load_pose(a.pose, a.cam, ip, q, tt, c);
+				if (il < a.numL && il - l0 < nl) { const T* sx = st.xw + 4 * (il - l0); X[0] = sx[0]; X[1] = sx[1]; X[2] = sx[2]; }
+				else load_xw(a.Xw, il, X);
+				if (first) { m[0] = st.mx[tid]; m[1] = st.my[tid]; m[2] = stereo ? st.mz[tid] : T(0); }
+				else { m[0] = a.mx[e]; m[1] = a.my[e]; m[2] = stereo ? a.mz[e] : T(0); }
+				const T om = first ? st.om[tid] : a.om[e];
+				edge_residual(q, tt, c, X, m, stereo, Xc, r);
+				const T e2 = om * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+				T rho, drho;
+				robust<T>(a.rk.type[stereo ? 1 : 0], (T)a.rk.delta[stereo ? 1 : 0], e2, rho, drho);
+				chi += (double)rho;
+				const T w = om * drho;
+				if (il < a.numL) {
+					T JP[3][6], JL[3][3];
+					edge_jacobians(q, c, Xc, stereo, JP, JL);
+					T wJL[3][3], wr[3];
+#pragma unroll
+					for (int mm = 0; mm < 3; mm++) {
+						wr[mm] = w * r[mm];
+#pragma unroll
+						for (int n = 0; n < 3; n++) wJL[mm][n] = w * JL[mm][n];
+					}
+					v[0] = JL[0][0] * wJL[0][0] + JL[1][0] * wJL[1][0] + JL[2][0] * wJL[2][0];
+					v[1] = JL[0][0] * wJL[0][1] + JL[1][0] * wJL[1][1] + JL[2][0] * wJL[2][1];
+					v[2] = JL[0][0] * wJL[0][2] + JL[1][0] * wJL[1][2] + JL[2][0] * wJL[2][2];
+					v[3] = JL[0][1] * wJL[0][1] + JL[1][1] * wJL[1][1] + JL[2][1] * wJL[2][1];
+					v[4] = JL[0][1] * wJL[0][2] + JL[1][1] * wJL[1][2] + JL[2][1] * wJL[2][2];
+					v[5] = JL[0][2] * wJL[0][2] + JL[1][2] * wJL[1][2] + JL[2][2] * wJL[2][2];
+					v[6] = JL[0][0] * wr[0] + JL[1][0] * wr[1] + JL[2][0] * wr[2];
+					v[7] = JL[0][1] * wr[0] + JL[1][1] * wr[1] + JL[2][1] * wr[2];
+					v[8] = JL[0][2] * wr[0] + JL[1][2] * wr[1] + JL[2][2] * wr[2];
+					if (hp >= 0) {
+						T* dst = s_hpl + 18 * (hp - cur.h0 - hdone);    // consecutive within the chunk
+#pragma unroll
+						for (int n = 0; n < 3; n++) {
+#pragma unroll
+							for (int l = 0; l < 6; l += 2) {
+								const T h0 = JP[0][l] * wJL[0][n] + JP[1][l] * wJL[1][n] + JP[2][l] * wJL[2][n];
+								const T h1 = JP[0][l + 1] * wJL[0][n] + JP[1][l + 1] * wJL[1][n] + JP[2][l + 1] * wJL[2][n];
+								st2(dst + n * 6 + l, h0, h1);
+							}
+						}
+					}
+				}
+			}
+#pragma unroll
+			for (int i = 0; i < 9; i++) s_val[i][tid] = v[i];
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			const int hcount = __syncthreads_count(hp >= 0);        // blocks written by this chunk (also the barrier)
+			if (tid == 0 && hcount > 0) {
+				const unsigned int bytes = (unsigned int)(hcount * 18 * sizeof(T));
+				T* gdst = a.Hpl + 18 * (size_t)(cur.h0 + hdone);
+				asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(smem_u32(s_hpl)), "r"(bytes) : "memory");
+				asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+			}
+			for (int wi = tid; wi < nl * 9; wi += TL) {
+				const int j = wi / 9, cc = wi - 9 * j;
+				int s = st.ptr[j], tE = st.ptr[j + 1];
+				s = (s > cs ? s : cs) - cs;
+				tE = (tE < cend ? tE : cend) - cs;
+				if (tE > s) {
+					T sum = T(0);
+					for (int k = s; k < tE; k++) sum += s_val[cc][k];
+					s_acc[wi] += sum;
+				}
+			}
+			if (tid == 0 && hcount > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+			hdone += hcount;
+			__syncthreads();
+		}
+		{
+			const int map9[9] = { 0, 1, 2, 1, 3, 4, 2, 4, 5 };
+			for (int wi = tid; wi < nl * 9; wi += TL) {
+				const int j = wi / 9, cc = wi - 9 * j;
+				if (l0 + j < a.numL) a.Hll[9 * (size_t)l0 + wi] = s_acc[j * 9 + map9[cc]];
+			}
+			for (int wi = tid; wi < nl * 3; wi += TL) {
+				const int j = wi / 3, cc = wi - 3 * j;
+				if (l0 + j < a.numL) a.bl[3 * (size_t)l0 + wi] = s_acc[j * 9 + 6 + cc];
+			}
+		}
+		__syncthreads();      // s_acc / stage reuse
+		cur = nxt; nxt = nn;
+	}
+	asm volatile("cp.async.wait_group 0;" ::: "memory");
+	const double tot = block_sum(chi, s_red);
+	if (tid == 0) a.chiPartial[blockIdx.x] = tot;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Pose pass of the Jacobian+Hessian stage: one CTA per free pose over its pose-major edge list.
 // Each thread accumulates the 21 upper entries of JP^T w JP and the 6 of JP^T w r in registers;
 // one fixed-order block reduction per pose -- no atomics.  (reference cu:815-824)

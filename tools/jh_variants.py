@@ -9,7 +9,7 @@ import __graft_entry__ as ge  # noqa: E402
 pkg = ge.load_package()
 for workload in sys.argv[1:] or ["kitti00_shaped"]:
     prob = pkg.graphio.flatten(pkg.synth.make_config(workload))
-    for v in (0, 1, 4):
+    for v in (0, 5, 4):
         eng = pkg.Engine(device=0, jh_variant=v)
         eng.initialize(prob)
         chi = eng.linearize()
