@@ -546,7 +546,7 @@ struct Engine : EngineBase {
 			CUDA_TRY(cudaGetLastError());
 		}
 		CUDA_TRY(cudaFuncSetAttribute(k_linearize_landmark3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Jh3Smem)));
-		jh3Grid = std::max(1, std::min(ntiles, numSMs * 3));
+		jh3Grid = std::max(1, std::min(ntiles, numSMs * 4));
 		nChiLin = jhV3 ? jh3Grid : ntiles;
 		nPoseBlocks = (S.numP + RED_BLOCK - 1) / RED_BLOCK;
 		nChiBlocks = std::max(1, std::min((eL + RED_BLOCK - 1) / RED_BLOCK, numSMs * 8));

@@ -433,12 +433,13 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gptr)
 
 constexpr int JH3_TL = 128;          // threads per CTA == edges of a tile's first chunk
 constexpr int JH3_WINDOW = 112;      // edges per tile window (structure builder): leaves 16 slots for the last landmark's tail
-constexpr int JH3_POSES = 48;
+constexpr int JH3_POSES = 24;         // pose-window capacity of a stage (wider windows fall back to global gathers)
+constexpr int JH3_PSTRIDE = 18;       // doubles per staged pose record: 16-byte granules, rows shifted by 4 banks
 
 struct alignas(16) Jh3Stage {
 	double xw[JH3_TL * 4];            // landmark window (32-byte records)
 	double mx[JH3_TL], my[JH3_TL], mz[JH3_TL], om[JH3_TL];
-	double pose[JH3_POSES * JH2_PSTRIDE];
+	double pose[JH3_POSES * JH3_PSTRIDE];
 	int ip[JH3_TL], il[JH3_TL], hpl[JH3_TL];
 	int ptr[JH3_TL + 4];
 };
@@ -447,7 +448,6 @@ struct alignas(16) Jh3Smem {
 	Jh3Stage stage[2];
 	double hpl[JH3_TL * 18];
 	double val[9][JH3_TL + 1];
-	double acc[JH3_TL * 9];
 	double red[JH3_TL / 32];
 };
 
@@ -469,14 +469,15 @@ __device__ __forceinline__ void jh3_issue_loads(const LinLmArgs<double>& a, cons
 	// landmark window: rows l0 .. l0+nl-1 of Xw (the pseudo-landmark of the fixed ones maps to a real row, harmless)
 	for (int i = tid; i < nl * 2; i += JH3_TL) cp_async16(&st.xw[2 * i], a.Xw + 4 * (size_t)ti.l0 + 2 * i);
 	if (ti.poseN <= JH3_POSES) {
-		for (int i = tid; i < ti.poseN * 16; i += JH3_TL) {
-			const int p = i >> 4, k = i & 15;
-			if (k < 13) cp_async8(&st.pose[p * JH2_PSTRIDE + k], k < 8 ? a.pose + 8 * (size_t)(ti.pose0 + p) + k : a.cam + 8 * (size_t)(ti.pose0 + p) + (k - 8));
+		// 7 16-byte granules per pose: q,t (4) + fx..bf (3)
+		for (int i = tid; i < ti.poseN * 7; i += JH3_TL) {
+			const int p = i / 7, k = i - 7 * p;
+			cp_async16(&st.pose[p * JH3_PSTRIDE + 2 * k], k < 4 ? a.pose + 8 * (size_t)(ti.pose0 + p) + 2 * k : a.cam + 8 * (size_t)(ti.pose0 + p) + 2 * (k - 4));
 		}
 	}
 }
 
-__global__ void __launch_bounds__(JH3_TL, 3) k_linearize_landmark3(const LinLm3Args aa)
+__global__ void __launch_bounds__(JH3_TL, 4) k_linearize_landmark3(const LinLm3Args aa)
 {
 	typedef double T;
 	const LinLmArgs<T>& a = aa.base;
@@ -486,7 +487,6 @@ __global__ void __launch_bounds__(JH3_TL, 3) k_linearize_landmark3(const LinLm3A
 	Jh3Stage* s_stage = sm.stage;
 	T* s_hpl = sm.hpl;
 	T (*s_val)[JH3_TL + 1] = sm.val;
-	T* s_acc = sm.acc;
 	double* s_red = sm.red;
 
 	const int tid = threadIdx.x, G = gridDim.x;
@@ -510,7 +510,6 @@ __global__ void __launch_bounds__(JH3_TL, 3) k_linearize_landmark3(const LinLm3A
 
 		const int l0 = cur.l0, nl = cur.l1 - cur.l0, e0 = cur.e0, e1 = cur.e1, p0 = cur.pose0;
 		const bool cachePoses = cur.poseN <= JH3_POSES;
-		for (int i = tid; i < nl * 9; i += TL) s_acc[i] = T(0);
 		// Hpl blocks of the tile: [h0, h1); per chunk they are consecutive
 		int hdone = 0;
 		for (int cs = e0; cs < e1; cs += TL) {
@@ -530,7 +529,7 @@ __global__ void __launch_bounds__(JH3_TL, 3) k_linearize_landmark3(const LinLm3A
 				hp = first ? st.hpl[tid] : a.hpl[e];
 				T q[4], tt[3], c[5], X[3], m[3], Xc[3], r[3];
 				if (cachePoses) {
-					const T* sp = st.pose + (ip - p0) * JH2_PSTRIDE;
+					const T* sp = st.pose + (ip - p0) * JH3_PSTRIDE;
 					q[0] = sp[0]; q[1] = sp[1]; q[2] = sp[2]; q[3] = sp[3]; tt[0] = sp[4]; tt[1] = sp[5]; tt[2] = sp[6];
 					c[0] = sp[8]; c[1] = sp[9]; c[2] = sp[10]; c[3] = sp[11]; c[4] = sp[12];
 				} else load_pose(a.pose, a.cam, ip, q, tt, c);
@@ -588,33 +587,27 @@ __global__ void __launch_bounds__(JH3_TL, 3) k_linearize_landmark3(const LinLm3A
 				asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(smem_u32(s_hpl)), "r"(bytes) : "memory");
 				asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 			}
-			for (int wi = tid; wi < nl * 9; wi += TL) {
-				const int j = wi / 9, cc = wi - 9 * j;
+			// per-landmark sums of the 6+3 staged values, written straight to Hll (full symmetric 3x3) and bl.
+			// A tile is one chunk unless its last landmark has an unusually long tail; later chunks add to what the
+			// first one stored (same CTA, ordered by the barrier below: deterministic).
+			for (int wi = tid; wi < nl * 12; wi += TL) {
+				const int j = wi / 12, cc = wi - 12 * j;
+				if (l0 + j >= a.numL) continue;
 				int s = st.ptr[j], tE = st.ptr[j + 1];
 				s = (s > cs ? s : cs) - cs;
 				tE = (tE < cend ? tE : cend) - cs;
 				if (tE > s) {
+					const int src = cc < 9 ? (cc == 0 ? 0 : cc == 1 ? 1 : cc == 2 ? 2 : cc == 3 ? 1 : cc == 4 ? 3 : cc == 5 ? 4 : cc == 6 ? 2 : cc == 7 ? 4 : 5) : cc - 3;
 					T sum = T(0);
-					for (int k = s; k < tE; k++) sum += s_val[cc][k];
-					s_acc[wi] += sum;
+					for (int k = s; k < tE; k++) sum += s_val[src][k];
+					T* dst = cc < 9 ? a.Hll + 9 * (size_t)(l0 + j) + cc : a.bl + 3 * (size_t)(l0 + j) + (cc - 9);
+					*dst = first ? sum : *dst + sum;
 				}
 			}
 			if (tid == 0 && hcount > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 			hdone += hcount;
 			__syncthreads();
 		}
-		{
-			const int map9[9] = { 0, 1, 2, 1, 3, 4, 2, 4, 5 };
-			for (int wi = tid; wi < nl * 9; wi += TL) {
-				const int j = wi / 9, cc = wi - 9 * j;
-				if (l0 + j < a.numL) a.Hll[9 * (size_t)l0 + wi] = s_acc[j * 9 + map9[cc]];
-			}
-			for (int wi = tid; wi < nl * 3; wi += TL) {
-				const int j = wi / 3, cc = wi - 3 * j;
-				if (l0 + j < a.numL) a.bl[3 * (size_t)l0 + wi] = s_acc[j * 9 + 6 + cc];
-			}
-		}
-		__syncthreads();      // s_acc / stage reuse
 		cur = nxt; nxt = nn;
 	}
 	asm volatile("cp.async.wait_group 0;" ::: "memory");
