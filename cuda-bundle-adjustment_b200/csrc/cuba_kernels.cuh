@@ -433,11 +433,12 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gptr)
 
 constexpr int JH3_TL = 128;          // threads per CTA == edges of a tile's first chunk
 constexpr int JH3_WINDOW = 112;      // edges per tile window (structure builder): leaves 16 slots for the last landmark's tail
-constexpr int JH3_POSES = 24;         // pose-window capacity of a stage (wider windows fall back to global gathers)
+constexpr int JH3_POSES = 40;         // pose-window capacity of a stage (wider windows fall back to global gathers)
+constexpr int JH3_LMS = 64;           // landmark-window capacity of a stage (later landmarks of a tile are gathered)
 constexpr int JH3_PSTRIDE = 18;       // doubles per staged pose record: 16-byte granules, rows shifted by 4 banks
 
 struct alignas(16) Jh3Stage {
-	double xw[JH3_TL * 4];            // landmark window (32-byte records)
+	double xw[JH3_LMS * 4];           // landmark window (32-byte records)
 	double mx[JH3_TL], my[JH3_TL], mz[JH3_TL], om[JH3_TL];
 	double pose[JH3_POSES * JH3_PSTRIDE];
 	int ip[JH3_TL], il[JH3_TL], hpl[JH3_TL];
@@ -467,7 +468,8 @@ __device__ __forceinline__ void jh3_issue_loads(const LinLmArgs<double>& a, cons
 	}
 	for (int i = tid; i <= nl; i += JH3_TL) cp_async4(&st.ptr[i], a.lmPtr + ti.l0 + i);
 	// landmark window: rows l0 .. l0+nl-1 of Xw (the pseudo-landmark of the fixed ones maps to a real row, harmless)
-	for (int i = tid; i < nl * 2; i += JH3_TL) cp_async16(&st.xw[2 * i], a.Xw + 4 * (size_t)ti.l0 + 2 * i);
+	const int nw = nl < JH3_LMS ? nl : JH3_LMS;
+	for (int i = tid; i < nw * 2; i += JH3_TL) cp_async16(&st.xw[2 * i], a.Xw + 4 * (size_t)ti.l0 + 2 * i);
 	if (ti.poseN <= JH3_POSES) {
 		// 7 16-byte granules per pose: q,t (4) + fx..bf (3)
 		for (int i = tid; i < ti.poseN * 7; i += JH3_TL) {
@@ -533,7 +535,7 @@ __global__ void __launch_bounds__(JH3_TL, 4) k_linearize_landmark3(const LinLm3A
 					q[0] = sp[0]; q[1] = sp[1]; q[2] = sp[2]; q[3] = sp[3]; tt[0] = sp[4]; tt[1] = sp[5]; tt[2] = sp[6];
 					c[0] = sp[8]; c[1] = sp[9]; c[2] = sp[10]; c[3] = sp[11]; c[4] = sp[12];
 				} else load_pose(a.pose, a.cam, ip, q, tt, c);
-				if (il < a.numL && il - l0 < nl) { const T* sx = st.xw + 4 * (il - l0); X[0] = sx[0]; X[1] = sx[1]; X[2] = sx[2]; }
+				if (il < a.numL && il - l0 < JH3_LMS) { const T* sx = st.xw + 4 * (il - l0); X[0] = sx[0]; X[1] = sx[1]; X[2] = sx[2]; }
 				else load_xw(a.Xw, il, X);
 				if (first) { m[0] = st.mx[tid]; m[1] = st.my[tid]; m[2] = stereo ? st.mz[tid] : T(0); }
 				else { m[0] = a.mx[e]; m[1] = a.my[e]; m[2] = stereo ? a.mz[e] : T(0); }
