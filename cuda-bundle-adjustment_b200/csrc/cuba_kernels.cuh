@@ -471,149 +471,159 @@ __device__ __forceinline__ void jh3_issue_loads(const LinLmArgs<double>& a, cons
 	const int nw = nl < JH3_LMS ? nl : JH3_LMS;
 	for (int i = tid; i < nw * 2; i += JH3_TL) cp_async16(&st.xw[2 * i], a.Xw + 4 * (size_t)ti.l0 + 2 * i);
 	if (ti.poseN <= JH3_POSES) {
-		// 7 16-byte granules per pose: q,t (4) + fx..bf (3)
-		for (int i = tid; i < ti.poseN * 7; i += JH3_TL) {
-			const int p = i / 7, k = i - 7 * p;
-			cp_async16(&st.pose[p * JH3_PSTRIDE + 2 * k], k < 4 ? a.pose + 8 * (size_t)(ti.pose0 + p) + 2 * k : a.cam + 8 * (size_t)(ti.pose0 + p) + 2 * (k - 4));
+		// 8 16-byte granules per pose: q,t,pad (4) + fx..bf,pad (4); pose and cam are two [Pall][8] arrays
+		for (int i = tid; i < ti.poseN * 8; i += JH3_TL) {
+			const int p = i >> 3, k = i & 7;
+			cp_async16(&st.pose[p * JH3_PSTRIDE + 2 * k], (k < 4 ? a.pose : a.cam - 8) + 8 * (size_t)(ti.pose0 + p) + 2 * k);
 		}
 	}
 }
 
-__global__ void __launch_bounds__(JH3_TL, 4) k_linearize_landmark3(const LinLm3Args aa)
+// One chunk (<= JH3_TL edges) of a tile.  FIRST: the chunk's inputs are in the shared-memory stage (the normal case);
+// otherwise (a tile whose last landmark has an unusually long tail) they are read from global memory.
+template <bool FIRST>
+__device__ __forceinline__ void jh3_chunk(const LinLmArgs<double>& a, const TileInfo& cur, const Jh3Stage& st, Jh3Smem& sm,
+	int cs, int tid, int& hdone, double& chi)
 {
 	typedef double T;
-	const LinLmArgs<T>& a = aa.base;
 	constexpr int TL = JH3_TL;
+	const int l0 = cur.l0, nl = cur.l1 - cur.l0, e1 = cur.e1, p0 = cur.pose0;
+	const bool cachePoses = cur.poseN <= JH3_POSES;
+	const int e = cs + tid;
+	const int cend = cs + TL < e1 ? cs + TL : e1;
+	T v[9];
+#pragma unroll
+	for (int i = 0; i < 9; i++) v[i] = T(0);
+	int hp = -1;
+	if (e < e1) {
+		const int ipf = FIRST ? st.ip[tid] : a.ip[e];
+		const bool stereo = ipf < 0;
+		const int ip = ipf & 0x7fffffff;
+		const int il = FIRST ? st.il[tid] : a.il[e];
+		hp = FIRST ? st.hpl[tid] : a.hpl[e];
+		T q[4], tt[3], c[5], X[3], m[3], Xc[3], r[3];
+		if (cachePoses) {
+			const T* sp = st.pose + (ip - p0) * JH3_PSTRIDE;
+			q[0] = sp[0]; q[1] = sp[1]; q[2] = sp[2]; q[3] = sp[3]; tt[0] = sp[4]; tt[1] = sp[5]; tt[2] = sp[6];
+			c[0] = sp[8]; c[1] = sp[9]; c[2] = sp[10]; c[3] = sp[11]; c[4] = sp[12];
+		} else load_pose(a.pose, a.cam, ip, q, tt, c);
+		if (il < a.numL && il - l0 < JH3_LMS) { const T* sx = st.xw + 4 * (il - l0); X[0] = sx[0]; X[1] = sx[1]; X[2] = sx[2]; }
+		else load_xw(a.Xw, il, X);
+		m[0] = FIRST ? st.mx[tid] : a.mx[e];
+		m[1] = FIRST ? st.my[tid] : a.my[e];
+		m[2] = stereo ? (FIRST ? st.mz[tid] : a.mz[e]) : T(0);
+		const T om = FIRST ? st.om[tid] : a.om[e];
+		edge_residual(q, tt, c, X, m, stereo, Xc, r);
+		const T e2 = om * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+		T rho, drho;
+		robust<T>(a.rk.type[stereo ? 1 : 0], (T)a.rk.delta[stereo ? 1 : 0], e2, rho, drho);
+		chi += (double)rho;
+		const T w = om * drho;
+		if (il < a.numL) {
+			T JP[3][6], JL[3][3];
+			edge_jacobians(q, c, Xc, stereo, JP, JL);
+			T wJL[3][3], wr[3];
+#pragma unroll
+			for (int mm = 0; mm < 3; mm++) {
+				wr[mm] = w * r[mm];
+#pragma unroll
+				for (int n = 0; n < 3; n++) wJL[mm][n] = w * JL[mm][n];
+			}
+			v[0] = JL[0][0] * wJL[0][0] + JL[1][0] * wJL[1][0] + JL[2][0] * wJL[2][0];
+			v[1] = JL[0][0] * wJL[0][1] + JL[1][0] * wJL[1][1] + JL[2][0] * wJL[2][1];
+			v[2] = JL[0][0] * wJL[0][2] + JL[1][0] * wJL[1][2] + JL[2][0] * wJL[2][2];
+			v[3] = JL[0][1] * wJL[0][1] + JL[1][1] * wJL[1][1] + JL[2][1] * wJL[2][1];
+			v[4] = JL[0][1] * wJL[0][2] + JL[1][1] * wJL[1][2] + JL[2][1] * wJL[2][2];
+			v[5] = JL[0][2] * wJL[0][2] + JL[1][2] * wJL[1][2] + JL[2][2] * wJL[2][2];
+			v[6] = JL[0][0] * wr[0] + JL[1][0] * wr[1] + JL[2][0] * wr[2];
+			v[7] = JL[0][1] * wr[0] + JL[1][1] * wr[1] + JL[2][1] * wr[2];
+			v[8] = JL[0][2] * wr[0] + JL[1][2] * wr[1] + JL[2][2] * wr[2];
+			if (hp >= 0) {
+				T* dst = sm.hpl + 18 * (hp - cur.h0 - hdone);    // consecutive within the chunk
+#pragma unroll
+				for (int n = 0; n < 3; n++) {
+#pragma unroll
+					for (int l = 0; l < 6; l += 2) {
+						const T h0 = JP[0][l] * wJL[0][n] + JP[1][l] * wJL[1][n] + JP[2][l] * wJL[2][n];
+						const T h1 = JP[0][l + 1] * wJL[0][n] + JP[1][l + 1] * wJL[1][n] + JP[2][l + 1] * wJL[2][n];
+						st2(dst + n * 6 + l, h0, h1);
+					}
+				}
+			}
+		}
+	}
+#pragma unroll
+	for (int i = 0; i < 9; i++) sm.val[i][tid] = v[i];
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	const int hcount = __syncthreads_count(hp >= 0);        // blocks written by this chunk (also the barrier)
+	if (tid == 0 && hcount > 0) {
+		const unsigned int bytes = (unsigned int)(hcount * 18 * sizeof(T));
+		T* gdst = a.Hpl + 18 * (size_t)(cur.h0 + hdone);
+		asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(smem_u32(sm.hpl)), "r"(bytes) : "memory");
+		asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+	}
+	// per-landmark sums of the staged values, written straight to Hll (full symmetric 3x3) and bl: item = (landmark, slot),
+	// slot 0..5 the unique Hll entries (each written to its one or two mirrored positions), 6..8 bl.
+	// Later chunks add to what the first one stored (same CTA, ordered by the barrier below: deterministic).
+	for (int wi = tid; wi < nl * 9; wi += TL) {
+		const int j = wi / 9, cc = wi - 9 * j;
+		if (l0 + j >= a.numL) continue;
+		int s = st.ptr[j], tE = st.ptr[j + 1];
+		s = (s > cs ? s : cs) - cs;
+		tE = (tE < cend ? tE : cend) - cs;
+		if (tE > s) {
+			T sum = T(0);
+			for (int k = s; k < tE; k++) sum += sm.val[cc][k];
+			if (cc < 6) {
+				// unique entry cc of (00,01,02,11,12,22) -> column-major positions
+				const int pa = cc == 0 ? 0 : cc == 1 ? 1 : cc == 2 ? 2 : cc == 3 ? 4 : cc == 4 ? 5 : 8;
+				const int pb = cc == 1 ? 3 : cc == 2 ? 6 : cc == 4 ? 7 : pa;
+				T* H = a.Hll + 9 * (size_t)(l0 + j);
+				if (FIRST) { H[pa] = sum; if (pb != pa) H[pb] = sum; }
+				else { const T t2 = H[pa] + sum; H[pa] = t2; if (pb != pa) H[pb] = t2; }
+			} else {
+				T* b = a.bl + 3 * (size_t)(l0 + j) + (cc - 6);
+				*b = FIRST ? sum : *b + sum;
+			}
+		}
+	}
+	if (tid == 0 && hcount > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+	hdone += hcount;
+	__syncthreads();
+}
+
+__global__ void __launch_bounds__(JH3_TL, 4) k_linearize_landmark3(const LinLm3Args aa)
+{
+	const LinLmArgs<double>& a = aa.base;
 	extern __shared__ __align__(16) unsigned char jh3_smem_raw[];
 	Jh3Smem& sm = *reinterpret_cast<Jh3Smem*>(jh3_smem_raw);
-	Jh3Stage* s_stage = sm.stage;
-	T* s_hpl = sm.hpl;
-	T (*s_val)[JH3_TL + 1] = sm.val;
-	double* s_red = sm.red;
 
 	const int tid = threadIdx.x, G = gridDim.x;
 	int t = blockIdx.x;
 	TileInfo cur = {}, nxt = {};
 	if (t < aa.ntiles) cur = aa.info[t];
 	if (t + G < aa.ntiles) nxt = aa.info[t + G];
-	if (t < aa.ntiles) jh3_issue_loads(a, cur, s_stage[0], tid);
+	if (t < aa.ntiles) jh3_issue_loads(a, cur, sm.stage[0], tid);
 	asm volatile("cp.async.commit_group;" ::: "memory");
 
 	double chi = 0;
 	for (int it = 0; t < aa.ntiles; t += G, it++) {
-		Jh3Stage& st = s_stage[it & 1];
+		const Jh3Stage& st = sm.stage[it & 1];
 		// prefetch the next tile into the other stage and the descriptor after it into registers
-		if (t + G < aa.ntiles) jh3_issue_loads(a, nxt, s_stage[(it & 1) ^ 1], tid);
+		if (t + G < aa.ntiles) jh3_issue_loads(a, nxt, sm.stage[(it & 1) ^ 1], tid);
 		asm volatile("cp.async.commit_group;" ::: "memory");
 		TileInfo nn = {};
 		if (t + 2 * G < aa.ntiles) nn = aa.info[t + 2 * G];
 		asm volatile("cp.async.wait_group 1;" ::: "memory");      // everything but the group just committed has landed
 		__syncthreads();
 
-		const int l0 = cur.l0, nl = cur.l1 - cur.l0, e0 = cur.e0, e1 = cur.e1, p0 = cur.pose0;
-		const bool cachePoses = cur.poseN <= JH3_POSES;
-		// Hpl blocks of the tile: [h0, h1); per chunk they are consecutive
 		int hdone = 0;
-		for (int cs = e0; cs < e1; cs += TL) {
-			const bool first = cs == e0;
-			const int e = cs + tid;
-			const int cend = cs + TL < e1 ? cs + TL : e1;
-			T v[9];
-#pragma unroll
-			for (int i = 0; i < 9; i++) v[i] = T(0);
-			// number of Hpl blocks in this chunk: count of hpl >= 0
-			int hp = -1;
-			if (e < e1) {
-				const int ipf = first ? st.ip[tid] : a.ip[e];
-				const bool stereo = ipf < 0;
-				const int ip = ipf & 0x7fffffff;
-				const int il = first ? st.il[tid] : a.il[e];
-				hp = first ? st.hpl[tid] : a.hpl[e];
-				T q[4], tt[3], c[5], X[3], m[3], Xc[3], r[3];
-				if (cachePoses) {
-					const T* sp = st.pose + (ip - p0) * JH3_PSTRIDE;
-					q[0] = sp[0]; q[1] = sp[1]; q[2] = sp[2]; q[3] = sp[3]; tt[0] = sp[4]; tt[1] = sp[5]; tt[2] = sp[6];
-					c[0] = sp[8]; c[1] = sp[9]; c[2] = sp[10]; c[3] = sp[11]; c[4] = sp[12];
-				} else load_pose(a.pose, a.cam, ip, q, tt, c);
-				if (il < a.numL && il - l0 < JH3_LMS) { const T* sx = st.xw + 4 * (il - l0); X[0] = sx[0]; X[1] = sx[1]; X[2] = sx[2]; }
-				else load_xw(a.Xw, il, X);
-				if (first) { m[0] = st.mx[tid]; m[1] = st.my[tid]; m[2] = stereo ? st.mz[tid] : T(0); }
-				else { m[0] = a.mx[e]; m[1] = a.my[e]; m[2] = stereo ? a.mz[e] : T(0); }
-				const T om = first ? st.om[tid] : a.om[e];
-				edge_residual(q, tt, c, X, m, stereo, Xc, r);
-				const T e2 = om * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
-				T rho, drho;
-				robust<T>(a.rk.type[stereo ? 1 : 0], (T)a.rk.delta[stereo ? 1 : 0], e2, rho, drho);
-				chi += (double)rho;
-				const T w = om * drho;
-				if (il < a.numL) {
-					T JP[3][6], JL[3][3];
-					edge_jacobians(q, c, Xc, stereo, JP, JL);
-					T wJL[3][3], wr[3];
-#pragma unroll
-					for (int mm = 0; mm < 3; mm++) {
-						wr[mm] = w * r[mm];
-#pragma unroll
-						for (int n = 0; n < 3; n++) wJL[mm][n] = w * JL[mm][n];
-					}
-					v[0] = JL[0][0] * wJL[0][0] + JL[1][0] * wJL[1][0] + JL[2][0] * wJL[2][0];
-					v[1] = JL[0][0] * wJL[0][1] + JL[1][0] * wJL[1][1] + JL[2][0] * wJL[2][1];
-					v[2] = JL[0][0] * wJL[0][2] + JL[1][0] * wJL[1][2] + JL[2][0] * wJL[2][2];
-					v[3] = JL[0][1] * wJL[0][1] + JL[1][1] * wJL[1][1] + JL[2][1] * wJL[2][1];
-					v[4] = JL[0][1] * wJL[0][2] + JL[1][1] * wJL[1][2] + JL[2][1] * wJL[2][2];
-					v[5] = JL[0][2] * wJL[0][2] + JL[1][2] * wJL[1][2] + JL[2][2] * wJL[2][2];
-					v[6] = JL[0][0] * wr[0] + JL[1][0] * wr[1] + JL[2][0] * wr[2];
-					v[7] = JL[0][1] * wr[0] + JL[1][1] * wr[1] + JL[2][1] * wr[2];
-					v[8] = JL[0][2] * wr[0] + JL[1][2] * wr[1] + JL[2][2] * wr[2];
-					if (hp >= 0) {
-						T* dst = s_hpl + 18 * (hp - cur.h0 - hdone);    // consecutive within the chunk
-#pragma unroll
-						for (int n = 0; n < 3; n++) {
-#pragma unroll
-							for (int l = 0; l < 6; l += 2) {
-								const T h0 = JP[0][l] * wJL[0][n] + JP[1][l] * wJL[1][n] + JP[2][l] * wJL[2][n];
-								const T h1 = JP[0][l + 1] * wJL[0][n] + JP[1][l + 1] * wJL[1][n] + JP[2][l + 1] * wJL[2][n];
-								st2(dst + n * 6 + l, h0, h1);
-							}
-						}
-					}
-				}
-			}
-#pragma unroll
-			for (int i = 0; i < 9; i++) s_val[i][tid] = v[i];
-			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-			const int hcount = __syncthreads_count(hp >= 0);        // blocks written by this chunk (also the barrier)
-			if (tid == 0 && hcount > 0) {
-				const unsigned int bytes = (unsigned int)(hcount * 18 * sizeof(T));
-				T* gdst = a.Hpl + 18 * (size_t)(cur.h0 + hdone);
-				asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(smem_u32(s_hpl)), "r"(bytes) : "memory");
-				asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-			}
-			// per-landmark sums of the 6+3 staged values, written straight to Hll (full symmetric 3x3) and bl.
-			// A tile is one chunk unless its last landmark has an unusually long tail; later chunks add to what the
-			// first one stored (same CTA, ordered by the barrier below: deterministic).
-			for (int wi = tid; wi < nl * 12; wi += TL) {
-				const int j = wi / 12, cc = wi - 12 * j;
-				if (l0 + j >= a.numL) continue;
-				int s = st.ptr[j], tE = st.ptr[j + 1];
-				s = (s > cs ? s : cs) - cs;
-				tE = (tE < cend ? tE : cend) - cs;
-				if (tE > s) {
-					const int src = cc < 9 ? (cc == 0 ? 0 : cc == 1 ? 1 : cc == 2 ? 2 : cc == 3 ? 1 : cc == 4 ? 3 : cc == 5 ? 4 : cc == 6 ? 2 : cc == 7 ? 4 : 5) : cc - 3;
-					T sum = T(0);
-					for (int k = s; k < tE; k++) sum += s_val[src][k];
-					T* dst = cc < 9 ? a.Hll + 9 * (size_t)(l0 + j) + cc : a.bl + 3 * (size_t)(l0 + j) + (cc - 9);
-					*dst = first ? sum : *dst + sum;
-				}
-			}
-			if (tid == 0 && hcount > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-			hdone += hcount;
-			__syncthreads();
-		}
+		jh3_chunk<true>(a, cur, st, sm, cur.e0, tid, hdone, chi);
+		for (int cs = cur.e0 + JH3_TL; cs < cur.e1; cs += JH3_TL) jh3_chunk<false>(a, cur, st, sm, cs, tid, hdone, chi);
 		cur = nxt; nxt = nn;
 	}
 	asm volatile("cp.async.wait_group 0;" ::: "memory");
-	const double tot = block_sum(chi, s_red);
+	const double tot = block_sum(chi, sm.red);
 	if (tid == 0) a.chiPartial[blockIdx.x] = tot;
 }
 

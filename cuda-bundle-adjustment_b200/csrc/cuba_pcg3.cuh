@@ -227,35 +227,43 @@ __global__ void __launch_bounds__(PCG3_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 				//      Every CTA sums everybody's partial products itself, in the same fixed order (one L2 hop).  With all G CTAs
 				//      polling the same 2G slots the hot L2 lines cost ~2.5 us per round on B200 (tools/microbench), so the board
 				//      is published in PCG3_REPL replicas and CTA c reads replica c % PCG3_REPL.
+				// slots are kept as 32-bit offsets (in 16-byte words) to keep the two register-resident blocks out of local memory
 				double wv[PCG3_WPT], pv[2];
-				const unsigned long long* wslot[PCG3_WPT];
-				const unsigned long long* pslot[2];
+				unsigned int woff[PCG3_WPT], poff[2];
 				unsigned int pend = 0;                             // bit i: w item i pending; bits 8,9: partial words pending
 #pragma unroll
 				for (int u = 0; u < PCG3_WPT; u++) {
 					const int wi = u * PCG3_BLOCK + tid;
-					wv[u] = 0; wslot[u] = aa.wFlag;
+					wv[u] = 0; woff[u] = 0;
 					if (wi < nneed * 6) {
 						const int c = wi / 6, comp = wi - 6 * c;
-						wslot[u] = aa.wFlag + 2 * ((size_t)par * n6 + 6 * (size_t)s_need[c] + comp);
+						woff[u] = (unsigned int)(par * (int)n6 + 6 * s_need[c] + comp);
 						pend |= 1u << u;
 					}
 				}
 #pragma unroll
 				for (int u = 0; u < 2; u++) {
 					const int pi = u * PCG3_BLOCK + tid;
-					pv[u] = 0; pslot[u] = aa.pFlag;
+					pv[u] = 0; poff[u] = 0;
 					if (pi < 2 * G) {
-						pslot[u] = aa.pFlag + 2 * (((size_t)par * PCG3_REPL + (size_t)(cta % PCG3_REPL)) * 2 * G + (size_t)pi);
+						poff[u] = (unsigned int)((par * PCG3_REPL + (cta % PCG3_REPL)) * 2 * G + pi);
 						pend |= 0x100u << u;
 					}
 				}
 				bool ok = true;
-				for (unsigned int spin = 0; pend; spin++) {
+				// the w entries are published before the partial products (which need the producer's block reduction), so
+				// they are polled first; this also halves the registers live in either polling loop
+				for (unsigned int spin = 0; pend & 0xffu; spin++) {
 #pragma unroll
-					for (int u = 0; u < PCG3_WPT; u++) if ((pend >> u) & 1u) { if (ll_try_load(wslot[u], tag, wv[u])) pend &= ~(1u << u); }
+					for (int u = 0; u < PCG3_WPT; u++) if ((pend >> u) & 1u) { if (ll_try_load(aa.wFlag + 2 * (size_t)woff[u], tag, wv[u])) pend &= ~(1u << u); }
+					if ((spin & 1023u) == 1023u) {
+						if (*(volatile int*)aa.abortFlag) { ok = false; break; }
+						if (spin >= PCG3_SPIN_LIMIT) { atomicExch(aa.abortFlag, 1); ok = false; break; }
+					}
+				}
+				for (unsigned int spin = 0; ok && (pend & 0x300u); spin++) {
 #pragma unroll
-					for (int u = 0; u < 2; u++) if ((pend >> (8 + u)) & 1u) { if (ll_try_load(pslot[u], tag, pv[u])) pend &= ~(0x100u << u); }
+					for (int u = 0; u < 2; u++) if ((pend >> (8 + u)) & 1u) { if (ll_try_load(aa.pFlag + 2 * (size_t)poff[u], tag, pv[u])) pend &= ~(0x100u << u); }
 					if ((spin & 1023u) == 1023u) {
 						if (*(volatile int*)aa.abortFlag) { ok = false; break; }
 						if (spin >= PCG3_SPIN_LIMIT) { atomicExch(aa.abortFlag, 1); ok = false; break; }
