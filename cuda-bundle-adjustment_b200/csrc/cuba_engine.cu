@@ -18,6 +18,7 @@
 #include "cuba_kernels.cuh"
 #include "cuba_pcg2.cuh"
 #include "cuba_pcg3.cuh"
+#include "cuba_schur2.cuh"
 #include "cuba_structure.h"
 #include "cuba_structure_gpu.cuh"
 
@@ -142,6 +143,13 @@ struct Engine : EngineBase {
 	bool jhV3 = true;       // k_linearize_landmark3 (v2 + persistent CTAs with a cp.async double-buffered input stage)
 	int jh3Grid = 0, nChiLin = 0;
 	DBuf<TileInfo> tileInfo;
+	// tile-local Schur (cuba_schur2.cuh)
+	bool useSchur2 = true;
+	int s2Nseg = 0;
+	DBuf<unsigned long long> s2_key, s2_keyS, s2_key3, s2_key3S;
+	DBuf<int> s2_val, s2_valS, s2_head, s2_segId, s2_segStart, s2_segTile, s2_segDest, s2_val3, s2_val3S, s2_segRank, s2_rankDest, s2_tileSegPtr, s2_destSegPtr, s2_p2i, s2_p2j;
+	DBuf<schur2::Counts> s2_counts;
+	DBuf<T> s2_partial;
 	DBuf<int> tilePose0, tilePoseN;
 	int cur = 0;            // current state buffer
 	bool trialValid = false;
@@ -547,6 +555,8 @@ struct Engine : EngineBase {
 		}
 		CUDA_TRY(cudaFuncSetAttribute(k_linearize_landmark3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Jh3Smem)));
 		jh3Grid = std::max(1, std::min(ntiles, numSMs * 4));
+		useSchur2 = cfg.reserved[3] != 1 && S.numP > 0 && S.numL > 0 && ntiles > 0;
+		if (useSchur2) { int rc = setup_schur2(); if (rc) return rc; }
 		nChiLin = jhV3 ? jh3Grid : ntiles;
 		nPoseBlocks = (S.numP + RED_BLOCK - 1) / RED_BLOCK;
 		nChiBlocks = std::max(1, std::min((eL + RED_BLOCK - 1) / RED_BLOCK, numSMs * 8));
@@ -747,6 +757,27 @@ struct Engine : EngineBase {
 	int launch_schur(T lambda)
 	{
 		ProfScope ps(this, CUBA_PROF_SCHUR_COMPLEMENT);
+		if (useSchur2) {
+			schur2::TileArgs<T> ta;
+			ta.Hpl = Hpl; ta.Hll = Hll; ta.bl = bl; ta.info = tileInfo; ta.hplLm = hplLm;
+			ta.tileSegPtr = s2_tileSegPtr; ta.segStart = s2_segStart; ta.segDest = s2_segDest; ta.segRank = s2_segRank; ta.p2i = s2_p2i; ta.p2j = s2_p2j;
+			ta.blkRow = blkRow; ta.blkCol = blkCol; ta.numL = S.numL; ta.lambda = lambda; ta.invHll = invHll; ta.partial = s2_partial;
+			schur2::k_schur_tiles<T><<<ntiles, schur2::TL, 0, stream>>>(ta);
+			launches++;
+			CUDA_TRY(cudaGetLastError());
+			schur2::ReduceArgs<T> ra;
+			ra.partial = s2_partial; ra.destSegPtr = s2_destSegPtr; ra.Hpp = Hpp; ra.bp = bp;
+			ra.blkRow = blkRow; ra.blkCol = blkCol; ra.u2f = u2f; ra.u2fT = u2fT; ra.nblk = S.nblk; ra.lambda = lambda;
+			ra.addDiag = rank == 0 ? 1 : 0; ra.fVal = fVal; ra.bsc = bsc;
+			schur2::k_schur_reduce<T><<<(S.nblk + 3) / 4, 128, 0, stream>>>(ra);
+			launches++;
+			CUDA_TRY(cudaGetLastError());
+			if (world > 1) {
+				int rc = allreduce(fVal.p, 36 * (size_t)S.nfull, true); if (rc) return rc;
+				rc = allreduce(bsc.p, 6 * (size_t)S.numP, true); if (rc) return rc;
+			}
+			return CUBA_OK;
+		}
 		if (S.numL > 0) {
 			k_inv_hll<T><<<(S.numL + 255) / 256, 256, 0, stream>>>(Hll, S.numL, lambda, invHll);
 			launches++;
@@ -767,6 +798,40 @@ struct Engine : EngineBase {
 				rc = allreduce(bsc.p, 6 * (size_t)S.numP, true); if (rc) return rc;
 			}
 		}
+		return CUBA_OK;
+	}
+
+	// (tile, destination) segments of the block products for the tile-local Schur kernels
+	int setup_schur2()
+	{
+		using namespace schur2;
+		const int N = (int)S.nmulLocal, nblk = S.nblk;
+		if (N <= 0) { useSchur2 = false; return CUBA_OK; }
+		CUDA_TRY(s2_key.alloc(N)); CUDA_TRY(s2_keyS.alloc(N)); CUDA_TRY(s2_val.alloc(N)); CUDA_TRY(s2_valS.alloc(N));
+		CUDA_TRY(s2_head.alloc(N)); CUDA_TRY(s2_segId.alloc(N)); CUDA_TRY(s2_counts.alloc(1));
+		KLAUNCH(schur2::k_keys, N, prodPtr.p, nblk, prodI.p, N, tileInfo.p, ntiles, s2_key.p, s2_val.p);
+		int rc = sortPairs(s2_key.p, s2_keyS.p, s2_val.p, s2_valS.p, N, 64); if (rc) return rc;
+		KLAUNCH(schur2::k_heads, N, s2_keyS.p, N, s2_head.p);
+		rc = exclusiveSum(s2_head.p, s2_segId.p, N); if (rc) return rc;
+		schur2::k_counts<<<1, 32, 0, stream>>>(s2_keyS.p, s2_head.p, s2_segId.p, N, s2_counts.p);
+		launches++;
+		schur2::Counts hc;
+		CUDA_TRY(cudaMemcpyAsync(&hc, s2_counts.p, sizeof(hc), cudaMemcpyDeviceToHost, stream));
+		CUDA_TRY(cudaStreamSynchronize(stream));
+		const int nseg = hc.nseg;
+		s2Nseg = nseg;
+		CUDA_TRY(s2_segStart.alloc((size_t)nseg + 1)); CUDA_TRY(s2_segTile.alloc(nseg)); CUDA_TRY(s2_segDest.alloc(nseg));
+		CUDA_TRY(s2_key3.alloc(nseg)); CUDA_TRY(s2_key3S.alloc(nseg)); CUDA_TRY(s2_val3.alloc(nseg)); CUDA_TRY(s2_val3S.alloc(nseg));
+		CUDA_TRY(s2_segRank.alloc(nseg)); CUDA_TRY(s2_rankDest.alloc(nseg));
+		CUDA_TRY(s2_tileSegPtr.alloc((size_t)ntiles + 1)); CUDA_TRY(s2_destSegPtr.alloc((size_t)nblk + 1));
+		CUDA_TRY(s2_p2i.alloc(N)); CUDA_TRY(s2_p2j.alloc(N));
+		KLAUNCH(schur2::k_segments, N + 1, s2_keyS.p, s2_valS.p, s2_head.p, s2_segId.p, prodI.p, prodJ.p, N, nseg, hc.nvalid,
+			s2_segStart.p, s2_segTile.p, s2_segDest.p, s2_p2i.p, s2_p2j.p, s2_key3.p, s2_val3.p);
+		KLAUNCH(schur2::k_ptr_from_field, ntiles + 1, s2_segTile.p, nseg, ntiles, s2_tileSegPtr.p);
+		rc = sortPairs(s2_key3.p, s2_key3S.p, s2_val3.p, s2_val3S.p, nseg, 32 + sgpu::bits_for((unsigned long long)std::max(nblk, 1))); if (rc) return rc;
+		KLAUNCH(schur2::k_rank, nseg, s2_key3S.p, s2_val3S.p, nseg, s2_segRank.p, s2_rankDest.p);
+		KLAUNCH(schur2::k_ptr_from_field, nblk + 1, s2_rankDest.p, nseg, nblk, s2_destSegPtr.p);
+		CUDA_TRY(s2_partial.alloc((size_t)schur2::PW * std::max(nseg, 1)));
 		return CUBA_OK;
 	}
 

@@ -77,7 +77,9 @@ typedef struct cuba_config {
 	                          no barrier in the iteration; default), 2 = k_pcg2 (same, one grid barrier per iteration),
 	                          1 = k_pcg (first generation, two cooperative-groups syncs)
 	                          reserved[1]: 1 = build the index structures on the host (cuba_structure.cpp) instead of
-	                          on the device (cuba_structure_gpu.cuh, default); both give identical structures */
+	                          on the device (cuba_structure_gpu.cuh, default); both give identical structures
+	                          reserved[2]: J+H landmark kernel, 0 = k_linearize_landmark3 (default), 5 = ..._landmark2, 1-4 = first generation
+	                          reserved[3]: 1 = first-generation Schur kernel (k_schur) instead of the tile-local pair (cuba_schur2.cuh) */
 } cuba_config;
 
 /* Flat problem: exactly what CudaBlockSolver::initialize produces (cpp:115-261).

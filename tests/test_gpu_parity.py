@@ -203,6 +203,21 @@ def test_device_and_host_structure_builders_agree(pkg, problems, name):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("name", ["small", "kitti07_shaped"])
+def test_schur_kernels_agree(pkg, oracle, problems, name):
+    """tile-local Schur (cuba_schur2.cuh, default) vs the destination-gather kernel k_schur vs the oracle"""
+    prob = problems(name); rk = KERNELS["huber"]
+    a = make_engine(pkg, prob, rk); b = make_engine(pkg, prob, rk, schur_variant=1)
+    o = oracle.Oracle(prob, *rk)
+    a.linearize(); b.linearize(); o.compute_errors(); o.build_system()
+    for lam in (1e3, 1.0):
+        assert a.solve(lam)[1] and b.solve(lam)[1] and o.solve(lam)
+        for nme, x, y, z in zip(("Hsc", "bsc", "invHll"), a.schur(), b.schur(), o.schur()):
+            assert relerr(x, y) < 1e-12, nme
+            assert relerr(x, z) < STAGE_TOL, nme
+    a.close(); b.close()
+
+
 def test_rejects_bad_problems(pkg, problems):
     p = problems("tiny").copy()
     p.idx3 = p.idx3.copy(); p.idx3[5, 1] = p.Lall + 3
