@@ -782,7 +782,14 @@ __global__ void __launch_bounds__(SCHUR_BLOCK) k_schur(const SchurArgs<T> a)
 		const T* pi = a.Hpl + 18 * (size_t)i;
 		const T* pj = a.Hpl + 18 * (size_t)j;
 #pragma unroll
-		for (int x = 0; x < 18; x += 2) { ld2(pi + x, Ai[x], Ai[x + 1]); ld2(pj + x, Aj[x], Aj[x + 1]); }
+		for (int x = 0; x < 18; x += 2) ld2(pi + x, Ai[x], Ai[x + 1]);
+		if (i == j) {                                  // every product of a diagonal destination: one block, not two
+#pragma unroll
+			for (int x = 0; x < 18; x++) Aj[x] = Ai[x];
+		} else {
+#pragma unroll
+			for (int x = 0; x < 18; x += 2) ld2(pj + x, Aj[x], Aj[x + 1]);
+		}
 		const T* iv = a.invHll + 9 * (size_t)l;
 		inv[0] = iv[0]; inv[1] = iv[3]; inv[2] = iv[6]; inv[3] = iv[4]; inv[4] = iv[7]; inv[5] = iv[8];
 		T b3[3] = { T(0), T(0), T(0) };

@@ -297,11 +297,13 @@ __global__ void __launch_bounds__(PCG3_BLOCK, 1) k_pcg3(const Pcg3Args<T> aa)
 				} else {
 					it = k;
 					if (gnew <= a.tol2 * gamma0) { gamma = gnew; status = 0; break; }
+					// beta = g'/g and alpha' = g' / (delta - beta g'/alpha) with the two divisions independent of each other
 					beta = gnew / gamma;
-					const double den = delta - beta * gnew / alpha;
+					const double ga = gamma * alpha;
+					const double den = delta * ga - gnew * gnew;      // = ga * (delta - beta g'/alpha)
+					if (!(den > 0) || !(ga > 0)) { gamma = gnew; status = 2; break; }
+					alpha = gnew * ga / den;
 					gamma = gnew;
-					if (!(den > 0)) { status = 2; break; }
-					alpha = gnew / den;
 				}
 				if (k >= a.maxIters) { status = 1; break; }
 				PCG_T(t3);

@@ -71,7 +71,7 @@ typedef struct cuba_config {
 	int device;            /* CUDA device ordinal, -1 = current device                            */
 	int use_fp32;          /* 0 = fp64 (default); 1 = reference's USE_FLOAT32 behaviour           */
 	int pcg_max_iters;     /* <=0: default                                         */
-	double pcg_tol;        /* stop when sqrt(r'z / r0'z0) <= pcg_tol; <=0: default 1e-13           */
+	double pcg_tol;        /* stop when sqrt(r'z / r0'z0) <= pcg_tol; <=0: default 1e-11 (fp64)    */
 	int deterministic;     /* 1 (default): fixed-order reductions, bit-reproducible run to run     */
 	int reserved[7];       /* reserved[0]: PCG kernel, 0 = k_pcg3 (shared-memory resident, flag-synchronised exchange,
 	                          no barrier in the iteration; default), 2 = k_pcg2 (same, one grid barrier per iteration),
@@ -79,7 +79,7 @@ typedef struct cuba_config {
 	                          reserved[1]: 1 = build the index structures on the host (cuba_structure.cpp) instead of
 	                          on the device (cuba_structure_gpu.cuh, default); both give identical structures
 	                          reserved[2]: J+H landmark kernel, 0 = k_linearize_landmark3 (default), 5 = ..._landmark2, 1-4 = first generation
-	                          reserved[3]: 1 = first-generation Schur kernel (k_schur) instead of the tile-local pair (cuba_schur2.cuh) */
+	                          reserved[3]: 2 = tile-local Schur kernels (cuba_schur2.cuh, experimental) instead of k_schur */
 } cuba_config;
 
 /* Flat problem: exactly what CudaBlockSolver::initialize produces (cpp:115-261).

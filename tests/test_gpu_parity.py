@@ -40,7 +40,7 @@ def test_stage_parity(pkg, oracle, problems, name, kernel):
     for nme, a, b in zip(("Hsc", "bsc", "invHll"), eng.schur(), o.schur()):
         assert relerr(a, b) < STAGE_TOL, nme
     for nme, a, b in zip(("xp", "xl"), eng.delta(), o.delta()):
-        assert relerr(a, b) < TOL, nme          # PCG (tol 1e-13) vs direct Cholesky
+        assert relerr(a, b) < TOL, nme          # PCG (tol 1e-11) vs direct Cholesky
     fh, sc = eng.update(lam); o.update()
     assert abs(fh - o.compute_errors()) <= TOL * fh
     assert abs(sc - o.compute_scale(lam)) <= TOL * abs(sc)
@@ -205,9 +205,9 @@ def test_device_and_host_structure_builders_agree(pkg, problems, name):
 
 @pytest.mark.parametrize("name", ["small", "kitti07_shaped"])
 def test_schur_kernels_agree(pkg, oracle, problems, name):
-    """tile-local Schur (cuba_schur2.cuh, default) vs the destination-gather kernel k_schur vs the oracle"""
+    """tile-local Schur (cuba_schur2.cuh, opt-in) vs the destination-gather kernel k_schur (default) vs the oracle"""
     prob = problems(name); rk = KERNELS["huber"]
-    a = make_engine(pkg, prob, rk); b = make_engine(pkg, prob, rk, schur_variant=1)
+    a = make_engine(pkg, prob, rk, schur_variant=2); b = make_engine(pkg, prob, rk)
     o = oracle.Oracle(prob, *rk)
     a.linearize(); b.linearize(); o.compute_errors(); o.build_system()
     for lam in (1e3, 1.0):
