@@ -19,6 +19,7 @@
 #include "cuba_pcg2.cuh"
 #include "cuba_pcg3.cuh"
 #include "cuba_schur2.cuh"
+#include "cuba_jh4.cuh"
 #include "cuba_structure.h"
 #include "cuba_structure_gpu.cuh"
 
@@ -142,6 +143,13 @@ struct Engine : EngineBase {
 	bool jhV2 = true;       // k_linearize_landmark2 (pose window in smem + TMA bulk store of Hpl)
 	bool jhV3 = true;       // k_linearize_landmark3 (v2 + persistent CTAs with a cp.async double-buffered input stage)
 	int jh3Grid = 0, nChiLin = 0;
+	// warp-tile J+H landmark pass (cuba_jh4.cuh)
+	bool jhV4 = true;
+	int ntW = 0, jh4Grid = 0, jh4HasBig = 0, jh4MinB = 4, jh4Nst = 2;
+	DBuf<int> w_levels, w_start, w_pieces, w_base, w_tilePose, w_tilePieces, w_pieceCount, w_flag;
+	DBuf<jh4::WTile> w_tile;
+	DBuf<jh4::Rec> w_rec;
+	DBuf<double> w_bigPartial;
 	DBuf<TileInfo> tileInfo;
 	// tile-local Schur (cuba_schur2.cuh)
 	bool useSchur2 = true;
@@ -297,8 +305,12 @@ struct Engine : EngineBase {
 		case 1: tileSize = 256; jhMinBlocks = 2; break;
 		default: tileSize = JH2_TL; jhMinBlocks = 4; break;
 		}
-		jhV3 = cfg.reserved[2] == 0 && sizeof(T) == 8;
-		jhV2 = (cfg.reserved[2] == 5 || cfg.reserved[2] == 0) && sizeof(T) == 8 && !jhV3;
+		// k_linearize_landmark4: 0 = two-stage pipeline, 4 CTAs of 4 warps per SM (default); 8/9 = 5/6 CTAs per SM; 7 = three stages
+		jhV4 = (cfg.reserved[2] == 0 || (cfg.reserved[2] >= 7 && cfg.reserved[2] <= 9)) && sizeof(T) == 8;
+		jh4Nst = cfg.reserved[2] == 7 ? 3 : 2;
+		jh4MinB = cfg.reserved[2] == 8 ? 5 : (cfg.reserved[2] == 9 ? 6 : 4);
+		jhV3 = cfg.reserved[2] == 6 && sizeof(T) == 8;
+		jhV2 = cfg.reserved[2] == 5 && sizeof(T) == 8;
 		if (cfg.reserved[2] == 5) { tileSize = JH2_TL; jhMinBlocks = 4; }
 		// (the bulk copy needs 16-byte multiples: 144-byte fp64 blocks qualify, 72-byte fp32 blocks do not)
 		if (cfg.reserved[2] == 0 && sizeof(T) != 8) { tileSize = 128; jhMinBlocks = 6; }
@@ -558,10 +570,11 @@ struct Engine : EngineBase {
 		// the tile-local Schur pair is correct but (round 1) slower than k_schur: 387 vs 267 us on kitti00_shaped -> opt-in
 		useSchur2 = cfg.reserved[3] == 2 && S.numP > 0 && S.numL > 0 && ntiles > 0;
 		if (useSchur2) { int rc = setup_schur2(); if (rc) return rc; }
-		nChiLin = jhV3 ? jh3Grid : ntiles;
+		if (jhV4) { int rc = setup_jh4(); if (rc) return rc; }
+		nChiLin = jhV4 ? jh4Grid : (jhV3 ? jh3Grid : ntiles);
 		nPoseBlocks = (S.numP + RED_BLOCK - 1) / RED_BLOCK;
 		nChiBlocks = std::max(1, std::min((eL + RED_BLOCK - 1) / RED_BLOCK, numSMs * 8));
-		CUDA_TRY(chiPartial.alloc((size_t)std::max(ntiles, nChiBlocks) + 1));
+		CUDA_TRY(chiPartial.alloc((size_t)std::max(std::max(ntiles, nChiBlocks), jh4Grid) + 1));
 		CUDA_TRY(scalePartialL.alloc((size_t)std::max(ntiles, (S.numL + RED_BLOCK - 1) / RED_BLOCK) + 1));
 		CUDA_TRY(scalePartialP.alloc((size_t)nPoseBlocks + 1));
 		CUDA_TRY(chiSq.alloc((size_t)S.E));
@@ -634,7 +647,57 @@ struct Engine : EngineBase {
 		a.mx = e_mx; a.my = e_my; a.mz = e_mz; a.om = e_om; a.ip = e_ip; a.il = e_il; a.hpl = e_hpl;
 		a.lmPtr = tilePtr; a.tileLm = tileLm; a.numP = S.numP; a.numL = S.numL;
 		a.Hpl = Hpl; a.Hll = Hll; a.bl = bl; a.chiPartial = chiPartial; a.rk = rkParams();
-		if (jhV3) {
+		if (jhV4) {
+			if constexpr (sizeof(T) == 8) {
+				if (ntW <= 0) return CUBA_OK;
+				jh4::Args b;
+				b.pose = pose[cur]; b.cam = cam; b.Xw = Xw[cur];
+				b.rec = w_rec; b.tile = w_tile; b.tilePose = w_tilePose; b.tilePieces = w_tilePieces; b.pieceCount = w_pieceCount; b.ntiles = ntW; b.numL = S.numL;
+				b.Hpl = Hpl; b.Hll = Hll; b.bl = bl; b.bigPartial = w_bigPartial; b.chiPartial = chiPartial; b.rk = rkParams();
+				const void* fn = nullptr; size_t smem = 0;
+#define JH4_PICK(MB, NS, DB) { fn = (const void*)jh4::k_linearize_landmark4<MB, NS, DB>; smem = (size_t)NS * jh4::WARPS * sizeof(jh4::StageOf<MB, NS>); }
+				int dbg = 0;
+#ifdef CUBA_JH4_DEBUG
+				dbg = getenv("CUBA_JH4_DBG") ? atoi(getenv("CUBA_JH4_DBG")) : 0;
+				if (jh4Nst == 3) { switch (dbg) { case 1: JH4_PICK(4, 3, 1) break; case 2: JH4_PICK(4, 3, 2) break; case 4: JH4_PICK(4, 3, 4) break; case 6: JH4_PICK(4, 3, 6) break;
+					case 7: JH4_PICK(4, 3, 7) break; case 8: JH4_PICK(4, 3, 8) break; case 15: JH4_PICK(4, 3, 15) break; default: dbg = 0; } }
+				else { switch (dbg) { case 8: JH4_PICK(5, 2, 8) break; case 7: JH4_PICK(5, 2, 7) break; default: dbg = 0; } }
+#endif
+				if (!fn) {
+					if (jh4Nst == 3) JH4_PICK(4, 3, 0)
+					else if (jh4MinB == 4) JH4_PICK(4, 2, 0)
+					else if (jh4MinB == 5) JH4_PICK(5, 2, 0)
+					else JH4_PICK(6, 2, 0)
+				}
+				CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+				void* kargs[] = { (void*)&b };
+				CUDA_TRY(cudaLaunchKernel(fn, dim3(jh4Grid), dim3(jh4::WARPS * 32), kargs, smem, stream));
+#ifdef CUBA_JH4_DEBUG
+				if (dbg & 8) {
+					const int nw = jh4Grid * jh4::WARPS;
+					std::vector<double> h(11 * (size_t)nw);
+					cudaMemcpyAsync(h.data(), w_bigPartial.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, stream);
+					cudaStreamSynchronize(stream);
+					double acc[8] = { 0 };
+					for (int w = 0; w < nw; w++) for (int i = 0; i < 8; i++) acc[i] += h[8 * (size_t)w + i];
+					static int once = 0;
+					if (once++ == 3) {
+						const char* nm[8] = { "cpasync_wait", "mbar_wait", "lds_inputs", "math+hpl_staging", "fence+bulk_store", "wait_read+issue", "reduce+stores", "rotate(descr)" };
+						double tot = 0; for (int i = 0; i < 8; i++) tot += acc[i];
+						for (int i = 0; i < 8; i++) fprintf(stderr, "jh4 phase %-18s %9.0f cycles/warp  %5.1f %%\n", nm[i], acc[i] / nw, 100 * acc[i] / tot);
+						fprintf(stderr, "jh4 total %9.0f cycles/warp, %d warps, %d tiles\n", tot / nw, nw, ntW);
+						double s0 = 1e300, s1 = 0, l0 = 1e300, l1 = 0, e0 = 1e300, e1 = 0;
+						for (int w = 0; w < nw; w++) {
+							const double* g = h.data() + 8 * (size_t)nw + 3 * (size_t)w;
+							s0 = std::min(s0, g[0]); s1 = std::max(s1, g[0]); l0 = std::min(l0, g[1]); l1 = std::max(l1, g[1]); e0 = std::min(e0, g[2]); e1 = std::max(e1, g[2]);
+						}
+						fprintf(stderr, "jh4 globaltimer (ns, rel. first start): start %.0f..%.0f  loop entry %.0f..%.0f  loop exit %.0f..%.0f\n", 0.0, s1 - s0, l0 - s0, l1 - s0, e0 - s0, e1 - s0);
+					}
+				}
+#endif
+			}
+		}
+		else if (jhV3) {
 			if constexpr (sizeof(T) == 8) {
 				LinLm3Args b;
 				b.base = a; b.info = tileInfo; b.ntiles = ntiles;
@@ -798,6 +861,41 @@ struct Engine : EngineBase {
 				int rc = allreduce(fVal.p, 36 * (size_t)S.nfull, true); if (rc) return rc;
 				rc = allreduce(bsc.p, 6 * (size_t)S.numP, true); if (rc) return rc;
 			}
+		}
+		return CUBA_OK;
+	}
+
+	// warp tiles of the J+H landmark pass (cuba_jh4.cuh): greedy packing by binary lifting, padded records, pose lists
+	int setup_jh4()
+	{
+		ntW = 0; jh4Grid = 0; jh4HasBig = 0;
+		if constexpr (sizeof(T) == 8) {
+			using namespace jh4;
+			const int lb = S.lmBeg, N = S.lmEnd - S.lmBeg;
+			if (N <= 0 || S.eLocal <= 0) return CUBA_OK;
+			int K = 1;
+			while ((1LL << K) <= (long long)N) K++;
+			CUDA_TRY(w_levels.alloc((size_t)K * ((size_t)N + 1)));
+			CUDA_TRY(w_start.alloc((size_t)N + 1)); CUDA_TRY(w_pieces.alloc((size_t)N + 1)); CUDA_TRY(w_base.alloc((size_t)N + 1));
+			CUDA_TRY(w_flag.alloc(1));
+			CUDA_TRY(cudaMemsetAsync(w_flag.p, 0, sizeof(int), stream));
+			KLAUNCH(jh4::k_next, N + 1, lmPtr.p, lb, N, w_levels.p);
+			for (int k = 1; k < K; k++)
+				KLAUNCH(jh4::k_lift, N + 1, w_levels.p + (size_t)(k - 1) * ((size_t)N + 1), N, w_levels.p + (size_t)k * ((size_t)N + 1));
+			KLAUNCH(jh4::k_starts, N + 1, w_levels.p, K, N, lmPtr.p, lb, w_start.p, w_pieces.p, w_flag.p);
+			int rc = exclusiveSum(w_pieces.p, w_base.p, N + 1); if (rc) return rc;
+			int total = 0, big = 0;
+			CUDA_TRY(cudaMemcpyAsync(&total, w_base.p + N, sizeof(int), cudaMemcpyDeviceToHost, stream));
+			CUDA_TRY(cudaMemcpyAsync(&big, w_flag.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+			CUDA_TRY(cudaStreamSynchronize(stream));
+			ntW = total; jh4HasBig = big;
+			if (ntW <= 0) return CUBA_OK;
+			CUDA_TRY(w_tile.alloc(ntW)); CUDA_TRY(w_rec.alloc(ntW)); CUDA_TRY(w_tilePose.alloc(32 * (size_t)ntW)); CUDA_TRY(w_tilePieces.alloc(ntW)); CUDA_TRY(w_pieceCount.alloc(ntW));
+			CUDA_TRY(cudaMemsetAsync(w_pieceCount.p, 0, sizeof(int) * (size_t)ntW, stream));
+			CUDA_TRY(w_bigPartial.alloc(std::max<size_t>(big ? 12 * (size_t)ntW : 12, 11 * (size_t)numSMs * 6 * jh4::WARPS)));
+			KLAUNCH(jh4::k_emit, (long long)N * 32, w_start.p, w_pieces.p, w_base.p, N, lmPtr.p, lb, w_levels.p,
+				e_mx.p, e_my.p, e_mz.p, e_om.p, e_ip.p, e_il.p, e_hpl.p, w_tile.p, w_rec.p, w_tilePose.p, w_tilePieces.p);
+			jh4Grid = std::max(1, std::min((ntW + WARPS - 1) / WARPS, numSMs * jh4MinB));
 		}
 		return CUBA_OK;
 	}

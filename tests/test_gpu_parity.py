@@ -293,3 +293,30 @@ def test_full_size_properties(pkg, problems):
     # per-edge chi2 (non-robust) is consistent with the robustified total: Huber rho(e) <= e
     assert eng.chi_squared().sum() >= chi[-1]
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["small", "kitti07_shaped", "ba_kitti_00"])
+def test_jh_landmark_kernels_agree(pkg, oracle, problems, name):
+    """k_linearize_landmark4 (warp tiles, default) vs generations 3, 2 and 1 of the J+H landmark pass: same Hpl/Hll/bl/chi2
+    to rounding (the kernels group the per-landmark sums differently).  The real ba_kitti_00 has 203 landmarks with
+    more than 32 observations, which the warp-tile kernel cuts into pieces (k_big_reduce)."""
+    if name.startswith("ba_") and not have_fixture(name):
+        pytest.skip("reference fixture absent")
+    prob = problems(name); rk = KERNELS["huber"]
+    ref = None
+    for v in (0, 6, 5, 4):
+        eng = make_engine(pkg, prob, rk, jh_variant=v)
+        chi = eng.linearize()
+        out = (np.array([chi]),) + tuple(eng.system())
+        eng.close()
+        if ref is None:
+            ref = out
+            continue
+        for nme, x, y in zip(("chi2", "Hpp", "bp", "Hll", "bl", "Hpl"), out, ref):
+            assert relerr(x, y) < 1e-13, (v, nme)
+    if name == "small":
+        o = oracle.Oracle(prob, *rk)
+        ochi = o.compute_errors(); o.build_system()
+        assert abs(ref[0][0] - ochi) <= STAGE_TOL * ochi
+        for nme, a, b in zip(("Hpp", "bp", "Hll", "bl", "Hpl"), ref[1:], o.system()):
+            assert relerr(a, b) < STAGE_TOL, nme
