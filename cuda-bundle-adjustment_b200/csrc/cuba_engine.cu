@@ -20,6 +20,7 @@
 #include "cuba_pcg3.cuh"
 #include "cuba_schur2.cuh"
 #include "cuba_jh4.cuh"
+#include "cuba_schur3.cuh"
 #include "cuba_structure.h"
 #include "cuba_structure_gpu.cuh"
 
@@ -169,7 +170,8 @@ struct Engine : EngineBase {
 	DBuf<int> e_ip, e_il, e_hpl, e_user, lmPtr, tileLm, hplLm, posePtr, p_il;
 	// system
 	DBuf<T> Hpp, bp, Hll, bl, Hpl, invHll, fVal, bsc, xp, xl;
-	DBuf<int> prodPtr, prodI, prodJ, blkRow, blkCol, u2f, u2fT, fRowPtr, fColInd;
+	DBuf<int> prodPtr, prodI, prodJ, prodL, blkRow, blkCol, u2f, u2fT, fRowPtr, fColInd;
+	bool useSchur3 = true;
 	// pcg
 	DBuf<T> pr, pz, pq, pp0, pp1, Minv;
 	DBuf<double> pcgPartial;
@@ -569,6 +571,13 @@ struct Engine : EngineBase {
 		jh3Grid = std::max(1, std::min(ntiles, numSMs * 4));
 		// the tile-local Schur pair is correct but (round 1) slower than k_schur: 387 vs 267 us on kitti00_shaped -> opt-in
 		useSchur2 = cfg.reserved[3] == 2 && S.numP > 0 && S.numL > 0 && ntiles > 0;
+		// 0 = k_schur3 (six lanes per product; default), 4 = k_schur4 (same + cooperative cp.async block loads: slower, kept for the record),
+		// 1 = k_schur (lane per product), 2 = tile-local pair
+		useSchur3 = cfg.reserved[3] == 0 || cfg.reserved[3] == 4;
+		if (useSchur3 && S.nmulLocal > 0) {
+			CUDA_TRY(prodL.alloc((size_t)S.nmulLocal));
+			KLAUNCH(schur3::k_prod_landmark, S.nmulLocal, prodI.p, hplLm.p, (int)S.nmulLocal, prodL.p);
+		}
 		if (useSchur2) { int rc = setup_schur2(); if (rc) return rc; }
 		if (jhV4) { int rc = setup_jh4(); if (rc) return rc; }
 		nChiLin = jhV4 ? jh4Grid : (jhV3 ? jh3Grid : ntiles);
@@ -847,7 +856,22 @@ struct Engine : EngineBase {
 			launches++;
 			CUDA_TRY(cudaGetLastError());
 		}
-		if (S.numP > 0 && S.numL > 0) {
+		if (useSchur3 && S.numP > 0 && S.numL > 0) {
+			schur3::Args<T> a;
+			a.Hpl = Hpl; a.invHll = invHll; a.bl = bl; a.Hpp = Hpp; a.bp = bp;
+			a.prodPtr = prodPtr; a.prodI = prodI; a.prodJ = prodJ; a.prodL = prodL;
+			a.blkRow = blkRow; a.blkCol = blkCol; a.u2f = u2f; a.u2fT = u2fT; a.nblk = S.nblk;
+			a.lambda = lambda; a.addDiag = rank == 0 ? 1 : 0; a.fVal = fVal; a.bsc = bsc;
+			if (cfg.reserved[3] != 4) schur3::k_schur3<T><<<(S.nblk + schur3::WARPS - 1) / schur3::WARPS, schur3::WARPS * 32, 0, stream>>>(a);
+			else schur3::k_schur4<T><<<(S.nblk + schur3::WARPS - 1) / schur3::WARPS, schur3::WARPS * 32, 0, stream>>>(a);
+			launches++;
+			CUDA_TRY(cudaGetLastError());
+			if (world > 1) {
+				int rc = allreduce(fVal.p, 36 * (size_t)S.nfull, true); if (rc) return rc;
+				rc = allreduce(bsc.p, 6 * (size_t)S.numP, true); if (rc) return rc;
+			}
+		}
+		else if (S.numP > 0 && S.numL > 0) {
 			SchurArgs<T> a;
 			a.Hpl = Hpl; a.invHll = invHll; a.bl = bl; a.Hpp = Hpp; a.bp = bp;
 			a.prodPtr = prodPtr; a.prodI = prodI; a.prodJ = prodJ; a.hplLm = hplLm;

@@ -653,18 +653,30 @@ __global__ void __launch_bounds__(POSE_BLOCK) k_linearize_pose(const LinPoseArgs
 	T acc[27];
 #pragma unroll
 	for (int i = 0; i < 27; i++) acc[i] = T(0);
-	for (int e = e0 + tid; e < e1; e += POSE_BLOCK) {
-		const int ilf = a.il[e];
+	// software pipeline: the inputs of the thread's next edge (stream entries, then the gathered landmark) are in flight
+	// while the current edge is computed -- the gather through il is a dependent L2 access
+	int e = e0 + tid;
+	int ilfN = 0; T XN[3] = { T(0), T(0), T(0) }, mN[3] = { T(0), T(0), T(0) }, omN = T(0);
+	if (e < e1) {
+		ilfN = a.il[e]; mN[0] = a.mx[e]; mN[1] = a.my[e]; mN[2] = ilfN < 0 ? a.mz[e] : T(0); omN = a.om[e];
+		load_xw(a.Xw, ilfN & 0x7fffffff, XN);
+	}
+	for (; e < e1; e += POSE_BLOCK) {
+		const int ilf = ilfN;
 		const bool stereo = ilf < 0;
-		const int il = ilf & 0x7fffffff;
 		T X[3], m[3], Xc[3], r[3];
-		load_xw(a.Xw, il, X);
-		m[0] = a.mx[e]; m[1] = a.my[e]; m[2] = stereo ? a.mz[e] : T(0);
-		const T om = a.om[e];
+#pragma unroll
+		for (int i = 0; i < 3; i++) { X[i] = XN[i]; m[i] = mN[i]; }
+		const T om = omN;
+		const int en = e + POSE_BLOCK;
+		if (en < e1) {
+			ilfN = a.il[en]; mN[0] = a.mx[en]; mN[1] = a.my[en]; mN[2] = ilfN < 0 ? a.mz[en] : T(0); omN = a.om[en];
+			load_xw(a.Xw, ilfN & 0x7fffffff, XN);
+		}
 		edge_residual(q, t, c, X, m, stereo, Xc, r);
 		const T e2 = om * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
 		T rho, drho;
-		robust<T>(a.rk.type[stereo ? 1 : 0], (T)a.rk.delta[stereo ? 1 : 0], e2, rho, drho);
+		robust<T>(stereo ? a.rk.type[1] : a.rk.type[0], (T)(stereo ? a.rk.delta[1] : a.rk.delta[0]), e2, rho, drho);
 		const T w = om * drho;
 		T JP[3][6], JL[3][3];
 		edge_jacobians(q, c, Xc, stereo, JP, JL);

@@ -205,17 +205,21 @@ def test_device_and_host_structure_builders_agree(pkg, problems, name):
 
 @pytest.mark.parametrize("name", ["small", "kitti07_shaped"])
 def test_schur_kernels_agree(pkg, oracle, problems, name):
-    """tile-local Schur (cuba_schur2.cuh, opt-in) vs the destination-gather kernel k_schur (default) vs the oracle"""
+    """k_schur3 (six lanes per product, default) vs k_schur4 (+ cooperative loads, same bits) vs k_schur (lane per product) vs the tile-local pair (cuba_schur2.cuh) vs the oracle"""
     prob = problems(name); rk = KERNELS["huber"]
-    a = make_engine(pkg, prob, rk, schur_variant=2); b = make_engine(pkg, prob, rk)
+    a = make_engine(pkg, prob, rk, schur_variant=2); b = make_engine(pkg, prob, rk); c = make_engine(pkg, prob, rk, schur_variant=1)
+    d = make_engine(pkg, prob, rk, schur_variant=4)
     o = oracle.Oracle(prob, *rk)
-    a.linearize(); b.linearize(); o.compute_errors(); o.build_system()
+    a.linearize(); b.linearize(); c.linearize(); d.linearize(); o.compute_errors(); o.build_system()
     for lam in (1e3, 1.0):
-        assert a.solve(lam)[1] and b.solve(lam)[1] and o.solve(lam)
-        for nme, x, y, z in zip(("Hsc", "bsc", "invHll"), a.schur(), b.schur(), o.schur()):
+        assert a.solve(lam)[1] and b.solve(lam)[1] and c.solve(lam)[1] and d.solve(lam)[1] and o.solve(lam)
+        for x, y in zip(d.schur(), b.schur()):
+            assert np.array_equal(x, y)        # k_schur3 and k_schur4 sum in the same order
+        for nme, x, y, w, z in zip(("Hsc", "bsc", "invHll"), a.schur(), b.schur(), c.schur(), o.schur()):
             assert relerr(x, y) < 1e-12, nme
-            assert relerr(x, z) < STAGE_TOL, nme
-    a.close(); b.close()
+            assert relerr(w, y) < 1e-12, nme
+            assert relerr(y, z) < STAGE_TOL, nme
+    a.close(); b.close(); c.close(); d.close()
 
 
 def test_rejects_bad_problems(pkg, problems):
