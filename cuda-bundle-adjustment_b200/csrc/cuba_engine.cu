@@ -18,6 +18,7 @@
 #include "cuba_kernels.cuh"
 #include "cuba_pcg2.cuh"
 #include "cuba_pcg3.cuh"
+#include "cuba_pcg4.cuh"
 #include "cuba_schur2.cuh"
 #include "cuba_jh4.cuh"
 #include "cuba_schur3.cuh"
@@ -184,6 +185,15 @@ struct Engine : EngineBase {
 	DBuf<long long> pcgTiming;
 	DBuf<unsigned long long> llFlags;   // k_pcg3: [wFlag 2*6numP*2 | pFlag 2*2G*2 | abort word]
 	int pcg2Grid = 0, pcg2Cap = 0, pcg2NeedMax = 0, pcg2MaxRows = 0;
+	// two-level PCG (cuba_pcg4.cuh)
+	DBuf<T> cZx, cZhat, cAcInv;
+	DBuf<double> cAcP, cPart, cU;
+	DBuf<int> cAggRow, cNaPtr, cNaList, cNeedAgg, cInfo, cRowOf, cCbPtr, cCbList;
+	int pcg4A = 0, pcg4Gs = 1, pcg4MaxNeedAgg = 0, pcg4Cap = 0, pcg4SliceInSmem = 0;
+	size_t pcg4Smem = 0, pcg4InvSmem = 0;
+	bool pcg4Ok = false, tlActive = false;
+	bool coarseValid = false;       // cAcInv holds the inverse coarse matrix of an earlier solve of this problem
+	int coarseAge = 0;              // two-level solves since the coarse matrix was last rebuilt
 	bool pcg3Ok = false;
 	size_t pcg2Smem = 0;
 	// reductions
@@ -1029,8 +1039,116 @@ struct Engine : EngineBase {
 		CUDA_TRY(pcg2Partial.alloc(4 * (size_t)G));
 		CUDA_TRY(gridBar.alloc(1));
 		CUDA_TRY(cudaMemsetAsync(gridBar.p, 0, sizeof(GridBar), stream));
+		// ---- two-level PCG: aggregates = groups of gs consecutive CTAs (at most PCG4_MAXAGG of them) ----
+		{
+			const int gs = (G + PCG4_MAXAGG - 1) / PCG4_MAXAGG, A = (G + gs - 1) / gs, nc = 6 * A;
+			std::vector<int> aggRow(A + 1, numP);
+			for (int ag = 0; ag < A; ag++) aggRow[ag] = rows[std::min(ag * gs, G)];
+			std::vector<int> rowAgg(numP, 0);
+			for (int ag = 0; ag < A; ag++) for (int r = aggRow[ag]; r < aggRow[ag + 1]; r++) rowAgg[r] = ag;
+			std::vector<int> naPtr(G + 1, 0), naList, needAgg(ncol.size(), 0);
+			int maxNA = 0;
+			for (int c = 0; c < G; c++) {
+				std::vector<int> ags;
+				for (int k = nptr[c]; k < nptr[c + 1]; k++) ags.push_back(rowAgg[ncol[k]]);
+				std::sort(ags.begin(), ags.end());
+				ags.erase(std::unique(ags.begin(), ags.end()), ags.end());
+				naPtr[c] = (int)naList.size();
+				for (int k = nptr[c]; k < nptr[c + 1]; k++)
+					needAgg[k] = (int)(std::lower_bound(ags.begin(), ags.end(), rowAgg[ncol[k]]) - ags.begin());
+				naList.insert(naList.end(), ags.begin(), ags.end());
+				maxNA = std::max(maxNA, (int)ags.size());
+			}
+			naPtr[G] = (int)naList.size();
+			pcg4A = A; pcg4Gs = gs; pcg4MaxNeedAgg = std::max(maxNA, 1);
+			size_t fixed4 = (size_t)needMax * (48 * sizeof(T) + 8) + (size_t)maxRows * (6 * sizeof(T) + 8) + 8 + 2 * (size_t)nc * sizeof(T)
+				+ (size_t)pcg4MaxNeedAgg * (6 * sizeof(T) + 4) + 64;
+			// the CTA's slices of the inverse coarse matrix stay in shared memory when the whole A^ still fits beside them
+			const size_t sliceBytes = (size_t)pcg4MaxNeedAgg * 6 * nc * sizeof(T);
+			pcg4SliceInSmem = (budget > fixed4 + sliceBytes && (budget - fixed4 - sliceBytes) / (36 * sizeof(T) + 4) >= (size_t)blkMax) ? 1 : 0;
+			if (pcg4SliceInSmem) fixed4 += sliceBytes;
+			size_t cap4 = budget > fixed4 ? (budget - fixed4) / (36 * sizeof(T) + 4) : 0;
+			cap4 = std::min<size_t>(cap4, (size_t)blkMax);
+			pcg4Cap = (int)cap4;
+			pcg4Smem = (size_t)cap4 * (36 * sizeof(T) + 4) + fixed4;
+			pcg4InvSmem = ((size_t)A * (A + 1) / 2 + 2 * (size_t)A) * 36 * sizeof(double);
+			pcg4Ok = budget > fixed4 && nc + 64 <= PCG4_BLOCK && pcg4InvSmem + 1024 <= (size_t)smemMax && numP >= 2 * A;
+			if (pcg4Ok) {
+				CUDA_TRY(cudaFuncSetAttribute(k_pcg4<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pcg4Smem));
+				CUDA_TRY(cudaFuncSetAttribute(k_coarse_invert<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pcg4InvSmem));
+				int perSM4 = 0;
+				CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM4, k_pcg4<T>, PCG4_BLOCK, pcg4Smem));
+				if (perSM4 < 1) pcg4Ok = false;
+			}
+			if (pcg4Ok) {
+				CUDA_TRY(cAggRow.upload(aggRow, stream)); CUDA_TRY(cNaPtr.upload(naPtr, stream)); CUDA_TRY(cNaList.upload(naList, stream));
+				CUDA_TRY(cNeedAgg.upload(needAgg, stream));
+				// fine blocks of every coarse block (lower triangle), ascending -> fixed-order sums in k_coarse_assemble
+				const int nblkP = A * (A + 1) / 2;
+				std::vector<int> rowOf(S.nfull), cbPtr(nblkP + 1, 0), cbList;
+				for (int i = 0; i < numP; i++) for (int n = S.fRowPtr[i]; n < S.fRowPtr[i + 1]; n++) rowOf[n] = i;
+				auto cbOf = [&](int n) { const int ai = rowAgg[rowOf[n]], aj = rowAgg[S.fColInd[n]]; return ai >= aj ? ai * (ai + 1) / 2 + aj : -1; };
+				for (int n = 0; n < S.nfull; n++) { const int cb = cbOf(n); if (cb >= 0) cbPtr[cb + 1]++; }
+				for (int cb = 0; cb < nblkP; cb++) cbPtr[cb + 1] += cbPtr[cb];
+				cbList.resize(cbPtr[nblkP]);
+				{
+					std::vector<int> fill(cbPtr.begin(), cbPtr.end() - 1);
+					for (int n = 0; n < S.nfull; n++) { const int cb = cbOf(n); if (cb >= 0) cbList[fill[cb]++] = n; }
+				}
+				CUDA_TRY(cRowOf.upload(rowOf, stream)); CUDA_TRY(cCbPtr.upload(cbPtr, stream)); CUDA_TRY(cCbList.upload(cbList, stream));
+				CUDA_TRY(cZx.alloc(36 * (size_t)numP)); CUDA_TRY(cZhat.alloc(36 * (size_t)numP)); CUDA_TRY(cU.alloc(36 * (size_t)S.nfull));
+				CUDA_TRY(cAcP.alloc((size_t)A * (A + 1) / 2 * 36)); CUDA_TRY(cAcInv.alloc((size_t)nc * nc));
+				CUDA_TRY(cPart.alloc(2 * (size_t)G * PCG4_PSTRIDE)); CUDA_TRY(cInfo.alloc(1));
+				CUDA_TRY(cudaMemsetAsync(cPart.p, 0, sizeof(double) * cPart.n, stream));
+				CUDA_TRY(cudaStreamSynchronize(stream));      // the host vectors above die here
+			}
+			tlActive = false; coarseValid = false; coarseAge = 0;
+		}
 		return CUBA_OK;
 	}
+
+	// two-level PCG: coarse basis, coarse matrix and its inverse, then the cooperative solve
+	int launch_pcg4()
+	{
+		ProfScope ps(this, CUBA_PROF_DECOMP_NUMERICAL);
+		const int numP = S.numP, A = pcg4A, nblkP = A * (A + 1) / 2;
+		KLAUNCH(k_coarse_basis<T>, numP, pose[cur].p, numP, cZx.p);
+		// The coarse matrix Ac = Z^T S Z and its inverse are rebuilt only now and then: ANY symmetric positive definite
+		// stand-in for Ac^-1 keeps M^-1 = D^-1 + Z B Z^T a valid preconditioner, and the coarse operator of an earlier
+		// damping / linearisation preconditions as well as the current one (CPU prototype: 26..201 iterations over ten LM
+		// iterations with a fresh inverse, 26..193 with one that is refreshed every fifth iteration).
+		const int refreshEvery = cfg.reserved[4] > 0 ? cfg.reserved[4] : 8;
+		if (!coarseValid || coarseAge >= refreshEvery) {
+			KLAUNCH(k_coarse_project<T>, 36LL * S.nfull, fVal.p, cRowOf.p, fColInd.p, S.nfull, cZx.p, cU.p);
+			KLAUNCH(k_coarse_assemble, (long long)nblkP * 36, cCbPtr.p, cCbList.p, cU.p, nblkP, cAcP.p);
+			k_coarse_invert<T><<<1, 1024, pcg4InvSmem, stream>>>(cAcP.p, A, cAcInv.p, cInfo.p);
+			launches++;
+			CUDA_TRY(cudaGetLastError());
+			coarseValid = true; coarseAge = 0;
+		}
+		coarseAge++;
+		Pcg4Args<T> b;
+		Pcg2Args<T>& a = b.base;
+		a.fRowPtr = fRowPtr; a.fColInd = fColInd; a.fLocal = fLocal; a.fVal = fVal; a.fHat = fHat;
+		a.ctaRow = ctaRow; a.needPtr = needPtr; a.needCol = needCol; a.b = bsc; a.numP = S.numP; a.Linv = Linv;
+		a.R0 = vR0; a.R1 = vR1; a.S0 = vS0; a.S1 = vS1; a.W0 = vW0; a.W1 = vW1; a.P = vP; a.Y = vY; a.x = xp;
+		a.partial = pcg2Partial; a.bar = gridBar; a.capBlocks = pcg4Cap; a.needMax = pcg2NeedMax; a.maxRows = pcg2MaxRows;
+		a.maxIters = cfg.pcg_max_iters > 0 ? cfg.pcg_max_iters : std::max(200, 40 * S.numP);
+		const double tol = cfg.pcg_tol > 0 ? cfg.pcg_tol : (sizeof(T) == 8 ? 1e-11 : 1e-6);
+		a.tol2 = tol * tol;
+		a.status = &dScal.p->pcg;
+		b.Zx = cZx; b.Zhat = cZhat; b.AcInv = cAcInv; b.aggRow = cAggRow; b.naPtr = cNaPtr; b.naList = cNaList; b.needAgg = cNeedAgg;
+		b.A = A; b.gs = pcg4Gs; b.maxNeedAgg = pcg4MaxNeedAgg; b.sliceInSmem = pcg4SliceInSmem; b.cpart = cPart;
+		void* args[] = { (void*)&b };
+		CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_pcg4<T>, dim3(pcg2Grid), dim3(PCG4_BLOCK), args, pcg4Smem, stream));
+		launches++;
+		lastPcgTwoLevel = true;
+		return CUBA_OK;
+	}
+	bool lastPcgTwoLevel = false;
+	// policy of the default solver: block-Jacobi (k_pcg3) while it converges quickly, two-level once a solve needed more than
+	// PCG4_SWITCH_ITERS iterations (the count grows as the LM damping falls); decisions depend on iteration counts only
+	void note_pcg_iters(int iters) { if (!lastPcgTwoLevel && iters > 60) tlActive = true; }
 
 	int launch_pcg2(bool flagged)
 	{
@@ -1069,7 +1187,10 @@ struct Engine : EngineBase {
 
 	int launch_pcg()
 	{
-		if (cfg.reserved[0] == 0) return launch_pcg2(pcg3Ok);  // k_pcg3: flag-synchronised exchange (default; k_pcg2 beyond ~85 rows per CTA)
+		lastPcgTwoLevel = false;
+		// 0: automatic (block-Jacobi k_pcg3 while quick, two-level k_pcg4 afterwards); 3: always two-level; 4: always k_pcg3
+		if (pcg4Ok && (cfg.reserved[0] == 3 || (cfg.reserved[0] == 0 && tlActive))) return launch_pcg4();
+		if (cfg.reserved[0] == 0 || cfg.reserved[0] == 3 || cfg.reserved[0] == 4) return launch_pcg2(pcg3Ok);  // k_pcg3: flag-synchronised exchange (k_pcg2 beyond ~85 rows per CTA)
 		if (cfg.reserved[0] == 2) return launch_pcg2(false);   // k_pcg2: one grid barrier per iteration
 		ProfScope ps(this, CUBA_PROF_DECOMP_NUMERICAL);
 		PcgArgs<T> a;
@@ -1127,6 +1248,7 @@ struct Engine : EngineBase {
 		if (iters || ok) {
 			rc = fetchScalars(); if (rc) return rc;
 			const bool usedPcg = S.numP > 0 && S.numL > 0;
+			if (usedPcg) note_pcg_iters(hScal->pcg.iters);
 			if (iters) *iters = usedPcg ? hScal->pcg.iters : 0;
 			if (ok) *ok = usedPcg ? (hScal->pcg.status == 0) : 1;
 		}
@@ -1175,6 +1297,7 @@ struct Engine : EngineBase {
 		const double tau = 1e-5;
 		double nu = 2, lambda = 0, F = 0;
 		int n = 0;
+		tlActive = false;
 		bool haveF = false;
 		for (int it = 0; it < niter; it++) {
 			double chi0 = 0;
@@ -1195,7 +1318,7 @@ struct Engine : EngineBase {
 				rc = stage_solve(lambda, nullptr, nullptr); if (rc) return rc;
 				double Fhat = 0, scale = 0;
 				rc = stage_update(lambda, &Fhat, &scale); if (rc) return rc;
-				if (S.numP > 0 && S.numL > 0) { iters = hScal->pcg.iters; ok = hScal->pcg.status == 0; }
+				if (S.numP > 0 && S.numL > 0) { iters = hScal->pcg.iters; ok = hScal->pcg.status == 0; note_pcg_iters(iters); }
 				pcgIters += iters; if (!ok) pcgFailed++;
 				scale += 1e-3;
 				rho = ok ? (F - Fhat) / scale : -1;

@@ -143,9 +143,10 @@ def test_against_compiled_reference(pkg, problems, name, kernel):
     eng.close()
 
 
-@pytest.mark.parametrize("variant", [0, 2, 1])
+@pytest.mark.parametrize("variant", [0, 3, 4, 2, 1])
 def test_all_pcg_kernels_solve_the_same_system(pkg, oracle, problems, variant):
-    """k_pcg3 (flag-synchronised), k_pcg2 (single barrier) and k_pcg (first generation) against the direct solve"""
+    """automatic policy (0), two-level k_pcg4 (3), k_pcg3 (4, flag-synchronised), k_pcg2 (single barrier) and k_pcg (first
+    generation) against the direct solve"""
     prob = problems("kitti07_shaped"); rk = KERNELS["huber"]
     eng = make_engine(pkg, prob, rk, pcg_variant=variant)
     o = oracle.Oracle(prob, *rk)
@@ -324,3 +325,19 @@ def test_jh_landmark_kernels_agree(pkg, oracle, problems, name):
         assert abs(ref[0][0] - ochi) <= STAGE_TOL * ochi
         for nme, a, b in zip(("Hpp", "bp", "Hll", "bl", "Hpl"), ref[1:], o.system()):
             assert relerr(a, b) < STAGE_TOL, nme
+
+
+@pytest.mark.parametrize("name", ["kitti07_shaped", "kitti00_shaped"])
+def test_two_level_pcg_converges_faster_to_the_same_solution(pkg, problems, name):
+    """k_pcg4 (block-Jacobi + rigid-aggregate coarse correction) vs k_pcg3 (block-Jacobi) on the same reduced system at a low
+    damping: same solution to the CG tolerance, several times fewer iterations"""
+    prob = problems(name); rk = KERNELS["huber"]
+    a = make_engine(pkg, prob, rk, pcg_variant=3); b = make_engine(pkg, prob, rk, pcg_variant=4)
+    a.linearize(); b.linearize()
+    lam = 1e-8 * a.max_diagonal()
+    ia, oka = a.solve(lam); ib, okb = b.solve(lam)
+    assert oka and okb
+    for nme, x, y in zip(("xp", "xl"), a.delta(), b.delta()):
+        assert relerr(x, y) < 1e-7, (nme, ia, ib, relerr(x, y))
+    assert ia * 1.5 < ib, (ia, ib)
+    a.close(); b.close()
