@@ -186,10 +186,11 @@ struct Engine : EngineBase {
 	DBuf<unsigned long long> llFlags;   // k_pcg3: [wFlag 2*6numP*2 | pFlag 2*2G*2 | abort word]
 	int pcg2Grid = 0, pcg2Cap = 0, pcg2NeedMax = 0, pcg2MaxRows = 0;
 	// two-level PCG (cuba_pcg4.cuh)
-	DBuf<T> cZx, cZhat, cAcInv;
+	DBuf<T> cZx, cZhat;
+	DBuf<float> cAcInv;
 	DBuf<double> cAcP, cPart, cU;
 	DBuf<int> cAggRow, cNaPtr, cNaList, cNeedAgg, cInfo, cRowOf, cCbPtr, cCbList;
-	int pcg4A = 0, pcg4Gs = 1, pcg4MaxNeedAgg = 0, pcg4Cap = 0, pcg4SliceInSmem = 0;
+	int pcg4A = 0, pcg4Gs = 1, pcg4MaxNeedAgg = 0, pcg4Cap = 0, pcg4SliceInSmem = 0, pcg4ZhInSmem = 0;
 	size_t pcg4Smem = 0, pcg4InvSmem = 0;
 	bool pcg4Ok = false, tlActive = false;
 	bool coarseValid = false;       // cAcInv holds the inverse coarse matrix of an earlier solve of this problem
@@ -1061,16 +1062,22 @@ struct Engine : EngineBase {
 			}
 			naPtr[G] = (int)naList.size();
 			pcg4A = A; pcg4Gs = gs; pcg4MaxNeedAgg = std::max(maxNA, 1);
-			size_t fixed4 = (size_t)needMax * (48 * sizeof(T) + 8) + (size_t)maxRows * (6 * sizeof(T) + 8) + 8 + 2 * (size_t)nc * sizeof(T)
+			size_t fixed4 = (size_t)needMax * (12 * sizeof(T) + 8) + (size_t)maxRows * (6 * sizeof(T) + 8) + 8 + 2 * (size_t)nc * sizeof(T)
 				+ (size_t)pcg4MaxNeedAgg * (6 * sizeof(T) + 4) + 64;
-			// the CTA's slices of the inverse coarse matrix stay in shared memory when the whole A^ still fits beside them
-			const size_t sliceBytes = (size_t)pcg4MaxNeedAgg * 6 * nc * sizeof(T);
-			pcg4SliceInSmem = (budget > fixed4 + sliceBytes && (budget - fixed4 - sliceBytes) / (36 * sizeof(T) + 4) >= (size_t)blkMax) ? 1 : 0;
+			// shared-memory priorities: all of A^ first, then Z^ of the needed columns, then the CTA's slices of the inverse coarse matrix
+			const size_t matAll = (size_t)blkMax * (36 * sizeof(T) + 4);
+			const size_t zhBytes = (size_t)needMax * 36 * sizeof(T);
+			const size_t sliceBytes = (((size_t)pcg4MaxNeedAgg * 6 * nc + 1) & ~(size_t)1) * sizeof(float);
+			pcg4ZhInSmem = budget >= fixed4 + matAll + zhBytes ? 1 : 0;
+			if (pcg4ZhInSmem) fixed4 += zhBytes;
+			pcg4SliceInSmem = budget >= fixed4 + matAll + sliceBytes ? 1 : 0;
 			if (pcg4SliceInSmem) fixed4 += sliceBytes;
 			size_t cap4 = budget > fixed4 ? (budget - fixed4) / (36 * sizeof(T) + 4) : 0;
 			cap4 = std::min<size_t>(cap4, (size_t)blkMax);
 			pcg4Cap = (int)cap4;
 			pcg4Smem = (size_t)cap4 * (36 * sizeof(T) + 4) + fixed4;
+			if (getenv("CUBA_PCG_VERBOSE")) fprintf(stderr, "pcg4: G %d A %d gs %d needMax %d maxRows %d blkMax %d maxNeedAgg %d zhInSmem %d sliceInSmem %d cap %d smem %zu\n",
+				G, A, gs, needMax, maxRows, blkMax, pcg4MaxNeedAgg, pcg4ZhInSmem, pcg4SliceInSmem, pcg4Cap, pcg4Smem);
 			pcg4InvSmem = ((size_t)A * (A + 1) / 2 + 2 * (size_t)A) * 36 * sizeof(double);
 			pcg4Ok = budget > fixed4 && nc + 64 <= PCG4_BLOCK && pcg4InvSmem + 1024 <= (size_t)smemMax && numP >= 2 * A;
 			if (pcg4Ok) {
@@ -1138,7 +1145,7 @@ struct Engine : EngineBase {
 		a.tol2 = tol * tol;
 		a.status = &dScal.p->pcg;
 		b.Zx = cZx; b.Zhat = cZhat; b.AcInv = cAcInv; b.aggRow = cAggRow; b.naPtr = cNaPtr; b.naList = cNaList; b.needAgg = cNeedAgg;
-		b.A = A; b.gs = pcg4Gs; b.maxNeedAgg = pcg4MaxNeedAgg; b.sliceInSmem = pcg4SliceInSmem; b.cpart = cPart;
+		b.A = A; b.gs = pcg4Gs; b.maxNeedAgg = pcg4MaxNeedAgg; b.sliceInSmem = pcg4SliceInSmem; b.zhInSmem = pcg4ZhInSmem; b.cpart = cPart;
 		void* args[] = { (void*)&b };
 		CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_pcg4<T>, dim3(pcg2Grid), dim3(PCG4_BLOCK), args, pcg4Smem, stream));
 		launches++;
@@ -1146,9 +1153,10 @@ struct Engine : EngineBase {
 		return CUBA_OK;
 	}
 	bool lastPcgTwoLevel = false;
-	// policy of the default solver: block-Jacobi (k_pcg3) while it converges quickly, two-level once a solve needed more than
-	// PCG4_SWITCH_ITERS iterations (the count grows as the LM damping falls); decisions depend on iteration counts only
-	void note_pcg_iters(int iters) { if (!lastPcgTwoLevel && iters > 60) tlActive = true; }
+	// policy of the default solver: block-Jacobi (k_pcg3, ~5.4 us per iteration) while it converges quickly, two-level (k_pcg4,
+	// ~9 us per iteration but 2-8x fewer of them) once a block-Jacobi solve needed more than 150 iterations -- the count grows
+	// as the LM damping falls.  The decision depends on iteration counts only, so runs stay bit-reproducible.
+	void note_pcg_iters(int iters) { if (!lastPcgTwoLevel && iters > (cfg.reserved[5] > 0 ? cfg.reserved[5] : 150)) tlActive = true; }
 
 	int launch_pcg2(bool flagged)
 	{

@@ -38,13 +38,15 @@ struct Pcg4Args {
 	Pcg2Args<T> base;
 	const T* Zx;          // [numP][36] Ad(T_i), column-major
 	T* Zhat;              // [numP][36] L_i^T Z_i, written by the row's owner before the first barrier
-	const T* AcInv;       // [nc][nc] row-major (symmetric)
+	const float* AcInv;   // [nc][nc] row-major (symmetric), SINGLE precision: it only shapes the preconditioner -- every CTA
+	                      // applies the same rounded operator, so M^-1 stays one fixed symmetric matrix and CG stays exact
 	const int* aggRow;    // [A+1] first row of every aggregate (aggregates are groups of gs consecutive CTAs)
 	const int* naPtr;     // [G+1]
 	const int* naList;    // aggregates a CTA needs (sorted)
 	const int* needAgg;   // per need entry (indexing of needCol): position of its aggregate in the CTA's list
 	int A, gs, maxNeedAgg;
 	int sliceInSmem;      // 1: the CTA's slices of AcInv live in shared memory for the whole solve
+	int zhInSmem;         // 1: Z^ of the needed columns lives in shared memory (else it is read from L2 every pass)
 	double* cpart;        // [2][G][PCG4_PSTRIDE]
 };
 
@@ -90,9 +92,9 @@ __global__ void __launch_bounds__(PCG4_BLOCK, 1) k_pcg4(const Pcg4Args<T> aa)
 	T* s_rc = s_uown + (size_t)a.maxRows * 6;                           // [nc] coarse residual Z^^T r
 	T* s_sc = s_rc + nc;                                                // [nc] Z^^T s
 	T* s_c = s_sc + nc;                                                 // [maxNeedAgg][6] coarse correction of the needed aggregates
-	T* s_zh = s_c + (size_t)aa.maxNeedAgg * 6;                          // [needMax][36] Z^ of the needed columns
-	T* s_ai = s_zh + (size_t)a.needMax * 36;                            // [maxNeedAgg*6][nc] slices of AcInv (if sliceInSmem)
-	int* s_loc = reinterpret_cast<int*>(s_ai + (aa.sliceInSmem ? (size_t)aa.maxNeedAgg * 6 * nc : 0));  // [capBlocks]
+	T* s_zh = s_c + (size_t)aa.maxNeedAgg * 6;                          // [needMax][36] Z^ of the needed columns (if zhInSmem)
+	float* s_ai = reinterpret_cast<float*>(s_zh + (aa.zhInSmem ? (size_t)a.needMax * 36 : 0));   // [maxNeedAgg*6][nc] slices of AcInv (if sliceInSmem)
+	int* s_loc = reinterpret_cast<int*>(s_ai + (aa.sliceInSmem ? (((size_t)aa.maxNeedAgg * 6 * nc + 1) & ~(size_t)1) : 0));  // [capBlocks]
 	int* s_rowPtr = s_loc + a.capBlocks;                                // [maxRows+1]
 	int* s_need = s_rowPtr + a.maxRows + 1;                             // [needMax] global column of each need entry
 	int* s_nagg = s_need + a.needMax;                                   // [needMax] position of the column's aggregate in s_alist
@@ -173,7 +175,8 @@ __global__ void __launch_bounds__(PCG4_BLOCK, 1) k_pcg4(const Pcg4Args<T> aa)
 	__syncthreads();
 	nbad = s_bc[0];
 	// Z^ of the needed columns (published by their owners before the barrier) and the CTA's slices of AcInv
-	for (int wi = tid; wi < nneed * 36; wi += PCG4_BLOCK) s_zh[wi] = __ldcg(aa.Zhat + 36 * (size_t)s_need[wi / 36] + (wi % 36));
+	if (aa.zhInSmem)
+		for (int wi = tid; wi < nneed * 36; wi += PCG4_BLOCK) s_zh[wi] = __ldcg(aa.Zhat + 36 * (size_t)s_need[wi / 36] + (wi % 36));
 	if (aa.sliceInSmem)
 		for (int wi = tid; wi < nagg * 6 * nc; wi += PCG4_BLOCK) {
 			const int rowi = wi / nc, q = wi - rowi * nc;
@@ -311,12 +314,12 @@ __global__ void __launch_bounds__(PCG4_BLOCK, 1) k_pcg4(const Pcg4Args<T> aa)
 				T s = T(0);
 				if (rowi < nagg * 6) {
 					if (aa.sliceInSmem) {
-						const T* Arow = s_ai + (size_t)rowi * nc;
-						for (int q = sub; q < nc; q += PCG4_TPR) s += Arow[q] * s_rc[q];
+						const float* Arow = s_ai + (size_t)rowi * nc;
+						for (int q = sub; q < nc; q += PCG4_TPR) s += (T)Arow[q] * s_rc[q];
 					} else {
 						const int la = rowi / 6, comp = rowi - 6 * la;
-						const T* Arow = aa.AcInv + (size_t)(s_alist[la] * 6 + comp) * nc;
-						for (int q = sub; q < nc; q += PCG4_TPR) s += __ldg(Arow + q) * s_rc[q];
+						const float* Arow = aa.AcInv + (size_t)(s_alist[la] * 6 + comp) * nc;
+						for (int q = sub; q < nc; q += PCG4_TPR) s += (T)__ldg(Arow + q) * s_rc[q];
 					}
 				}
 #pragma unroll
@@ -327,11 +330,17 @@ __global__ void __launch_bounds__(PCG4_BLOCK, 1) k_pcg4(const Pcg4Args<T> aa)
 			// ---- u_j = r_j + Z^_j c_a(j) for every needed column ----
 			for (int wi = tid; wi < nneed * 6; wi += PCG4_BLOCK) {
 				const int c = wi / 6, comp = wi - 6 * c;
-				const T* Zh = s_zh + 36 * (size_t)c + comp;
 				const T* cc = s_c + 6 * (size_t)s_nagg[c];
 				T u = s_r[wi];
+				if (aa.zhInSmem) {
+					const T* Zh = s_zh + 36 * (size_t)c + comp;
 #pragma unroll
-				for (int q = 0; q < 6; q++) u += Zh[6 * q] * cc[q];
+					for (int q = 0; q < 6; q++) u += Zh[6 * q] * cc[q];
+				} else {
+					const T* Zh = aa.Zhat + 36 * (size_t)s_need[c] + comp;
+#pragma unroll
+					for (int q = 0; q < 6; q++) u += __ldcg(Zh + 6 * q) * cc[q];
+				}
 				s_u[wi] = u;
 			}
 			__syncthreads();
@@ -382,10 +391,10 @@ __global__ void __launch_bounds__(PCG4_BLOCK, 1) k_pcg4(const Pcg4Args<T> aa)
 					pr += (double)ri * (double)ri;
 				}
 				// Z^_i^T w_i: lane comp holds w_i[comp]; (Z^^T w)(q) = sum_comp Z^(comp,q) w(comp)
-				const T* Zh = s_zh + 36 * (size_t)dl;
+				const T* Zh = aa.zhInSmem ? s_zh + 36 * (size_t)dl : aa.Zhat + 36 * (size_t)(row0 + li);
 #pragma unroll
 				for (int q = 0; q < 6; q++) {
-					double t = lane < 6 ? (double)(Zh[6 * q + lane] * wv) : 0.0;
+					double t = lane < 6 ? (double)((aa.zhInSmem ? Zh[6 * q + lane] : __ldcg(Zh + 6 * q + lane)) * wv) : 0.0;
 					t += __shfl_xor_sync(0xffffffffu, t, 1); t += __shfl_xor_sync(0xffffffffu, t, 2); t += __shfl_xor_sync(0xffffffffu, t, 4);
 					pw[q] += t;                                  // lanes 0..7 hold the sum of lanes 0..7
 				}
@@ -486,7 +495,7 @@ __global__ void k_coarse_assemble(const int* __restrict__ cbPtr, const int* __re
 // AcInv = Ac^-1 by block Cholesky (6x6 blocks) of the packed lower triangle in shared memory: ONE CTA.
 // On a non-positive pivot the inverse is zeroed (the preconditioner degrades to block-Jacobi, still valid).
 template <typename T>
-__global__ void __launch_bounds__(1024, 1) k_coarse_invert(const double* __restrict__ AcP, int A, T* AcInv, int* info)
+__global__ void __launch_bounds__(1024, 1) k_coarse_invert(const double* __restrict__ AcP, int A, float* AcInv, int* info)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	double* B = reinterpret_cast<double*>(smem_raw);             // [nblkP][36] packed blocks
@@ -567,7 +576,7 @@ __global__ void __launch_bounds__(1024, 1) k_coarse_invert(const double* __restr
 		__syncthreads();
 	}
 	if (s_fail) {
-		for (int e = tid; e < nc * nc; e += NT) AcInv[e] = T(0);
+		for (int e = tid; e < nc * nc; e += NT) AcInv[e] = 0.f;
 		if (tid == 0 && info) *info = 1;
 		return;
 	}
@@ -608,8 +617,8 @@ __global__ void __launch_bounds__(1024, 1) k_coarse_invert(const double* __restr
 			const double* Wb = B + idx(k, jb);
 			for (int mm = 0; mm < 6; mm++) s += Wa[r * 6 + mm] * Wb[c * 6 + mm];
 		}
-		AcInv[(size_t)(ib * 6 + r) * nc + jb * 6 + c] = (T)s;
-		AcInv[(size_t)(jb * 6 + c) * nc + ib * 6 + r] = (T)s;
+		AcInv[(size_t)(ib * 6 + r) * nc + jb * 6 + c] = (float)s;
+		AcInv[(size_t)(jb * 6 + c) * nc + ib * 6 + r] = (float)s;
 	}
 	if (tid == 0 && info) *info = 0;
 }

@@ -73,13 +73,19 @@ typedef struct cuba_config {
 	int pcg_max_iters;     /* <=0: default                                         */
 	double pcg_tol;        /* stop when sqrt(r'z / r0'z0) <= pcg_tol; <=0: default 1e-11 (fp64)    */
 	int deterministic;     /* 1 (default): fixed-order reductions, bit-reproducible run to run     */
-	int reserved[7];       /* reserved[0]: PCG kernel, 0 = k_pcg3 (shared-memory resident, flag-synchronised exchange,
-	                          no barrier in the iteration; default), 2 = k_pcg2 (same, one grid barrier per iteration),
-	                          1 = k_pcg (first generation, two cooperative-groups syncs)
+	int reserved[7];       /* reserved[0]: reduced-system solver.  0 (default) = automatic: block-Jacobi PCG (k_pcg3: shared-memory
+	                          resident, flag-synchronised exchange, no barrier in the iteration) while it converges within
+	                          reserved[5] iterations, two-level PCG afterwards (k_pcg4: block-Jacobi + coarse correction over
+	                          rigid motions of pose aggregates, cuba_pcg4.cuh); 3 = always k_pcg4; 4 = always k_pcg3;
+	                          2 = k_pcg2 (one grid barrier per iteration); 1 = k_pcg (first generation)
 	                          reserved[1]: 1 = build the index structures on the host (cuba_structure.cpp) instead of
 	                          on the device (cuba_structure_gpu.cuh, default); both give identical structures
-	                          reserved[2]: J+H landmark kernel, 0 = k_linearize_landmark3 (default), 5 = ..._landmark2, 1-4 = first generation
-	                          reserved[3]: 2 = tile-local Schur kernels (cuba_schur2.cuh, experimental) instead of k_schur */
+	                          reserved[2]: J+H landmark kernel, 0 = k_linearize_landmark4 (warp tiles, default; 8/9 = 5/6 CTAs per SM,
+	                          7 = three pipeline stages), 6 = k_linearize_landmark3, 5 = ..._landmark2, 1-4 = first generation
+	                          reserved[3]: Schur kernel, 0 = k_schur3 (six lanes per product, default), 1 = k_schur (lane per product),
+	                          2 = tile-local pair (cuba_schur2.cuh), 4 = k_schur4 (cooperative loads; slower)
+	                          reserved[4]: two-level PCG: solves between rebuilds of the coarse matrix (<=0: 8)
+	                          reserved[5]: automatic solver: block-Jacobi iteration count that switches to two-level (<=0: 150) */
 } cuba_config;
 
 /* Flat problem: exactly what CudaBlockSolver::initialize produces (cpp:115-261).
