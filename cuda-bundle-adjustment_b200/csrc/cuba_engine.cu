@@ -148,6 +148,9 @@ struct Engine : EngineBase {
 	// warp-tile J+H landmark pass (cuba_jh4.cuh)
 	bool jhV4 = true;
 	int ntW = 0, jh4Grid = 0, jh4HasBig = 0, jh4MinB = 4, jh4Nst = 2;
+	const void* jh4AttrSet = nullptr;
+	int* jh4Host = nullptr;      // pinned: {number of warp tiles, any cut landmark}
+	bool jh4Pending = false;
 	DBuf<int> w_levels, w_start, w_pieces, w_base, w_tilePose, w_tilePieces, w_pieceCount, w_flag;
 	DBuf<jh4::WTile> w_tile;
 	DBuf<jh4::Rec> w_rec;
@@ -188,11 +191,11 @@ struct Engine : EngineBase {
 	// two-level PCG (cuba_pcg4.cuh)
 	DBuf<T> cZx, cZhat;
 	DBuf<float> cAcInv;
-	DBuf<double> cAcP, cPart, cU;
+	DBuf<double> cAcP, cPart, cU, cLp, cLd, cWp;
 	DBuf<int> cAggRow, cNaPtr, cNaList, cNeedAgg, cInfo, cRowOf, cCbPtr, cCbList;
 	int pcg4A = 0, pcg4Gs = 1, pcg4MaxNeedAgg = 0, pcg4Cap = 0, pcg4SliceInSmem = 0, pcg4ZhInSmem = 0;
 	size_t pcg4Smem = 0, pcg4InvSmem = 0;
-	bool pcg4Ok = false, tlActive = false;
+	bool pcg4Ok = false, tlActive = false, pcg4Cluster = false;
 	bool coarseValid = false;       // cAcInv holds the inverse coarse matrix of an earlier solve of this problem
 	int coarseAge = 0;              // two-level solves since the coarse matrix was last rebuilt
 	bool pcg3Ok = false;
@@ -212,6 +215,7 @@ struct Engine : EngineBase {
 		for (auto ev : eventPool) cudaEventDestroy(ev);
 		if (hScal) cudaFreeHost(hScal);
 		if (hMeta) cudaFreeHost(hMeta);
+		if (jh4Host) cudaFreeHost(jh4Host);
 		if (stream) cudaStreamDestroy(stream);
 		if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
 	}
@@ -591,6 +595,8 @@ struct Engine : EngineBase {
 		}
 		if (useSchur2) { int rc = setup_schur2(); if (rc) return rc; }
 		if (jhV4) { int rc = setup_jh4(); if (rc) return rc; }
+		if (S.numP > 0) { int rc = setup_pcg2(); if (rc) return rc; }        // host-heavy: overlaps the warp-tile kernels queued above
+		if (jhV4) { int rc = setup_jh4_finish(); if (rc) return rc; }
 		nChiLin = jhV4 ? jh4Grid : (jhV3 ? jh3Grid : ntiles);
 		nPoseBlocks = (S.numP + RED_BLOCK - 1) / RED_BLOCK;
 		nChiBlocks = std::max(1, std::min((eL + RED_BLOCK - 1) / RED_BLOCK, numSMs * 8));
@@ -608,7 +614,6 @@ struct Engine : EngineBase {
 			pcgGrid = std::max(1, std::min(wantBlocks, numSMs * std::min(perSM, 2)));
 			CUDA_TRY(pcgPartial.alloc(2 * (size_t)pcgGrid));
 		}
-		if (S.numP > 0) { int rc = setup_pcg2(); if (rc) return rc; }
 		return CUBA_OK;
 	}
 
@@ -689,7 +694,7 @@ struct Engine : EngineBase {
 					else if (jh4MinB == 5) JH4_PICK(5, 2, 0)
 					else JH4_PICK(6, 2, 0)
 				}
-				CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+				if (fn != jh4AttrSet) { CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); jh4AttrSet = fn; }   // once per kernel, not per launch
 				void* kargs[] = { (void*)&b };
 				CUDA_TRY(cudaLaunchKernel(fn, dim3(jh4Grid), dim3(jh4::WARPS * 32), kargs, smem, stream));
 #ifdef CUBA_JH4_DEBUG
@@ -919,11 +924,24 @@ struct Engine : EngineBase {
 				KLAUNCH(jh4::k_lift, N + 1, w_levels.p + (size_t)(k - 1) * ((size_t)N + 1), N, w_levels.p + (size_t)k * ((size_t)N + 1));
 			KLAUNCH(jh4::k_starts, N + 1, w_levels.p, K, N, lmPtr.p, lb, w_start.p, w_pieces.p, w_flag.p);
 			int rc = exclusiveSum(w_pieces.p, w_base.p, N + 1); if (rc) return rc;
-			int total = 0, big = 0;
-			CUDA_TRY(cudaMemcpyAsync(&total, w_base.p + N, sizeof(int), cudaMemcpyDeviceToHost, stream));
-			CUDA_TRY(cudaMemcpyAsync(&big, w_flag.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+			if (!jh4Host) CUDA_TRY(cudaMallocHost((void**)&jh4Host, 2 * sizeof(int)));
+			CUDA_TRY(cudaMemcpyAsync(&jh4Host[0], w_base.p + N, sizeof(int), cudaMemcpyDeviceToHost, stream));
+			CUDA_TRY(cudaMemcpyAsync(&jh4Host[1], w_flag.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+			jh4Pending = true;
+		}
+		return CUBA_OK;
+	}
+	// second half of the warp-tile setup: the host work of setup_pcg2 runs between the two halves, overlapping the kernels above
+	int setup_jh4_finish()
+	{
+		if (!jh4Pending) return CUBA_OK;
+		jh4Pending = false;
+		if constexpr (sizeof(T) == 8) {
+			using namespace jh4;
+			const int lb = S.lmBeg, N = S.lmEnd - S.lmBeg;
 			CUDA_TRY(cudaStreamSynchronize(stream));
-			ntW = total; jh4HasBig = big;
+			const int big = jh4Host[1];
+			ntW = jh4Host[0]; jh4HasBig = big;
 			if (ntW <= 0) return CUBA_OK;
 			CUDA_TRY(w_tile.alloc(ntW)); CUDA_TRY(w_rec.alloc(ntW)); CUDA_TRY(w_tilePose.alloc(32 * (size_t)ntW)); CUDA_TRY(w_tilePieces.alloc(ntW)); CUDA_TRY(w_pieceCount.alloc(ntW));
 			CUDA_TRY(cudaMemsetAsync(w_pieceCount.p, 0, sizeof(int) * (size_t)ntW, stream));
@@ -1042,7 +1060,10 @@ struct Engine : EngineBase {
 		CUDA_TRY(cudaMemsetAsync(gridBar.p, 0, sizeof(GridBar), stream));
 		// ---- two-level PCG: aggregates = groups of gs consecutive CTAs (at most PCG4_MAXAGG of them) ----
 		{
-			const int gs = (G + PCG4_MAXAGG - 1) / PCG4_MAXAGG, A = (G + gs - 1) / gs, nc = 6 * A;
+			// up to 74 aggregates (coarse inverse in the shared memory of an 8-CTA cluster), 37 with cfg.reserved[6] == 37 (one CTA)
+			const int maxAgg = (cfg.reserved[6] > 0 && cfg.reserved[6] < PCG4_MAXAGG) ? cfg.reserved[6] : PCG4_MAXAGG;
+			const int gs = (G + maxAgg - 1) / maxAgg, A = (G + gs - 1) / gs, nc = 6 * A;
+			pcg4Cluster = A > PCG4_MAXAGG1;
 			std::vector<int> aggRow(A + 1, numP);
 			for (int ag = 0; ag < A; ag++) aggRow[ag] = rows[std::min(ag * gs, G)];
 			std::vector<int> rowAgg(numP, 0);
@@ -1078,11 +1099,14 @@ struct Engine : EngineBase {
 			pcg4Smem = (size_t)cap4 * (36 * sizeof(T) + 4) + fixed4;
 			if (getenv("CUBA_PCG_VERBOSE")) fprintf(stderr, "pcg4: G %d A %d gs %d needMax %d maxRows %d blkMax %d maxNeedAgg %d zhInSmem %d sliceInSmem %d cap %d smem %zu\n",
 				G, A, gs, needMax, maxRows, blkMax, pcg4MaxNeedAgg, pcg4ZhInSmem, pcg4SliceInSmem, pcg4Cap, pcg4Smem);
-			pcg4InvSmem = ((size_t)A * (A + 1) / 2 + 2 * (size_t)A) * 36 * sizeof(double);
+			const size_t nblkPz = (size_t)A * (A + 1) / 2;
+			pcg4InvSmem = pcg4Cluster ? (((nblkPz + PCG4_CL - 1) / PCG4_CL + 2 * (size_t)A) * 36 * sizeof(double) + 2 * nblkPz + 16)
+			                          : ((nblkPz + 2 * (size_t)A) * 36 * sizeof(double));
 			pcg4Ok = budget > fixed4 && nc + 64 <= PCG4_BLOCK && pcg4InvSmem + 1024 <= (size_t)smemMax && numP >= 2 * A;
 			if (pcg4Ok) {
 				CUDA_TRY(cudaFuncSetAttribute(k_pcg4<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pcg4Smem));
-				CUDA_TRY(cudaFuncSetAttribute(k_coarse_invert<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pcg4InvSmem));
+				if (pcg4Cluster) CUDA_TRY(cudaFuncSetAttribute(k_coarse_chol_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pcg4InvSmem));
+				else CUDA_TRY(cudaFuncSetAttribute(k_coarse_invert<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pcg4InvSmem));
 				int perSM4 = 0;
 				CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM4, k_pcg4<T>, PCG4_BLOCK, pcg4Smem));
 				if (perSM4 < 1) pcg4Ok = false;
@@ -1105,6 +1129,7 @@ struct Engine : EngineBase {
 				CUDA_TRY(cRowOf.upload(rowOf, stream)); CUDA_TRY(cCbPtr.upload(cbPtr, stream)); CUDA_TRY(cCbList.upload(cbList, stream));
 				CUDA_TRY(cZx.alloc(36 * (size_t)numP)); CUDA_TRY(cZhat.alloc(36 * (size_t)numP)); CUDA_TRY(cU.alloc(36 * (size_t)S.nfull));
 				CUDA_TRY(cAcP.alloc((size_t)A * (A + 1) / 2 * 36)); CUDA_TRY(cAcInv.alloc((size_t)nc * nc));
+				CUDA_TRY(cLp.alloc((size_t)A * (A + 1) / 2 * 36)); CUDA_TRY(cWp.alloc((size_t)A * (A + 1) / 2 * 36)); CUDA_TRY(cLd.alloc((size_t)A * 36));
 				CUDA_TRY(cPart.alloc(2 * (size_t)G * PCG4_PSTRIDE)); CUDA_TRY(cInfo.alloc(1));
 				CUDA_TRY(cudaMemsetAsync(cPart.p, 0, sizeof(double) * cPart.n, stream));
 				CUDA_TRY(cudaStreamSynchronize(stream));      // the host vectors above die here
@@ -1128,7 +1153,14 @@ struct Engine : EngineBase {
 		if (!coarseValid || coarseAge >= refreshEvery) {
 			KLAUNCH(k_coarse_project<T>, 36LL * S.nfull, fVal.p, cRowOf.p, fColInd.p, S.nfull, cZx.p, cU.p);
 			KLAUNCH(k_coarse_assemble, (long long)nblkP * 36, cCbPtr.p, cCbList.p, cU.p, nblkP, cAcP.p);
-			k_coarse_invert<T><<<1, 1024, pcg4InvSmem, stream>>>(cAcP.p, A, cAcInv.p, cInfo.p);
+			if (pcg4Cluster) {
+				// Cholesky in the shared memory of an 8-CTA cluster, then the triangular inverse (one CTA per block column) and W^T W on the whole chip
+				k_coarse_chol_cluster<<<PCG4_CL, 1024, pcg4InvSmem, stream>>>(cAcP.p, A, cLp.p, cLd.p, cAcInv.p, cInfo.p);
+				k_coarse_trinv<<<A, 256, (size_t)A * 36 * sizeof(double), stream>>>(cLp.p, cLd.p, A, cWp.p, cInfo.p);
+				k_coarse_wtw<<<(nblkP * 36 + 255) / 256, 256, 0, stream>>>(cWp.p, A, cAcInv.p, cInfo.p);
+				launches += 2;
+			}
+			else k_coarse_invert<T><<<1, 1024, pcg4InvSmem, stream>>>(cAcP.p, A, cAcInv.p, cInfo.p);
 			launches++;
 			CUDA_TRY(cudaGetLastError());
 			coarseValid = true; coarseAge = 0;
@@ -1146,6 +1178,11 @@ struct Engine : EngineBase {
 		a.status = &dScal.p->pcg;
 		b.Zx = cZx; b.Zhat = cZhat; b.AcInv = cAcInv; b.aggRow = cAggRow; b.naPtr = cNaPtr; b.naList = cNaList; b.needAgg = cNeedAgg;
 		b.A = A; b.gs = pcg4Gs; b.maxNeedAgg = pcg4MaxNeedAgg; b.sliceInSmem = pcg4SliceInSmem; b.zhInSmem = pcg4ZhInSmem; b.cpart = cPart;
+		b.timing = nullptr;
+#ifdef CUBA_PCG_TIMING
+		CUDA_TRY(pcgTiming.alloc(8 * (size_t)pcg2Grid));
+		b.timing = pcgTiming.p;
+#endif
 		void* args[] = { (void*)&b };
 		CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_pcg4<T>, dim3(pcg2Grid), dim3(PCG4_BLOCK), args, pcg4Smem, stream));
 		launches++;
@@ -1305,7 +1342,7 @@ struct Engine : EngineBase {
 		const double tau = 1e-5;
 		double nu = 2, lambda = 0, F = 0;
 		int n = 0;
-		tlActive = false;
+		tlActive = false; coarseValid = false; coarseAge = 0;     // results never depend on what the engine solved before
 		bool haveF = false;
 		for (int it = 0; it < niter; it++) {
 			double chi0 = 0;

@@ -24,13 +24,15 @@
 // Replaces convertBSRToCSR + cuSOLVER csrchol (reference cuda_linear_solver.cpp:301-335) like the other PCG kernels.
 #pragma once
 
-#include "cuba_pcg2.cuh"
+#include "cuba_pcg3.cuh"
 
 namespace cuba_b200 {
 
 constexpr int PCG4_BLOCK = 512;
 constexpr int PCG4_PSTRIDE = 12;    // doubles per CTA on the partial board: gamma, delta, rho, -, wc[6], -, -
-constexpr int PCG4_MAXAGG = 37;     // the packed block triangle of the coarse matrix must fit one CTA's shared memory
+constexpr int PCG4_MAXAGG = 74;     // k_coarse_invert_cluster: the packed block triangle lives in the shared memory of an 8-CTA cluster
+constexpr int PCG4_MAXAGG1 = 37;    // k_coarse_invert: ... of one CTA
+constexpr int PCG4_CL = 8;          // CTAs per cluster of k_coarse_invert_cluster
 constexpr int PCG4_TPR = 16;        // threads per row of the coarse slice product
 
 template <typename T>
@@ -48,6 +50,7 @@ struct Pcg4Args {
 	int sliceInSmem;      // 1: the CTA's slices of AcInv live in shared memory for the whole solve
 	int zhInSmem;         // 1: Z^ of the needed columns lives in shared memory (else it is read from L2 every pass)
 	double* cpart;        // [2][G][PCG4_PSTRIDE]
+	long long* timing;    // [G][8] per-phase clock64 sums of thread 0 (only with -DCUBA_PCG_TIMING)
 };
 
 // lower Cholesky factor L and its inverse of a 6x6 SPD block (column-major); false if not positive definite
@@ -217,6 +220,9 @@ __global__ void __launch_bounds__(PCG4_BLOCK, 1) k_pcg4(const Pcg4Args<T> aa)
 
 	int status = 1, it = 0;
 	double gamma = 0, rho0 = 0, rho = 0, alpha = 0, beta = 0;
+#ifdef CUBA_PCG_TIMING
+	long long tacc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+#endif
 	if (nbad > 0) status = 2;
 	else {
 		// pass k = -1: u0 = M^-1 r0, w0 = A^ u0 and the first inner products; pass k >= 0: CG iteration k
@@ -229,6 +235,7 @@ __global__ void __launch_bounds__(PCG4_BLOCK, 1) k_pcg4(const Pcg4Args<T> aa)
 			const T* Sprev = (par == 0) ? a.S1 : a.S0;
 			T* Scur = (par == 0) ? a.S0 : a.S1;
 			const double* src = aa.cpart + (size_t)(1 - par) * G * PCG4_PSTRIDE;   // written in pass k-1 (S1 for k = -1)
+			PCG_T(t0);
 			// ---- prefetch the first gather item of every thread (independent of alpha/beta) ----
 			T g_r = T(0), g_w = T(0), g_s = T(0);
 			if (tid < nneed * 6) {
@@ -277,6 +284,7 @@ __global__ void __launch_bounds__(PCG4_BLOCK, 1) k_pcg4(const Pcg4Args<T> aa)
 				}
 				if (k >= a.maxIters) { status = 1; break; }
 			}
+			PCG_T(t1);
 			// ---- coarse residual: rc0 = sum of the S1 partials; later sc = wc + beta sc, rc -= alpha sc ----
 			if (tid >= 64 && tid < 64 + nc) {
 				const int q = tid - 64;
@@ -308,6 +316,7 @@ __global__ void __launch_bounds__(PCG4_BLOCK, 1) k_pcg4(const Pcg4Args<T> aa)
 				s_r[wi] = (k < 0) ? __ldcg(a.R0 + o) : __ldcg(Rin + o) - (T)alpha * (__ldcg(Win + o) + (T)beta * __ldcg(Sprev + o));
 			}
 			__syncthreads();
+			PCG_T(t2);
 			// ---- c_a = (Ac^-1 rc)_a for the needed aggregates: PCG4_TPR threads per row, fixed-order butterfly ----
 			for (int rb = 0; rb < nagg * 6; rb += PCG4_BLOCK / PCG4_TPR) {
 				const int rowi = rb + tid / PCG4_TPR, sub = tid % PCG4_TPR;
@@ -327,6 +336,7 @@ __global__ void __launch_bounds__(PCG4_BLOCK, 1) k_pcg4(const Pcg4Args<T> aa)
 				if (rowi < nagg * 6 && sub == 0) s_c[rowi] = s;
 			}
 			__syncthreads();
+			PCG_T(t3);
 			// ---- u_j = r_j + Z^_j c_a(j) for every needed column ----
 			for (int wi = tid; wi < nneed * 6; wi += PCG4_BLOCK) {
 				const int c = wi / 6, comp = wi - 6 * c;
@@ -344,6 +354,7 @@ __global__ void __launch_bounds__(PCG4_BLOCK, 1) k_pcg4(const Pcg4Args<T> aa)
 				s_u[wi] = u;
 			}
 			__syncthreads();
+			PCG_T(t4);
 			// ---- w_{k+1} = A^ u_{k+1} for the own rows (warp per row), partials of gamma', delta, rho', Z^^T w ----
 			double pg = 0, pd = 0, pr = 0, pw[6] = { 0, 0, 0, 0, 0, 0 };
 			for (int li = wid; li < nrows; li += PCG4_BLOCK / 32) {
@@ -400,6 +411,7 @@ __global__ void __launch_bounds__(PCG4_BLOCK, 1) k_pcg4(const Pcg4Args<T> aa)
 				}
 			}
 			// ---- publish the partials, one grid barrier ----
+			PCG_T(t5);
 			pg = warp_sum(pg); pd = warp_sum(pd); pr = warp_sum(pr);
 			if (lane == 0) {
 				s_red[wid][0] = pg; s_red[wid][1] = pd; s_red[wid][2] = pr;
@@ -413,7 +425,10 @@ __global__ void __launch_bounds__(PCG4_BLOCK, 1) k_pcg4(const Pcg4Args<T> aa)
 				double* dst = aa.cpart + ((size_t)par * G + cta) * PCG4_PSTRIDE;
 				dst[tid < 3 ? tid : tid + 1] = v;                // 0,1,2 = gamma, delta, rho; 4..9 = wc
 			}
+			PCG_T(t6);
 			grid_barrier(a.bar, G, gen);
+			PCG_T(t7);
+			PCG_ACC(0, t0, t1); PCG_ACC(1, t1, t2); PCG_ACC(2, t2, t3); PCG_ACC(3, t3, t4); PCG_ACC(4, t4, t5); PCG_ACC(5, t5, t6); PCG_ACC(6, t6, t7);
 		}
 	}
 	// ---- x = L^-T y for the own rows ----
@@ -424,6 +439,9 @@ __global__ void __launch_bounds__(PCG4_BLOCK, 1) k_pcg4(const Pcg4Args<T> aa)
 		for (int c = r; c < 6; c++) s += Li[r * 6 + c] * a.Y[6 * (size_t)i + c];
 		a.x[6 * (size_t)i + r] = s;
 	}
+#ifdef CUBA_PCG_TIMING
+	if (tid == 0 && aa.timing) { for (int i = 0; i < 7; i++) aa.timing[(size_t)cta * 8 + i] = tacc[i]; aa.timing[(size_t)cta * 8 + 7] = it; }
+#endif
 	if (cta == 0 && tid == 0) { a.status->iters = it; a.status->status = status; a.status->rz0 = rho0; a.status->rz = rho; }
 }
 
@@ -503,7 +521,7 @@ __global__ void __launch_bounds__(1024, 1) k_coarse_invert(const double* __restr
 	double* sLi = B + (size_t)nblkP * 36;                        // [A][36] inverses of the diagonal factors
 	double* sRow = sLi + (size_t)A * 36;                         // [A][36] scratch row
 	__shared__ int s_fail;
-	__shared__ unsigned char s_ib[PCG4_MAXAGG * (PCG4_MAXAGG + 1) / 2], s_jb[PCG4_MAXAGG * (PCG4_MAXAGG + 1) / 2];   // packed index -> (ib, jb)
+	__shared__ unsigned char s_ib[PCG4_MAXAGG1 * (PCG4_MAXAGG1 + 1) / 2], s_jb[PCG4_MAXAGG1 * (PCG4_MAXAGG1 + 1) / 2];   // packed index -> (ib, jb)
 	__shared__ double s_L[36], s_id[6];
 	const int tid = threadIdx.x, NT = blockDim.x;
 	auto idx = [](int ib, int jb) { return (size_t)(ib * (ib + 1) / 2 + jb) * 36; };
@@ -621,6 +639,203 @@ __global__ void __launch_bounds__(1024, 1) k_coarse_invert(const double* __restr
 		AcInv[(size_t)(jb * 6 + c) * nc + ib * 6 + r] = (float)s;
 	}
 	if (tid == 0 && info) *info = 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// The same inversion for up to PCG4_MAXAGG aggregates: the packed triangle (74 aggregates: 2 775 blocks, 800 KB) is
+// spread over the shared memory of an 8-CTA thread-block cluster, block b in CTA b % 8 (distributed shared memory);
+// every CTA updates the blocks it owns and reads the others' through cluster.map_shared_rank.  cluster.sync() between
+// phases.  Same arithmetic and summation order as k_coarse_invert.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(PCG4_CL, 1, 1) __launch_bounds__(1024, 1)
+k_coarse_chol_cluster(const double* __restrict__ AcP, int A, double* Lp, double* Ld, float* AcInv, int* info)
+{
+	namespace cgx = cooperative_groups;
+	cgx::cluster_group cluster = cgx::this_cluster();
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int nblkP = A * (A + 1) / 2, nc = 6 * A;
+	const int nloc = (nblkP + PCG4_CL - 1) / PCG4_CL;              // blocks per CTA
+	double* Bl = reinterpret_cast<double*>(smem_raw);              // [nloc][36] own blocks: local slot lb holds block lb * 8 + rank
+	double* sLiL = Bl + (size_t)nloc * 36;                         // [A][36] inverses of the diagonal factors (rank 0's copy is the one in use)
+	double* sScr = sLiL + (size_t)A * 36;                          // [A][36] scratch (phase 2), [36] scratch of the diagonal factorisation
+	unsigned char* s_ib = reinterpret_cast<unsigned char*>(sScr + (size_t)A * 36);   // [nblkP] packed index -> (ib, jb)
+	unsigned char* s_jb = s_ib + nblkP;
+	__shared__ int s_fail;
+	const int rank = (int)cluster.block_rank(), tid = threadIdx.x, NT = blockDim.x;
+	double* base[PCG4_CL];
+#pragma unroll
+	for (int r = 0; r < PCG4_CL; r++) base[r] = cluster.map_shared_rank(Bl, r);
+	double* sLi0 = cluster.map_shared_rank(sLiL, 0);
+	int* fail0 = cluster.map_shared_rank(&s_fail, 0);
+	auto blk = [&](int ib, int jb) -> double* { const int b = ib * (ib + 1) / 2 + jb; return base[b & (PCG4_CL - 1)] + (size_t)(b / PCG4_CL) * 36; };
+	for (int e = tid; e < nloc * 36; e += NT) {
+		const int b = (e / 36) * PCG4_CL + rank;
+		Bl[e] = b < nblkP ? AcP[(size_t)b * 36 + (e % 36)] : 0.0;
+	}
+	for (int ib = tid; ib < A; ib += NT) for (int jb = 0; jb <= ib; jb++) { s_ib[ib * (ib + 1) / 2 + jb] = (unsigned char)ib; s_jb[ib * (ib + 1) / 2 + jb] = (unsigned char)jb; }
+	if (tid == 0) s_fail = 0;
+	cluster.sync();
+	// ---- phase 1: block Cholesky ----
+	for (int kb = 0; kb < A; kb++) {
+		if (rank == 0 && tid < 32) {
+			// copy the diagonal block here, factor it in place (lane r owns row r), write L back and L^-1 to sLi (this CTA's copy)
+			double* D = sScr;
+			double* Dg = blk(kb, kb);
+			for (int e = tid; e < 36; e += 32) D[e] = Dg[e];
+			__syncwarp();
+			const int r = tid;
+			for (int j = 0; j < 6; j++) {
+				const double d = D[j * 6 + j];
+				if (!(d > 0)) { if (r == 0) s_fail = 1; break; }
+				const double sq = sqrt(d);
+				__syncwarp();
+				if (r == j) D[j * 6 + j] = sq;
+				else if (r > j && r < 6) D[j * 6 + r] = D[j * 6 + r] / sq;
+				__syncwarp();
+				if (r > j && r < 6)
+					for (int c = j + 1; c <= r; c++) D[c * 6 + r] -= D[j * 6 + r] * D[j * 6 + c];
+				__syncwarp();
+			}
+			__syncwarp();
+			__shared__ double s_id[6];
+			if (r < 6) {
+				for (int c = r + 1; c < 6; c++) D[c * 6 + r] = 0.0;
+				s_id[r] = 1.0 / D[r * 6 + r];
+			}
+			__syncwarp();
+			if (r < 6) {
+				const int q = r;
+				double col[6];
+				for (int i = 0; i < 6; i++) col[i] = 0.0;
+				col[q] = s_id[q];
+				for (int i = q + 1; i < 6; i++) {
+					double sum = 0;
+					for (int k = q; k < i; k++) sum += D[k * 6 + i] * col[k];
+					col[i] = -sum * s_id[i];
+				}
+				for (int i = 0; i < 6; i++) sLiL[(size_t)kb * 36 + q * 6 + i] = col[i];
+			}
+			__syncwarp();
+			for (int e = tid; e < 36; e += 32) Dg[e] = D[e];
+		}
+		cluster.sync();
+		if (*fail0) break;
+		// panel + trailing update of the blocks this CTA owns
+		const double* Li = sLi0 + (size_t)kb * 36;
+		for (int w = tid; w < nloc * 6; w += NT) {            // panel: one thread per (own block, row)
+			const int lb = w / 6, r = w - 6 * lb, b = lb * PCG4_CL + rank;
+			if (b >= nblkP) continue;
+			const int ib = s_ib[b], jb = s_jb[b];
+			if (jb != kb || ib <= kb) continue;
+			double* X = Bl + (size_t)lb * 36;
+			double x[6], y[6];
+			for (int k = 0; k < 6; k++) x[k] = X[k * 6 + r];
+			for (int c = 0; c < 6; c++) { double sm = 0; for (int k = 0; k <= c; k++) sm += x[k] * Li[k * 6 + c]; y[c] = sm; }
+			for (int c = 0; c < 6; c++) X[c * 6 + r] = y[c];
+		}
+		cluster.sync();
+		for (int w = tid; w < nloc * 36; w += NT) {           // trailing: one thread per (own block, entry)
+			const int lb = w / 36, rc = w - 36 * lb, c = rc / 6, r = rc - 6 * c, b = lb * PCG4_CL + rank;
+			if (b >= nblkP) continue;
+			const int ib = s_ib[b], jb = s_jb[b];
+			if (jb <= kb) continue;                            // ib >= jb > kb
+			const double* P = blk(ib, kb);
+			const double* Q = blk(jb, kb);
+			double sm = 0;
+			for (int k = 0; k < 6; k++) sm += P[k * 6 + r] * Q[k * 6 + c];
+			Bl[(size_t)lb * 36 + rc] -= sm;
+		}
+		cluster.sync();
+	}
+	if (*fail0) {
+		for (int e = rank * NT + tid; e < nc * nc; e += PCG4_CL * NT) AcInv[e] = 0.f;
+		if (rank == 0 && tid == 0 && info) *info = 1;
+		cluster.sync();
+		return;
+	}
+	// ---- the factor L (packed, block b at Lp + 36 b) and the inverses of its diagonal blocks leave for k_coarse_trinv ----
+	for (int e = tid; e < nloc * 36; e += NT) {
+		const int b = (e / 36) * PCG4_CL + rank;
+		if (b < nblkP) Lp[(size_t)b * 36 + (e % 36)] = Bl[e];
+	}
+	if (rank == 0) for (int e = tid; e < A * 36; e += NT) Ld[e] = sLiL[e];
+	if (rank == 0 && tid == 0 && info) *info = 0;
+	cluster.sync();                                            // nobody leaves while its shared memory may still be read
+}
+
+
+// W = L^-1 (block lower triangular), one CTA per block column jb: W(jb,jb) = L_jj^-1,
+// W(ib,jb) = -L_ii^-1 sum_{k=jb}^{ib-1} L(ib,k) W(k,jb).  The columns are independent; a column is sequential in ib.
+constexpr int PCG4_KS = 7;      // k-slices of the inner sum (36 entries x 7 slices = 252 threads)
+__global__ void __launch_bounds__(256) k_coarse_trinv(const double* __restrict__ Lp, const double* __restrict__ Ld, int A, double* Wp, const int* __restrict__ info)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	double* Wcol = reinterpret_cast<double*>(smem_raw);          // [A][36] this column of W (rows < jb unused)
+	__shared__ double s_part[PCG4_KS][36], s_S[36];
+	if (*info != 0) return;
+	const int jb = blockIdx.x, tid = threadIdx.x;
+	const int e = tid % 36, sl = tid / 36, c = e / 6, r = e - 6 * c;
+	auto pidx = [](int ib, int kb) { return (size_t)(ib * (ib + 1) / 2 + kb) * 36; };
+	if (tid < 36) { const double v = Ld[(size_t)jb * 36 + tid]; Wcol[(size_t)jb * 36 + tid] = v; Wp[pidx(jb, jb) + tid] = v; }
+	__syncthreads();
+	for (int ib = jb + 1; ib < A; ib++) {
+		if (sl < PCG4_KS) {
+			double sm = 0;
+			for (int k = jb + sl; k < ib; k += PCG4_KS) {
+				const double* Lb = Lp + pidx(ib, k);
+				const double* Wb = Wcol + (size_t)k * 36;
+#pragma unroll
+				for (int mm = 0; mm < 6; mm++) sm += Lb[mm * 6 + r] * Wb[c * 6 + mm];
+			}
+			s_part[sl][e] = sm;
+		}
+		__syncthreads();
+		if (tid < 36) {
+			double sm = 0;
+#pragma unroll
+			for (int q = 0; q < PCG4_KS; q++) sm += s_part[q][tid];
+			s_S[tid] = sm;
+		}
+		__syncthreads();
+		if (tid < 36) {
+			const double* Li = Ld + (size_t)ib * 36;
+			double sm = 0;
+			for (int k = 0; k <= r; k++) sm += Li[k * 6 + r] * s_S[c * 6 + k];
+			Wcol[(size_t)ib * 36 + tid] = -sm;
+			Wp[pidx(ib, jb) + tid] = -sm;
+		}
+		__syncthreads();
+	}
+}
+
+// Ac^-1 = W^T W: one thread per entry of the lower block triangle, written to both triangles of the full fp32 matrix
+__global__ void k_coarse_wtw(const double* __restrict__ Wp, int A, float* AcInv, const int* __restrict__ info)
+{
+	const int w = blockIdx.x * blockDim.x + threadIdx.x;
+	const int nblkP = A * (A + 1) / 2, nc = 6 * A;
+	if (w >= nblkP * 36 || *info != 0) return;
+	const int bq = w / 36, rc = w - 36 * bq, c = rc / 6, r = rc - 6 * c;
+	int ib = (int)((sqrt(8.0 * bq + 1.0) - 1.0) * 0.5);
+	while ((ib + 1) * (ib + 2) / 2 <= bq) ib++;
+	while (ib * (ib + 1) / 2 > bq) ib--;
+	const int jb = bq - ib * (ib + 1) / 2;
+	double s0 = 0, s1 = 0;
+	int k = ib;
+	for (; k + 1 < A; k += 2) {
+		const double* Wa = Wp + (size_t)(k * (k + 1) / 2 + ib) * 36, *Wb = Wp + (size_t)(k * (k + 1) / 2 + jb) * 36;
+		const double* Wa1 = Wp + (size_t)((k + 1) * (k + 2) / 2 + ib) * 36, *Wb1 = Wp + (size_t)((k + 1) * (k + 2) / 2 + jb) * 36;
+#pragma unroll
+		for (int mm = 0; mm < 6; mm++) { s0 += Wa[r * 6 + mm] * Wb[c * 6 + mm]; s1 += Wa1[r * 6 + mm] * Wb1[c * 6 + mm]; }
+	}
+	if (k < A) {
+		const double* Wa = Wp + (size_t)(k * (k + 1) / 2 + ib) * 36, *Wb = Wp + (size_t)(k * (k + 1) / 2 + jb) * 36;
+#pragma unroll
+		for (int mm = 0; mm < 6; mm++) s0 += Wa[r * 6 + mm] * Wb[c * 6 + mm];
+	}
+	const float v = (float)(s0 + s1);
+	AcInv[(size_t)(ib * 6 + r) * nc + jb * 6 + c] = v;
+	AcInv[(size_t)(jb * 6 + c) * nc + ib * 6 + r] = v;
 }
 
 }  // namespace cuba_b200

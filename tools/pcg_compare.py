@@ -11,8 +11,8 @@ for workload in sys.argv[1:] or ["kitti07_shaped", "kitti00_shaped"]:
     path = os.path.join(ROOT, "oracle", "_ref", "fixtures", workload + ".cubagraph")
     g = pkg.graphio.read_graph(path) if workload.startswith("ba_") else pkg.synth.make_config(workload)
     prob = pkg.graphio.flatten(g)
-    for variant in (3, 4):
-        eng = pkg.Engine(device=0, pcg_variant=variant)
+    for variant, magg in ((3, 0), (3, 37), (4, 0)):
+        eng = pkg.Engine(device=0, pcg_variant=variant, max_aggregates=magg)
         eng.initialize(prob)
         eng.linearize()
         md = eng.max_diagonal()
@@ -20,5 +20,5 @@ for workload in sys.argv[1:] or ["kitti07_shaped", "kitti00_shaped"]:
             eng.linearize()
             it, ok = eng.solve(lam)
             ms = eng.bench_stage(4, reps=5, flush_l2=False, lam=lam)
-            print("%s variant %d lambda %.3g: iters %d ok %s  %.3f ms/solve  %.2f us/iter" % (workload, variant, lam, it, ok, ms, 1e3 * ms / max(it, 1)), flush=True)
+            print("%s variant %d/%d lambda %.3g: iters %d ok %s  %.3f ms/solve  %.2f us/iter" % (workload, variant, magg, lam, it, ok, ms, 1e3 * ms / max(it, 1)), flush=True)
         eng.close()

@@ -15,15 +15,17 @@ binding.library_path = lambda: os.path.join(ROOT, "cuda-bundle-adjustment_b200",
 L = pkg.load_library()
 L.cuba_debug_get_pcg_timing.restype = C.c_int
 L.cuba_debug_get_pcg_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
-names = ["poll", "sync_after_poll", "scalars", "update+sync", "spmv", "reduce+sync", "publish"]
+VARIANT = int(os.environ.get("PCG_VARIANT", "0"))
+names = ["poll", "sync_after_poll", "scalars", "update+sync", "spmv", "reduce+sync", "publish"] if VARIANT != 3 else \
+    ["loads+scalars", "rc+owners+gather", "coarse slices", "u", "spmv+restrict", "reduce+publish", "grid barrier"]
 for workload in sys.argv[1:] or ["kitti00_shaped"]:
     path = os.path.join(ROOT, "oracle", "_ref", "fixtures", workload + ".cubagraph")
     g = pkg.graphio.read_graph(path) if workload.startswith("ba_") else pkg.synth.make_config(workload)
     prob = pkg.graphio.flatten(g)
-    eng = pkg.Engine(device=0)
+    eng = pkg.Engine(device=0, pcg_variant=VARIANT, max_aggregates=int(os.environ.get("MAX_AGG", "0")))
     eng.initialize(prob)
     eng.linearize()
-    lam = 1e-8 * eng.max_diagonal()
+    lam = float(os.environ.get("LAM_SCALE", "1e-8")) * eng.max_diagonal()
     it, ok = eng.solve(lam)
     ms = eng.bench_stage(4, reps=3, flush_l2=False, lam=lam)
     buf = np.zeros((256, 8), dtype=np.int64)
