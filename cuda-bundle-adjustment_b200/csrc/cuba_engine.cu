@@ -42,6 +42,28 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 static thread_local long long g_h2dBytes = 0, g_d2hBytes = 0;   // host<->device traffic of this thread's engines
 
+// Pinned staging arena for the many small host->device uploads of the PCG setup: a cudaMemcpyAsync from pageable
+// memory is staged (and effectively synchronous) inside the driver, ~20 us each; from the arena it is a plain DMA.
+struct PinnedArena {
+	char* p = nullptr; size_t cap = 0, off = 0;
+	~PinnedArena() { if (p) cudaFreeHost(p); }
+	void reset() { off = 0; }
+	// returns nullptr when the arena would have to grow while earlier copies may still read it: the caller falls back
+	void* put(const void* src, size_t bytes)
+	{
+		const size_t o = (off + 255) & ~(size_t)255;
+		if (o + bytes > cap) {
+			if (off != 0) return nullptr;
+			if (p) cudaFreeHost(p);
+			cap = std::max<size_t>(2 * (o + bytes), (size_t)1 << 20);
+			if (cudaMallocHost((void**)&p, cap) != cudaSuccess) { p = nullptr; cap = 0; return nullptr; }
+		}
+		memcpy(p + o, src, bytes);
+		off = o + bytes;
+		return p + o;
+	}
+};
+
 template <typename U>
 struct DBuf {
 	U* p = nullptr; size_t n = 0, cap = 0;
@@ -66,6 +88,11 @@ struct DBuf {
 		return cudaMemcpyAsync(p, h, sizeof(U) * count, cudaMemcpyHostToDevice, s);
 	}
 	cudaError_t upload(const std::vector<U>& h, cudaStream_t s) { return upload(h.data(), h.size(), s); }
+	cudaError_t upload(const std::vector<U>& h, cudaStream_t s, PinnedArena& arena)
+	{
+		const void* src = h.empty() ? nullptr : arena.put(h.data(), sizeof(U) * h.size());
+		return upload(src ? (const U*)src : h.data(), h.size(), s);
+	}
 	operator U*() const { return p; }
 };
 
@@ -196,6 +223,7 @@ struct Engine : EngineBase {
 	int pcg4A = 0, pcg4Gs = 1, pcg4MaxNeedAgg = 0, pcg4Cap = 0, pcg4SliceInSmem = 0, pcg4ZhInSmem = 0;
 	size_t pcg4Smem = 0, pcg4InvSmem = 0;
 	bool pcg4Ok = false, tlActive = false, pcg4Cluster = false;
+	PinnedArena arena;
 	bool coarseValid = false;       // cAcInv holds the inverse coarse matrix of an earlier solve of this problem
 	int coarseAge = 0;              // two-level solves since the coarse matrix was last rebuilt
 	bool pcg3Ok = false;
@@ -281,33 +309,36 @@ struct Engine : EngineBase {
 
 	// ---- problem upload -------------------------------------------------------------------------------
 	// ---- problem upload ----------------------------------------------------------------------------
+	// The caller's flat fp64 arrays go to the device as they are; one kernel packs them into the padded records
+	// (pose [8] = q,t,pad; cam [8]; Xw [4]) of the initial state and of both working buffers.
+	DBuf<double> rawQ, rawT, rawC, rawX;
 	int upload_state(const double* q, const double* t, const double* c, const double* X)
 	{
 		const int Pall = S.Pall, Lall = S.Lall;
-		std::vector<T> hp((size_t)Pall * 8, T(0)), hx((size_t)Lall * 4, T(0));
-		for (int i = 0; i < Pall; i++) {
-			for (int k = 0; k < 4; k++) hp[8 * (size_t)i + k] = (T)q[4 * (size_t)i + k];
-			for (int k = 0; k < 3; k++) hp[8 * (size_t)i + 4 + k] = (T)t[3 * (size_t)i + k];
+		CUDA_TRY(rawQ.upload(q, 4 * (size_t)Pall, stream)); CUDA_TRY(rawT.upload(t, 3 * (size_t)Pall, stream));
+		CUDA_TRY(rawX.upload(X, 3 * (size_t)Lall, stream));
+		if (c) CUDA_TRY(rawC.upload(c, 5 * (size_t)Pall, stream));
+		CUDA_TRY(pose0.alloc(8 * (size_t)Pall)); CUDA_TRY(Xw0.alloc(4 * (size_t)Lall));
+		for (int b = 0; b < 2; b++) { CUDA_TRY(pose[b].alloc(8 * (size_t)Pall)); CUDA_TRY(Xw[b].alloc(4 * (size_t)Lall)); }
+		if (c) CUDA_TRY(cam.alloc(8 * (size_t)Pall));
+		const int n = std::max(Pall, Lall);
+		if (n > 0) {
+			k_pack_state<T><<<(n + 255) / 256, 256, 0, stream>>>(rawQ.p, rawT.p, c ? rawC.p : nullptr, rawX.p, Pall, Lall,
+				pose0.p, pose[0].p, pose[1].p, c ? cam.p : nullptr, Xw0.p, Xw[0].p, Xw[1].p);
+			launches++;
+			CUDA_TRY(cudaGetLastError());
 		}
-		for (int i = 0; i < Lall; i++) for (int k = 0; k < 3; k++) hx[4 * (size_t)i + k] = (T)X[3 * (size_t)i + k];
-		CUDA_TRY(pose0.upload(hp, stream)); CUDA_TRY(Xw0.upload(hx, stream));
-		for (int b = 0; b < 2; b++) {
-			CUDA_TRY(pose[b].alloc(hp.size())); CUDA_TRY(Xw[b].alloc(hx.size()));
-			if (!hp.empty()) CUDA_TRY(cudaMemcpyAsync(pose[b].p, pose0.p, sizeof(T) * hp.size(), cudaMemcpyDeviceToDevice, stream));
-			if (!hx.empty()) CUDA_TRY(cudaMemcpyAsync(Xw[b].p, Xw0.p, sizeof(T) * hx.size(), cudaMemcpyDeviceToDevice, stream));
-		}
-		if (c) {
-			std::vector<T> hc((size_t)Pall * 8, T(0));
-			for (int i = 0; i < Pall; i++) for (int k = 0; k < 5; k++) hc[8 * (size_t)i + k] = (T)c[5 * (size_t)i + k];
-			CUDA_TRY(cam.upload(hc, stream));
-		}
-		// pageable host staging buffers must outlive the asynchronous copies
-		CUDA_TRY(cudaStreamSynchronize(stream));
+		// no synchronisation here: set_problem / set_state synchronise before they return to the caller
 		return CUBA_OK;
 	}
 
+	// set_problem wall-clock marks (CUBA_SETUP_TIMING=1 prints them)
+	std::vector<std::pair<const char*, std::chrono::steady_clock::time_point>> marks;
+	void tmark(const char* name) { if (markOn) marks.push_back({ name, std::chrono::steady_clock::now() }); }
+	bool markOn = false;
 	int set_problem(const cuba_problem* p) override
 	{
+		markOn = getenv("CUBA_SETUP_TIMING") != nullptr; marks.clear(); tmark("start");
 		if (!p) return fail(CUBA_ERR_INVALID, "set_problem: null problem");
 		if (p->Pall < 0 || p->Lall < 0 || p->numP < 0 || p->numL < 0 || p->numP > p->Pall || p->numL > p->Lall || p->E2 < 0 || p->E3 < 0)
 			return fail(CUBA_ERR_INVALID, "set_problem: invalid sizes");
@@ -333,9 +364,17 @@ struct Engine : EngineBase {
 		if (cfg.reserved[2] == 0 && sizeof(T) != 8) { tileSize = 128; jhMinBlocks = 6; }
 		int rc = (cfg.reserved[1] == 1) ? build_on_host(p) : build_on_gpu(p);
 		if (rc) return rc;
+		tmark("structure built");
 		rc = upload_state(p->q, p->t, p->cam, p->Xw); if (rc) return rc;
+		tmark("state uploaded");
 		rc = alloc_system(); if (rc) return rc;
 		CUDA_TRY(cudaStreamSynchronize(stream));
+		tmark("alloc_system done");
+		if (markOn) {
+			for (size_t i = 1; i < marks.size(); i++)
+				fprintf(stderr, "setup %-28s %8.3f ms\n", marks[i].first, 1e3 * std::chrono::duration<double>(marks[i].second - marks[i - 1].second).count());
+			fprintf(stderr, "setup total %8.3f ms\n", 1e3 * std::chrono::duration<double>(marks.back().second - marks.front().second).count());
+		}
 		cur = 0; trialValid = false;
 		resolveProfile();   // drop the events of earlier problems
 		for (int i = 0; i < CUBA_PROF_NUM; i++) prof[i] = 0;
@@ -455,7 +494,9 @@ struct Engine : EngineBase {
 		k_shard_meta<<<1, 32, 0, stream>>>(g_lmPtrG.p, Lall, E, rank, world, g_ff.p, g_hplG.p, g_meta.p);
 		launches++;
 		CUDA_TRY(cudaGetLastError());
+		tmark("queued to sync 1");
 		rc = fetchMeta(); if (rc) return rc;                                   // sync point 1
+		tmark("sync 1");
 		S.nhpl = hMeta->nhpl; S.lmBeg = hMeta->lmBeg; S.lmEnd = hMeta->lmEnd; S.eLocal = hMeta->kEnd - hMeta->kBeg;
 		S.hplBase = hMeta->hplBase; S.nhplLocal = hMeta->hplEnd - hMeta->hplBase;
 		const int kBeg = hMeta->kBeg, kEnd = hMeta->kEnd, eL = S.eLocal, nhpl = S.nhpl;
@@ -497,7 +538,9 @@ struct Engine : EngineBase {
 		{
 			int last = 0;
 			CUDA_TRY(cudaMemcpyAsync(&last, g_off.p + nhpl, sizeof(int), cudaMemcpyDeviceToHost, stream));
+			tmark("queued to sync 2");
 			CUDA_TRY(cudaStreamSynchronize(stream));                              // sync point 2
+			tmark("sync 2");
 			nmul = last;
 		}
 		S.nmul = nmul;
@@ -514,7 +557,9 @@ struct Engine : EngineBase {
 		rc = exclusiveSum(g_head.p, g_blkId.p, (int)N); if (rc) return rc;
 		k_nblk<<<1, 32, 0, stream>>>(g_head.p, g_blkId.p, (int)N, g_meta.p);
 		launches++;
+		tmark("queued to sync 3");
 		rc = fetchMeta(); if (rc) return rc;                                   // sync point 3
+		tmark("sync 3");
 		const int nblk = hMeta->nblk;
 		S.nblk = nblk;
 		CUDA_TRY(blkRow.alloc(nblk)); CUDA_TRY(blkCol.alloc(nblk)); CUDA_TRY(prodPtr.alloc((size_t)nblk + 1));
@@ -536,7 +581,9 @@ struct Engine : EngineBase {
 		g_d2hBytes += (long long)(sizeof(int) * ((size_t)numP + 1 + nfull));
 		CUDA_TRY(cudaMemcpyAsync(S.fRowPtr.data(), fRowPtr.p, sizeof(int) * ((size_t)numP + 1), cudaMemcpyDeviceToHost, stream));
 		if (nfull > 0) CUDA_TRY(cudaMemcpyAsync(S.fColInd.data(), fColInd.p, sizeof(int) * (size_t)nfull, cudaMemcpyDeviceToHost, stream));
+		tmark("queued to sync 4");
 		CUDA_TRY(cudaStreamSynchronize(stream));                                  // sync point 4
+		tmark("sync 4");
 		return CUBA_OK;
 	}
 
@@ -594,9 +641,13 @@ struct Engine : EngineBase {
 			KLAUNCH(schur3::k_prod_landmark, S.nmulLocal, prodI.p, hplLm.p, (int)S.nmulLocal, prodL.p);
 		}
 		if (useSchur2) { int rc = setup_schur2(); if (rc) return rc; }
+		tmark("alloc + tile info queued");
 		if (jhV4) { int rc = setup_jh4(); if (rc) return rc; }
+		tmark("jh4 queued");
 		if (S.numP > 0) { int rc = setup_pcg2(); if (rc) return rc; }        // host-heavy: overlaps the warp-tile kernels queued above
+		tmark("pcg partition (host)");
 		if (jhV4) { int rc = setup_jh4_finish(); if (rc) return rc; }
+		tmark("jh4 finish");
 		nChiLin = jhV4 ? jh4Grid : (jhV3 ? jh3Grid : ntiles);
 		nPoseBlocks = (S.numP + RED_BLOCK - 1) / RED_BLOCK;
 		nChiBlocks = std::max(1, std::min((eL + RED_BLOCK - 1) / RED_BLOCK, numSMs * 8));
@@ -621,6 +672,7 @@ struct Engine : EngineBase {
 	{
 		if (!haveProblem) return fail(CUBA_ERR_STATE, "set_state before set_problem");
 		const int rc = upload_state(q, t, nullptr, X); if (rc) return rc;
+		CUDA_TRY(cudaStreamSynchronize(stream));      // the caller's buffers are free again
 		trialValid = false;
 		return CUBA_OK;
 	}
@@ -1049,8 +1101,9 @@ struct Engine : EngineBase {
 		int perSM = 0;
 		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_pcg2<T>, PCG2_BLOCK, pcg2Smem));
 		if (perSM < 1) return fail(CUBA_ERR_CUDA, "k_pcg2 cannot be resident with the requested shared memory");
-		CUDA_TRY(ctaRow.upload(rows, stream)); CUDA_TRY(needPtr.upload(nptr, stream)); CUDA_TRY(needCol.upload(ncol, stream));
-		CUDA_TRY(fLocal.upload(local, stream));
+		arena.reset();
+		CUDA_TRY(ctaRow.upload(rows, stream, arena)); CUDA_TRY(needPtr.upload(nptr, stream, arena)); CUDA_TRY(needCol.upload(ncol, stream, arena));
+		CUDA_TRY(fLocal.upload(local, stream, arena));
 		const size_t n6 = 6 * (size_t)numP;
 		CUDA_TRY(fHat.alloc(36 * (size_t)S.nfull)); CUDA_TRY(Linv.alloc(36 * (size_t)numP));
 		CUDA_TRY(vR0.alloc(n6)); CUDA_TRY(vR1.alloc(n6)); CUDA_TRY(vS0.alloc(n6)); CUDA_TRY(vS1.alloc(n6));
@@ -1058,6 +1111,7 @@ struct Engine : EngineBase {
 		CUDA_TRY(pcg2Partial.alloc(4 * (size_t)G));
 		CUDA_TRY(gridBar.alloc(1));
 		CUDA_TRY(cudaMemsetAsync(gridBar.p, 0, sizeof(GridBar), stream));
+		tmark("  pcg2 partition + uploads");
 		// ---- two-level PCG: aggregates = groups of gs consecutive CTAs (at most PCG4_MAXAGG of them) ----
 		{
 			// up to 74 aggregates (coarse inverse in the shared memory of an 8-CTA cluster), 37 with cfg.reserved[6] == 37 (one CTA)
@@ -1112,8 +1166,8 @@ struct Engine : EngineBase {
 				if (perSM4 < 1) pcg4Ok = false;
 			}
 			if (pcg4Ok) {
-				CUDA_TRY(cAggRow.upload(aggRow, stream)); CUDA_TRY(cNaPtr.upload(naPtr, stream)); CUDA_TRY(cNaList.upload(naList, stream));
-				CUDA_TRY(cNeedAgg.upload(needAgg, stream));
+				CUDA_TRY(cAggRow.upload(aggRow, stream, arena)); CUDA_TRY(cNaPtr.upload(naPtr, stream, arena)); CUDA_TRY(cNaList.upload(naList, stream, arena));
+				CUDA_TRY(cNeedAgg.upload(needAgg, stream, arena));
 				// fine blocks of every coarse block (lower triangle), ascending -> fixed-order sums in k_coarse_assemble
 				const int nblkP = A * (A + 1) / 2;
 				std::vector<int> rowOf(S.nfull), cbPtr(nblkP + 1, 0), cbList;
@@ -1126,13 +1180,13 @@ struct Engine : EngineBase {
 					std::vector<int> fill(cbPtr.begin(), cbPtr.end() - 1);
 					for (int n = 0; n < S.nfull; n++) { const int cb = cbOf(n); if (cb >= 0) cbList[fill[cb]++] = n; }
 				}
-				CUDA_TRY(cRowOf.upload(rowOf, stream)); CUDA_TRY(cCbPtr.upload(cbPtr, stream)); CUDA_TRY(cCbList.upload(cbList, stream));
+				CUDA_TRY(cRowOf.upload(rowOf, stream, arena)); CUDA_TRY(cCbPtr.upload(cbPtr, stream, arena)); CUDA_TRY(cCbList.upload(cbList, stream, arena));
 				CUDA_TRY(cZx.alloc(36 * (size_t)numP)); CUDA_TRY(cZhat.alloc(36 * (size_t)numP)); CUDA_TRY(cU.alloc(36 * (size_t)S.nfull));
 				CUDA_TRY(cAcP.alloc((size_t)A * (A + 1) / 2 * 36)); CUDA_TRY(cAcInv.alloc((size_t)nc * nc));
 				CUDA_TRY(cLp.alloc((size_t)A * (A + 1) / 2 * 36)); CUDA_TRY(cWp.alloc((size_t)A * (A + 1) / 2 * 36)); CUDA_TRY(cLd.alloc((size_t)A * 36));
 				CUDA_TRY(cPart.alloc(2 * (size_t)G * PCG4_PSTRIDE)); CUDA_TRY(cInfo.alloc(1));
 				CUDA_TRY(cudaMemsetAsync(cPart.p, 0, sizeof(double) * cPart.n, stream));
-				CUDA_TRY(cudaStreamSynchronize(stream));      // the host vectors above die here
+				// (no synchronisation: the uploads above read the pinned arena, or were staged by the driver before returning)
 			}
 			tlActive = false; coarseValid = false; coarseAge = 0;
 		}
@@ -1191,9 +1245,9 @@ struct Engine : EngineBase {
 	}
 	bool lastPcgTwoLevel = false;
 	// policy of the default solver: block-Jacobi (k_pcg3, ~5.4 us per iteration) while it converges quickly, two-level (k_pcg4,
-	// ~9 us per iteration but 2-8x fewer of them) once a block-Jacobi solve needed more than 150 iterations -- the count grows
+	// ~9 us per iteration but 2-8x fewer of them) once a block-Jacobi solve needed more than 100 iterations -- the count grows
 	// as the LM damping falls.  The decision depends on iteration counts only, so runs stay bit-reproducible.
-	void note_pcg_iters(int iters) { if (!lastPcgTwoLevel && iters > (cfg.reserved[5] > 0 ? cfg.reserved[5] : 150)) tlActive = true; }
+	void note_pcg_iters(int iters) { if (!lastPcgTwoLevel && iters > (cfg.reserved[5] > 0 ? cfg.reserved[5] : 100)) tlActive = true; }
 
 	int launch_pcg2(bool flagged)
 	{

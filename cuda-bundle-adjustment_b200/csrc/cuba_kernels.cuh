@@ -1199,6 +1199,31 @@ __global__ void __launch_bounds__(RED_BLOCK) k_sum_partials(const double* p0, in
 }
 
 // L2 flush helper for the micro-benchmarks: overwrite a buffer larger than L2.
+// flat fp64 state of the caller -> padded records of the engine's scalar type (initial copy + both working buffers)
+template <typename T>
+__global__ void k_pack_state(const double* __restrict__ q, const double* __restrict__ t, const double* __restrict__ c, const double* __restrict__ X,
+	int Pall, int Lall, T* pose0, T* poseA, T* poseB, T* cam, T* Xw0, T* XwA, T* XwB)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < Pall) {
+		T r[8];
+		for (int k = 0; k < 4; k++) r[k] = (T)q[4 * (size_t)i + k];
+		for (int k = 0; k < 3; k++) r[4 + k] = (T)t[3 * (size_t)i + k];
+		r[7] = T(0);
+		for (int k = 0; k < 8; k++) { pose0[8 * (size_t)i + k] = r[k]; poseA[8 * (size_t)i + k] = r[k]; poseB[8 * (size_t)i + k] = r[k]; }
+		if (cam) {
+			for (int k = 0; k < 5; k++) cam[8 * (size_t)i + k] = (T)c[5 * (size_t)i + k];
+			for (int k = 5; k < 8; k++) cam[8 * (size_t)i + k] = T(0);
+		}
+	}
+	if (i < Lall) {
+		T r[4];
+		for (int k = 0; k < 3; k++) r[k] = (T)X[3 * (size_t)i + k];
+		r[3] = T(0);
+		for (int k = 0; k < 4; k++) { Xw0[4 * (size_t)i + k] = r[k]; XwA[4 * (size_t)i + k] = r[k]; XwB[4 * (size_t)i + k] = r[k]; }
+	}
+}
+
 __global__ void k_fill(double* p, size_t n, double v)
 {
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;

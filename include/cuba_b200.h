@@ -85,7 +85,7 @@ typedef struct cuba_config {
 	                          reserved[3]: Schur kernel, 0 = k_schur3 (six lanes per product, default), 1 = k_schur (lane per product),
 	                          2 = tile-local pair (cuba_schur2.cuh), 4 = k_schur4 (cooperative loads; slower)
 	                          reserved[4]: two-level PCG: solves between rebuilds of the coarse matrix (<=0: 8)
-	                          reserved[5]: automatic solver: block-Jacobi iteration count that switches to two-level (<=0: 150)
+	                          reserved[5]: automatic solver: block-Jacobi iteration count that switches to two-level (<=0: 100)
 	                          reserved[6]: two-level PCG: upper bound on the number of pose aggregates (<=0: 74; <= 37 uses the one-CTA inverse) */
 } cuba_config;
 
