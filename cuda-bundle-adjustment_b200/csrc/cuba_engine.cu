@@ -226,6 +226,7 @@ struct Engine : EngineBase {
 	PinnedArena arena;
 	bool coarseValid = false;       // cAcInv holds the inverse coarse matrix of an earlier solve of this problem
 	int coarseAge = 0;              // two-level solves since the coarse matrix was last rebuilt
+	double coarseLambda = 0, curLambda = 0;   // damping of that rebuild / of the solve being launched
 	bool pcg3Ok = false;
 	size_t pcg2Smem = 0;
 	// reductions
@@ -1203,8 +1204,11 @@ struct Engine : EngineBase {
 		// stand-in for Ac^-1 keeps M^-1 = D^-1 + Z B Z^T a valid preconditioner, and the coarse operator of an earlier
 		// damping / linearisation preconditions as well as the current one (CPU prototype: 26..201 iterations over ten LM
 		// iterations with a fresh inverse, 26..193 with one that is refreshed every fifth iteration).
+		// Measured limits of that freedom: a coarse inverse from an 81x larger damping costs nothing, one from a 1e5x larger damping
+		// costs 8x the iterations (1 276 vs 149 on kitti00_shaped) -> it is also rebuilt when the damping moved by more than 300x.
 		const int refreshEvery = cfg.reserved[4] > 0 ? cfg.reserved[4] : 8;
-		if (!coarseValid || coarseAge >= refreshEvery) {
+		const double lamRatio = (coarseValid && coarseLambda > 0 && curLambda > 0) ? std::max(curLambda / coarseLambda, coarseLambda / curLambda) : 1.0;
+		if (!coarseValid || coarseAge >= refreshEvery || lamRatio > 300.0) {
 			KLAUNCH(k_coarse_project<T>, 36LL * S.nfull, fVal.p, cRowOf.p, fColInd.p, S.nfull, cZx.p, cU.p);
 			KLAUNCH(k_coarse_assemble, (long long)nblkP * 36, cCbPtr.p, cCbList.p, cU.p, nblkP, cAcP.p);
 			if (pcg4Cluster) {
@@ -1217,7 +1221,7 @@ struct Engine : EngineBase {
 			else k_coarse_invert<T><<<1, 1024, pcg4InvSmem, stream>>>(cAcP.p, A, cAcInv.p, cInfo.p);
 			launches++;
 			CUDA_TRY(cudaGetLastError());
-			coarseValid = true; coarseAge = 0;
+			coarseValid = true; coarseAge = 0; coarseLambda = curLambda;
 		}
 		coarseAge++;
 		Pcg4Args<T> b;
@@ -1325,6 +1329,7 @@ struct Engine : EngineBase {
 	{
 		if (!haveProblem) return fail(CUBA_ERR_STATE, "solve before set_problem");
 		const T lam = (T)lambda;
+		curLambda = lambda;
 		int rc = launch_schur(lam); if (rc) return rc;
 		int nScaleL = 0;
 		if (S.numP > 0 && S.numL > 0) {
@@ -1588,7 +1593,7 @@ struct Engine : EngineBase {
 			case 1: rc = launch_linearize_landmark(); break;
 			case 2: rc = launch_linearize_pose(); break;
 			case 3: rc = launch_schur(lam); break;
-			case 4: rc = launch_pcg(); break;
+			case 4: curLambda = lambda; rc = launch_pcg(); break;
 			case 5: rc = launch_backsub(lam); if (!rc) rc = stage_update_nofetch(lam); break;
 			case 6: rc = launch_chi2(cur, 0); break;
 			default: rc = fail(CUBA_ERR_INVALID, "bench_stage: unknown stage");

@@ -676,12 +676,12 @@ k_coarse_chol_cluster(const double* __restrict__ AcP, int A, double* Lp, double*
 	for (int ib = tid; ib < A; ib += NT) for (int jb = 0; jb <= ib; jb++) { s_ib[ib * (ib + 1) / 2 + jb] = (unsigned char)ib; s_jb[ib * (ib + 1) / 2 + jb] = (unsigned char)jb; }
 	if (tid == 0) s_fail = 0;
 	cluster.sync();
-	// ---- phase 1: block Cholesky ----
+	// ---- phase 1: block Cholesky.  Every CTA factors the (already final) diagonal block itself -- two cluster barriers per
+	//      block column instead of three, and the panel reads its own copy of L_kk^-1 ----
 	for (int kb = 0; kb < A; kb++) {
-		if (rank == 0 && tid < 32) {
-			// copy the diagonal block here, factor it in place (lane r owns row r), write L back and L^-1 to sLi (this CTA's copy)
+		if (tid < 32) {
 			double* D = sScr;
-			double* Dg = blk(kb, kb);
+			const double* Dg = blk(kb, kb);                     // raw diagonal block: nobody writes it any more
 			for (int e = tid; e < 36; e += 32) D[e] = Dg[e];
 			__syncwarp();
 			const int r = tid;
@@ -717,12 +717,14 @@ k_coarse_chol_cluster(const double* __restrict__ AcP, int A, double* Lp, double*
 				for (int i = 0; i < 6; i++) sLiL[(size_t)kb * 36 + q * 6 + i] = col[i];
 			}
 			__syncwarp();
-			for (int e = tid; e < 36; e += 32) Dg[e] = D[e];
+			// the factor of the diagonal block goes straight to the output (its shared-memory copy stays raw)
+			if (rank == (((kb * (kb + 1)) / 2 + kb) & (PCG4_CL - 1))) for (int e = tid; e < 36; e += 32) Lp[((size_t)kb * (kb + 1) / 2 + kb) * 36 + e] = D[e];
 		}
-		cluster.sync();
-		if (*fail0) break;
-		// panel + trailing update of the blocks this CTA owns
-		const double* Li = sLi0 + (size_t)kb * 36;
+		__syncthreads();
+		if (s_fail) { *fail0 = 1; }                                // every CTA computes the same verdict; rank 0's flag is the shared one
+		// panel of the blocks this CTA owns
+		const double* Li = sLiL + (size_t)kb * 36;
+		if (!s_fail)
 		for (int w = tid; w < nloc * 6; w += NT) {            // panel: one thread per (own block, row)
 			const int lb = w / 6, r = w - 6 * lb, b = lb * PCG4_CL + rank;
 			if (b >= nblkP) continue;
@@ -735,6 +737,7 @@ k_coarse_chol_cluster(const double* __restrict__ AcP, int A, double* Lp, double*
 			for (int c = 0; c < 6; c++) X[c * 6 + r] = y[c];
 		}
 		cluster.sync();
+		if (*fail0) break;
 		for (int w = tid; w < nloc * 36; w += NT) {           // trailing: one thread per (own block, entry)
 			const int lb = w / 36, rc = w - 36 * lb, c = rc / 6, r = rc - 6 * c, b = lb * PCG4_CL + rank;
 			if (b >= nblkP) continue;
@@ -757,7 +760,7 @@ k_coarse_chol_cluster(const double* __restrict__ AcP, int A, double* Lp, double*
 	// ---- the factor L (packed, block b at Lp + 36 b) and the inverses of its diagonal blocks leave for k_coarse_trinv ----
 	for (int e = tid; e < nloc * 36; e += NT) {
 		const int b = (e / 36) * PCG4_CL + rank;
-		if (b < nblkP) Lp[(size_t)b * 36 + (e % 36)] = Bl[e];
+		if (b < nblkP && s_ib[b] != s_jb[b]) Lp[(size_t)b * 36 + (e % 36)] = Bl[e];     // diagonal factors were written in phase 1
 	}
 	if (rank == 0) for (int e = tid; e < A * 36; e += NT) Ld[e] = sLiL[e];
 	if (rank == 0 && tid == 0 && info) *info = 0;

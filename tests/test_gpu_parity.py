@@ -340,4 +340,9 @@ def test_two_level_pcg_converges_faster_to_the_same_solution(pkg, problems, name
     for nme, x, y in zip(("xp", "xl"), a.delta(), b.delta()):
         assert relerr(x, y) < 1e-7, (nme, ia, ib, relerr(x, y))
     assert ia * 1.5 < ib, (ia, ib)
+    # the cached coarse inverse is rebuilt when the damping has moved far (here 1e5x): the two-level solve must stay well ahead
+    md = a.max_diagonal()
+    assert a.solve(1e-5 * md)[1]
+    ia2, ok2 = a.solve(1e-10 * md); ib2, okb2 = b.solve(1e-10 * md)
+    assert ok2 and okb2 and ia2 * 3 < ib2, (ia2, ib2)
     a.close(); b.close()
