@@ -253,7 +253,7 @@ def main():
             traffic = json.load(open(tpath)).get(args.workload)
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_linearize_landmark4", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+    roofline = {"bound": "hbm", "kernel": ("k_linearize_landmark<float>" if args.fp32 else "k_linearize_landmark4"), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": b_kernel, "ms_per_launch": stage_ms["jh_landmark_pass"],
                 "stage_frac_jh_both_kernels": b_stage / ((stage_ms["jh_landmark_pass"] + stage_ms["jh_pose_pass"]) * 1e-3) / 1e9 / peak}
 
