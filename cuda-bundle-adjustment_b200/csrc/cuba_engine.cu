@@ -1768,6 +1768,27 @@ int cuba_debug_build_structure_host(const cuba_problem* p, int rank, int world, 
 	return CUBA_OK;
 }
 
+/* host side of the PCG setup on the CPU (no device needed): structure -> row partition over nCtas CTAs -> aggregates and coarse
+ * lists with at most maxAgg aggregates; runs the invariants of check_pcg_partition.  info[8] = G, gs, A, needMax, maxRows,
+ * blkMax, maxNeedAgg, size of the coarse lists. */
+int cuba_debug_pcg_partition(const cuba_problem* p, int nCtas, int maxAgg, int32_t* info)
+{
+	if (!p || nCtas < 1 || maxAgg < 1) return fail(CUBA_ERR_INVALID, "pcg_partition: bad arguments");
+	Structure S;
+	const char* err = "";
+	if (!build_structure(p->Pall, p->numP, p->Lall, p->numL, p->E2, p->idx2, p->E3, p->idx3, 0, 1, TILE, S, &err)) return fail(CUBA_ERR_INVALID, err);
+	if (S.numP < 1) return fail(CUBA_ERR_INVALID, "pcg_partition: no free pose");
+	const int G = std::max(1, std::min(nCtas, S.numP));
+	PcgPartition P; CoarsePartition C;
+	build_pcg_partition(S.numP, S.nfull, S.fRowPtr, S.fColInd, G, P);
+	build_coarse_partition(S.numP, P, maxAgg, C);
+	build_coarse_lists(S.numP, S.nfull, S.fRowPtr, S.fColInd, C);
+	const char* bad = check_pcg_partition(S.numP, S.nfull, S.fRowPtr, S.fColInd, P, C);
+	if (bad) return fail(CUBA_ERR_INVALID, std::string("pcg_partition self-check: ") + bad);
+	if (info) { info[0] = P.G; info[1] = C.gs; info[2] = C.A; info[3] = P.needMax; info[4] = P.maxRows; info[5] = P.blkMax; info[6] = C.maxNeedAgg; info[7] = (int32_t)C.cbList.size(); }
+	return CUBA_OK;
+}
+
 int cuba_bench_stage(cuba_engine* e, int stage, int reps, int flush, double lambda, double* ms) { ENGINE_OR_FAIL(e); return e->impl->bench_stage(stage, reps, flush, lambda, ms); }
 
 }  // extern "C"

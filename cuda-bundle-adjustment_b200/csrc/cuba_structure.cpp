@@ -202,4 +202,154 @@ bool build_structure(int Pall, int numP, int Lall, int numL, int E2, const int32
 	return true;
 }
 
+// ---- host side of the PCG setup ---------------------------------------------------------------------------------
+void build_pcg_partition(int numP, int nfull, const std::vector<int>& fRowPtr, const std::vector<int>& fColInd, int G, PcgPartition& P)
+{
+	P = PcgPartition();
+	P.G = G;
+	// contiguous row ranges balanced by block count
+	std::vector<int>& rows = P.rows;
+	rows.assign(G + 1, 0);
+	{
+		int r = 0;
+		for (int c = 0; c < G; c++) {
+			rows[c] = r;
+			const long long target = (long long)nfull * (c + 1) / G;
+			const int minRows = 1, remainingCtas = G - c - 1;
+			int end = r + minRows;
+			while (end < numP - remainingCtas && fRowPtr[end] < target) end++;
+			r = std::min(end, numP - remainingCtas);
+		}
+		rows[G] = numP;
+	}
+	P.nptr.assign(G + 1, 0);
+	P.local.assign(nfull, 0);
+	std::vector<int> mark(numP, -1);
+	for (int c = 0; c < G; c++) {
+		std::vector<int> cols;
+		for (int n = fRowPtr[rows[c]]; n < fRowPtr[rows[c + 1]]; n++) {
+			const int j = fColInd[n];
+			if (mark[j] != c) { mark[j] = c; cols.push_back(j); }
+		}
+		std::sort(cols.begin(), cols.end());
+		P.nptr[c] = (int)P.ncol.size();
+		for (size_t k = 0; k < cols.size(); k++) P.ncol.push_back(cols[k]);
+		// local index of each block's column: binary search in the sorted list
+		for (int n = fRowPtr[rows[c]]; n < fRowPtr[rows[c + 1]]; n++)
+			P.local[n] = (int)(std::lower_bound(cols.begin(), cols.end(), fColInd[n]) - cols.begin());
+		// the diagonal block of each own row is encoded as -1-loc (A^_ii = I is applied implicitly)
+		for (int r = rows[c]; r < rows[c + 1]; r++)
+			for (int n = fRowPtr[r]; n < fRowPtr[r + 1]; n++) if (fColInd[n] == r) P.local[n] = -1 - P.local[n];
+		P.maxRows = std::max(P.maxRows, rows[c + 1] - rows[c]);
+		P.needMax = std::max(P.needMax, (int)cols.size());
+		P.blkMax = std::max(P.blkMax, fRowPtr[rows[c + 1]] - fRowPtr[rows[c]]);
+	}
+	P.nptr[G] = (int)P.ncol.size();
+}
+
+void build_coarse_partition(int numP, const PcgPartition& P, int maxAgg, CoarsePartition& C)
+{
+	C = CoarsePartition();
+	const int G = P.G;
+	const int gs = (G + maxAgg - 1) / maxAgg, A = (G + gs - 1) / gs;
+	C.gs = gs; C.A = A;
+	C.aggRow.assign(A + 1, numP);
+	for (int ag = 0; ag < A; ag++) C.aggRow[ag] = P.rows[std::min(ag * gs, G)];
+	C.rowAgg.assign(numP, 0);
+	for (int ag = 0; ag < A; ag++) for (int r = C.aggRow[ag]; r < C.aggRow[ag + 1]; r++) C.rowAgg[r] = ag;
+	C.naPtr.assign(G + 1, 0);
+	C.needAgg.assign(P.ncol.size(), 0);
+	int maxNA = 0;
+	for (int c = 0; c < G; c++) {
+		std::vector<int> ags;
+		for (int k = P.nptr[c]; k < P.nptr[c + 1]; k++) ags.push_back(C.rowAgg[P.ncol[k]]);
+		std::sort(ags.begin(), ags.end());
+		ags.erase(std::unique(ags.begin(), ags.end()), ags.end());
+		C.naPtr[c] = (int)C.naList.size();
+		for (int k = P.nptr[c]; k < P.nptr[c + 1]; k++)
+			C.needAgg[k] = (int)(std::lower_bound(ags.begin(), ags.end(), C.rowAgg[P.ncol[k]]) - ags.begin());
+		C.naList.insert(C.naList.end(), ags.begin(), ags.end());
+		maxNA = std::max(maxNA, (int)ags.size());
+	}
+	C.naPtr[G] = (int)C.naList.size();
+	C.maxNeedAgg = std::max(maxNA, 1);
+}
+
+void build_coarse_lists(int numP, int nfull, const std::vector<int>& fRowPtr, const std::vector<int>& fColInd, CoarsePartition& C)
+{
+	// fine blocks of every coarse block (lower triangle), ascending -> fixed-order sums in k_coarse_assemble
+	const int A = C.A, nblkP = A * (A + 1) / 2;
+	C.rowOf.assign(nfull, 0);
+	C.cbPtr.assign(nblkP + 1, 0);
+	for (int i = 0; i < numP; i++) for (int n = fRowPtr[i]; n < fRowPtr[i + 1]; n++) C.rowOf[n] = i;
+	auto cbOf = [&](int n) { const int ai = C.rowAgg[C.rowOf[n]], aj = C.rowAgg[fColInd[n]]; return ai >= aj ? ai * (ai + 1) / 2 + aj : -1; };
+	for (int n = 0; n < nfull; n++) { const int cb = cbOf(n); if (cb >= 0) C.cbPtr[cb + 1]++; }
+	for (int cb = 0; cb < nblkP; cb++) C.cbPtr[cb + 1] += C.cbPtr[cb];
+	C.cbList.resize(C.cbPtr[nblkP]);
+	std::vector<int> fill(C.cbPtr.begin(), C.cbPtr.end() - 1);
+	for (int n = 0; n < nfull; n++) { const int cb = cbOf(n); if (cb >= 0) C.cbList[fill[cb]++] = n; }
+}
+
+const char* check_pcg_partition(int numP, int nfull, const std::vector<int>& fRowPtr, const std::vector<int>& fColInd,
+	const PcgPartition& P, const CoarsePartition& C)
+{
+	const int G = P.G;
+	if (G < 1 || (int)P.rows.size() != G + 1 || P.rows[0] != 0 || P.rows[G] != numP) return "rows do not cover [0, numP)";
+	for (int c = 0; c < G; c++) if (P.rows[c + 1] <= P.rows[c]) return "a CTA without rows";
+	for (int c = 0; c < G; c++) {
+		const int* nc = P.ncol.data() + P.nptr[c];
+		const int nn = P.nptr[c + 1] - P.nptr[c];
+		for (int k = 1; k < nn; k++) if (nc[k] <= nc[k - 1]) return "need list not strictly ascending";
+		for (int r = P.rows[c]; r < P.rows[c + 1]; r++) {
+			if (!std::binary_search(nc, nc + nn, r)) return "own row missing from the need list";
+			bool diag = false;
+			for (int n = fRowPtr[r]; n < fRowPtr[r + 1]; n++) {
+				const int loc = P.local[n], j = fColInd[n];
+				const int pos = loc < 0 ? -1 - loc : loc;
+				if (pos < 0 || pos >= nn || nc[pos] != j) return "local index does not point at the block's column";
+				if ((loc < 0) != (j == r)) return "diagonal encoding wrong";
+				diag |= j == r;
+			}
+			if (!diag) return "row without a diagonal block";
+		}
+		if (nn > P.needMax || P.rows[c + 1] - P.rows[c] > P.maxRows || fRowPtr[P.rows[c + 1]] - fRowPtr[P.rows[c]] > P.blkMax) return "maxima too small";
+	}
+	// coarse level
+	const int A = C.A;
+	if (A < 1 || (int)C.aggRow.size() != A + 1 || C.aggRow[0] != 0 || C.aggRow[A] != numP) return "aggregates do not cover [0, numP)";
+	for (int a = 0; a < A; a++) {
+		if (C.aggRow[a + 1] <= C.aggRow[a]) return "empty aggregate";
+		if (C.aggRow[a] != P.rows[std::min(a * C.gs, G)]) return "aggregate not aligned with a CTA boundary";
+		for (int r = C.aggRow[a]; r < C.aggRow[a + 1]; r++) if (C.rowAgg[r] != a) return "rowAgg inconsistent";
+	}
+	for (int c = 0; c < G; c++) {
+		const int* al = C.naList.data() + C.naPtr[c];
+		const int na = C.naPtr[c + 1] - C.naPtr[c];
+		if (na < 1 || na > C.maxNeedAgg) return "aggregate list size";
+		for (int k = 1; k < na; k++) if (al[k] <= al[k - 1]) return "aggregate list not ascending";
+		for (int k = P.nptr[c]; k < P.nptr[c + 1]; k++) {
+			const int pos = C.needAgg[k];
+			if (pos < 0 || pos >= na || al[pos] != C.rowAgg[P.ncol[k]]) return "needAgg does not point at the column's aggregate";
+		}
+		if (C.rowAgg[P.rows[c]] != c / C.gs) return "a CTA's rows are not in aggregate cta / gs";
+	}
+	if (!C.cbPtr.empty()) {
+		const int nblkP = A * (A + 1) / 2;
+		if ((int)C.cbPtr.size() != nblkP + 1) return "cbPtr size";
+		long long lower = 0;
+		for (int n = 0; n < nfull; n++) if (C.rowAgg[C.rowOf[n]] >= C.rowAgg[fColInd[n]]) lower++;
+		if ((long long)C.cbList.size() != lower || C.cbPtr[nblkP] != (int)lower) return "coarse lists do not hold every lower block exactly once";
+		for (int ib = 0; ib < A; ib++)
+			for (int jb = 0; jb <= ib; jb++) {
+				const int cb = ib * (ib + 1) / 2 + jb;
+				for (int k = C.cbPtr[cb]; k < C.cbPtr[cb + 1]; k++) {
+					const int n = C.cbList[k];
+					if (n < 0 || n >= nfull || C.rowAgg[C.rowOf[n]] != ib || C.rowAgg[fColInd[n]] != jb) return "block in the wrong coarse list";
+					if (k > C.cbPtr[cb] && C.cbList[k - 1] >= n) return "coarse list not ascending";
+				}
+			}
+	}
+	return nullptr;
+}
+
 }  // namespace cuba_b200

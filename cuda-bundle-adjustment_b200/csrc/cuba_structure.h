@@ -66,4 +66,38 @@ struct Structure {
 bool build_structure(int Pall, int numP, int Lall, int numL, int E2, const int32_t* idx2, int E3, const int32_t* idx3,
 	int rank, int world, int tileEdges, Structure& S, const char** err);
 
+// ---- host side of the PCG setup (pure C++, tested on the CPU through cuba_debug_pcg_partition) --------------------
+// (Engine::setup_pcg2 in cuba_engine.cu carries the same code inline; switching it over to these functions is a pure refactoring
+//  that waits for a GPU run to re-validate it.)
+// Row partition of the reduced pose system over G persistent CTAs: contiguous row ranges balanced by block count, the sorted
+// list of block columns every CTA needs, and the position of each block's column in that list (diagonal blocks: -1-pos).
+struct PcgPartition {
+	int G = 0;
+	std::vector<int> rows;     // [G+1]
+	std::vector<int> nptr;     // [G+1] offsets into ncol
+	std::vector<int> ncol;     // needed columns per CTA, ascending
+	std::vector<int> local;    // [nfull]
+	int needMax = 0, blkMax = 0, maxRows = 0;
+};
+void build_pcg_partition(int numP, int nfull, const std::vector<int>& fRowPtr, const std::vector<int>& fColInd, int G, PcgPartition& P);
+
+// Coarse level of the two-level PCG: aggregates = groups of gs consecutive CTAs (at most maxAgg of them), the aggregates every
+// CTA needs, and -- build_coarse_lists -- the fine blocks of every coarse block of the lower triangle in ascending order.
+struct CoarsePartition {
+	int gs = 1, A = 0, maxNeedAgg = 1;
+	std::vector<int> aggRow;   // [A+1] first row of every aggregate
+	std::vector<int> rowAgg;   // [numP]
+	std::vector<int> naPtr;    // [G+1]
+	std::vector<int> naList;   // aggregates per CTA, ascending
+	std::vector<int> needAgg;  // per need entry: position of its aggregate in the CTA's list
+	std::vector<int> rowOf;    // [nfull] row of every block
+	std::vector<int> cbPtr;    // [A(A+1)/2 + 1]
+	std::vector<int> cbList;   // fine blocks of coarse block (ib >= jb) at index ib (ib+1)/2 + jb
+};
+void build_coarse_partition(int numP, const PcgPartition& P, int maxAgg, CoarsePartition& C);
+void build_coarse_lists(int numP, int nfull, const std::vector<int>& fRowPtr, const std::vector<int>& fColInd, CoarsePartition& C);
+// invariants of both (nullptr when everything holds)
+const char* check_pcg_partition(int numP, int nfull, const std::vector<int>& fRowPtr, const std::vector<int>& fColInd,
+	const PcgPartition& P, const CoarsePartition& C);
+
 }  // namespace cuba_b200

@@ -205,6 +205,11 @@ int cuba_debug_build_structure_host(const cuba_problem* p, int rank, int world, 
 	int32_t* fullRowPtr /*numP+1*/, int32_t* fullColInd /*nblk_full*/,
 	int32_t* shard /*[4]: lmBeg, lmEnd, edges, local products*/);
 
+/* CPU-only check of the host side of the PCG setup (row partition over nCtas persistent CTAs, need lists, pose aggregates and
+ * coarse lists of the two-level PCG, csrc/cuba_structure.cpp): builds them for the problem and verifies their invariants.
+ * info[8] = G, gs, A, needMax, maxRows, blkMax, maxNeedAgg, size of the coarse lists.  No device needed. */
+int cuba_debug_pcg_partition(const cuba_problem* p, int nCtas, int maxAgg, int32_t* info);
+
 /* ---- micro-benchmark hooks for bench.py / profiles (device-resident data, CUDA-event timed) ---- */
 /* Runs the named stage `reps` times back to back and returns the average device milliseconds per
  * repetition.  stage: 0 linearize (landmark pass + pose pass), 1 landmark pass only, 2 pose pass only,

@@ -98,3 +98,26 @@ def test_structure_shards_partition_the_graph(pkg, problems, world):
     # balanced by edge count to within one landmark's degree
     per = [pkg.build_structure_host(prob, r, world)["shard"][2] for r in range(world)]
     assert max(per) - min(per) <= 2 * 64
+
+
+@pytest.mark.parametrize("name,n_ctas,max_agg", [("tiny", 148, 74), ("small", 148, 74), ("small", 7, 3), ("kitti07_shaped", 148, 74),
+                                                  ("kitti07_shaped", 31, 37), ("kitti07_shaped", 148, 37)])
+def test_pcg_partition_host_logic(pkg, problems, name, n_ctas, max_agg):
+    """host side of the PCG setup (csrc/cuba_structure.cpp, shared with the engine): row partition over the persistent CTAs, need
+    lists, block-local column positions, pose aggregates of the two-level PCG and the coarse-block lists -- the library builds them
+    and verifies every invariant (rows cover [0,P), own rows in the need list, diagonal encoding, aggregates aligned with CTA
+    groups, every lower-triangle block in exactly one ascending coarse list)"""
+    prob = problems(name)
+    info = pkg.pcg_partition_host(prob, n_ctas, max_agg)
+    assert info["G"] == min(n_ctas, prob.numP)
+    assert 1 <= info["A"] <= max_agg and info["A"] == -(-info["G"] // info["gs"])
+    assert info["maxRows"] >= -(-prob.numP // info["G"]) and info["needMax"] >= info["maxRows"]
+    assert 1 <= info["maxNeedAgg"] <= info["A"]
+    s = pkg.build_structure_host(prob)
+    # lower block triangle of the coarse matrix: at least the diagonal blocks of the fine matrix, at most all of them
+    assert prob.numP <= info["coarse_list_size"] <= s["nblk_full"]
+
+
+def test_pcg_partition_rejects_bad_arguments(pkg, problems):
+    with pytest.raises(pkg.CubaError):
+        pkg.pcg_partition_host(problems("tiny"), 0, 74)
