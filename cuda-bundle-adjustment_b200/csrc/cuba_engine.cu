@@ -1051,43 +1051,11 @@ struct Engine : EngineBase {
 		const size_t matBytes = (size_t)S.nfull * (36 * sizeof(T) + 4);
 		int G = std::max((numP + 7) / 8, (int)((matBytes + budget - 1) / std::max<size_t>(budget, 1)));
 		G = std::max(1, std::min(G, std::min(numSMs, numP)));
-		// contiguous row ranges balanced by block count
-		std::vector<int> rows(G + 1, 0);
-		{
-			int r = 0;
-			for (int c = 0; c < G; c++) {
-				rows[c] = r;
-				const long long target = (long long)S.nfull * (c + 1) / G;
-				const int minRows = 1, remainingCtas = G - c - 1;
-				int end = r + minRows;
-				while (end < numP - remainingCtas && S.fRowPtr[end] < target) end++;
-				r = std::min(end, numP - remainingCtas);
-			}
-			rows[G] = numP;
-		}
-		std::vector<int> nptr(G + 1, 0), ncol, local(S.nfull, 0);
-		int needMax = 0, blkMax = 0, maxRows = 0;
-		std::vector<int> mark(numP, -1);
-		for (int c = 0; c < G; c++) {
-			std::vector<int> cols;
-			for (int n = S.fRowPtr[rows[c]]; n < S.fRowPtr[rows[c + 1]]; n++) {
-				const int j = S.fColInd[n];
-				if (mark[j] != c) { mark[j] = c; cols.push_back(j); }
-			}
-			std::sort(cols.begin(), cols.end());
-			nptr[c] = (int)ncol.size();
-			for (size_t k = 0; k < cols.size(); k++) ncol.push_back(cols[k]);
-			// local index of each block's column: binary search in the sorted list
-			for (int n = S.fRowPtr[rows[c]]; n < S.fRowPtr[rows[c + 1]]; n++)
-				local[n] = (int)(std::lower_bound(cols.begin(), cols.end(), S.fColInd[n]) - cols.begin());
-			// the diagonal block of each own row is encoded as -1-loc (A^_ii = I is applied implicitly)
-			for (int r = rows[c]; r < rows[c + 1]; r++)
-				for (int n = S.fRowPtr[r]; n < S.fRowPtr[r + 1]; n++) if (S.fColInd[n] == r) local[n] = -1 - local[n];
-			maxRows = std::max(maxRows, rows[c + 1] - rows[c]);
-			needMax = std::max(needMax, (int)cols.size());
-			blkMax = std::max(blkMax, S.fRowPtr[rows[c + 1]] - S.fRowPtr[rows[c]]);
-		}
-		nptr[G] = (int)ncol.size();
+		// row partition, need lists, block-local column positions: cuba_structure.cpp (CPU-tested)
+		PcgPartition PP;
+		build_pcg_partition(numP, S.nfull, S.fRowPtr, S.fColInd, G, PP);
+		const std::vector<int>& rows = PP.rows; const std::vector<int>& nptr = PP.nptr; const std::vector<int>& ncol = PP.ncol; const std::vector<int>& local = PP.local;
+		const int needMax = PP.needMax, blkMax = PP.blkMax, maxRows = PP.maxRows;
 		// fixed shared-memory footprint of k_pcg3 (a superset of k_pcg2's): r,s per needed column, p,y per own row, index lists
 		const size_t needBytes = (size_t)needMax * (12 * sizeof(T) + 8) + (size_t)maxRows * (12 * sizeof(T) + 4) + ((size_t)maxRows + 1) * 4
 			+ (size_t)PCG3_CHUNK * 6 * sizeof(T);
@@ -1117,27 +1085,11 @@ struct Engine : EngineBase {
 		{
 			// up to 74 aggregates (coarse inverse in the shared memory of an 8-CTA cluster), 37 with cfg.reserved[6] == 37 (one CTA)
 			const int maxAgg = (cfg.reserved[6] > 0 && cfg.reserved[6] < PCG4_MAXAGG) ? cfg.reserved[6] : PCG4_MAXAGG;
-			const int gs = (G + maxAgg - 1) / maxAgg, A = (G + gs - 1) / gs, nc = 6 * A;
+			CoarsePartition CP;
+			build_coarse_partition(numP, PP, maxAgg, CP);
+			const int gs = CP.gs, A = CP.A, nc = 6 * A;
 			pcg4Cluster = A > PCG4_MAXAGG1;
-			std::vector<int> aggRow(A + 1, numP);
-			for (int ag = 0; ag < A; ag++) aggRow[ag] = rows[std::min(ag * gs, G)];
-			std::vector<int> rowAgg(numP, 0);
-			for (int ag = 0; ag < A; ag++) for (int r = aggRow[ag]; r < aggRow[ag + 1]; r++) rowAgg[r] = ag;
-			std::vector<int> naPtr(G + 1, 0), naList, needAgg(ncol.size(), 0);
-			int maxNA = 0;
-			for (int c = 0; c < G; c++) {
-				std::vector<int> ags;
-				for (int k = nptr[c]; k < nptr[c + 1]; k++) ags.push_back(rowAgg[ncol[k]]);
-				std::sort(ags.begin(), ags.end());
-				ags.erase(std::unique(ags.begin(), ags.end()), ags.end());
-				naPtr[c] = (int)naList.size();
-				for (int k = nptr[c]; k < nptr[c + 1]; k++)
-					needAgg[k] = (int)(std::lower_bound(ags.begin(), ags.end(), rowAgg[ncol[k]]) - ags.begin());
-				naList.insert(naList.end(), ags.begin(), ags.end());
-				maxNA = std::max(maxNA, (int)ags.size());
-			}
-			naPtr[G] = (int)naList.size();
-			pcg4A = A; pcg4Gs = gs; pcg4MaxNeedAgg = std::max(maxNA, 1);
+			pcg4A = A; pcg4Gs = gs; pcg4MaxNeedAgg = CP.maxNeedAgg;
 			size_t fixed4 = (size_t)needMax * (12 * sizeof(T) + 8) + (size_t)maxRows * (6 * sizeof(T) + 8) + 8 + 2 * (size_t)nc * sizeof(T)
 				+ (size_t)pcg4MaxNeedAgg * (6 * sizeof(T) + 4) + 64;
 			// shared-memory priorities: all of A^ first, then Z^ of the needed columns, then the CTA's slices of the inverse coarse matrix
@@ -1167,21 +1119,11 @@ struct Engine : EngineBase {
 				if (perSM4 < 1) pcg4Ok = false;
 			}
 			if (pcg4Ok) {
-				CUDA_TRY(cAggRow.upload(aggRow, stream, arena)); CUDA_TRY(cNaPtr.upload(naPtr, stream, arena)); CUDA_TRY(cNaList.upload(naList, stream, arena));
-				CUDA_TRY(cNeedAgg.upload(needAgg, stream, arena));
+				CUDA_TRY(cAggRow.upload(CP.aggRow, stream, arena)); CUDA_TRY(cNaPtr.upload(CP.naPtr, stream, arena)); CUDA_TRY(cNaList.upload(CP.naList, stream, arena));
+				CUDA_TRY(cNeedAgg.upload(CP.needAgg, stream, arena));
 				// fine blocks of every coarse block (lower triangle), ascending -> fixed-order sums in k_coarse_assemble
-				const int nblkP = A * (A + 1) / 2;
-				std::vector<int> rowOf(S.nfull), cbPtr(nblkP + 1, 0), cbList;
-				for (int i = 0; i < numP; i++) for (int n = S.fRowPtr[i]; n < S.fRowPtr[i + 1]; n++) rowOf[n] = i;
-				auto cbOf = [&](int n) { const int ai = rowAgg[rowOf[n]], aj = rowAgg[S.fColInd[n]]; return ai >= aj ? ai * (ai + 1) / 2 + aj : -1; };
-				for (int n = 0; n < S.nfull; n++) { const int cb = cbOf(n); if (cb >= 0) cbPtr[cb + 1]++; }
-				for (int cb = 0; cb < nblkP; cb++) cbPtr[cb + 1] += cbPtr[cb];
-				cbList.resize(cbPtr[nblkP]);
-				{
-					std::vector<int> fill(cbPtr.begin(), cbPtr.end() - 1);
-					for (int n = 0; n < S.nfull; n++) { const int cb = cbOf(n); if (cb >= 0) cbList[fill[cb]++] = n; }
-				}
-				CUDA_TRY(cRowOf.upload(rowOf, stream, arena)); CUDA_TRY(cCbPtr.upload(cbPtr, stream, arena)); CUDA_TRY(cCbList.upload(cbList, stream, arena));
+				build_coarse_lists(numP, S.nfull, S.fRowPtr, S.fColInd, CP);
+				CUDA_TRY(cRowOf.upload(CP.rowOf, stream, arena)); CUDA_TRY(cCbPtr.upload(CP.cbPtr, stream, arena)); CUDA_TRY(cCbList.upload(CP.cbList, stream, arena));
 				CUDA_TRY(cZx.alloc(36 * (size_t)numP)); CUDA_TRY(cZhat.alloc(36 * (size_t)numP)); CUDA_TRY(cU.alloc(36 * (size_t)S.nfull));
 				CUDA_TRY(cAcP.alloc((size_t)A * (A + 1) / 2 * 36)); CUDA_TRY(cAcInv.alloc((size_t)nc * nc));
 				CUDA_TRY(cLp.alloc((size_t)A * (A + 1) / 2 * 36)); CUDA_TRY(cWp.alloc((size_t)A * (A + 1) / 2 * 36)); CUDA_TRY(cLd.alloc((size_t)A * 36));
