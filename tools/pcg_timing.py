@@ -1,4 +1,7 @@
-"""Per-phase clock64 breakdown of k_pcg3 (needs cuda-bundle-adjustment_b200/libcuba_b200_timing.so built with -DCUBA_PCG_TIMING)."""
+"""Per-phase clock64 breakdown of k_pcg3 (default) or k_pcg4 (PCG_VARIANT=3; MAX_AGG, LAM_SCALE optional).
+Needs cuda-bundle-adjustment_b200/libcuba_b200_timing.so, the library built with -DCUBA_PCG_TIMING:
+  cd cuda-bundle-adjustment_b200 && nvcc -DCUBA_PCG_TIMING -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo \
+      -Xcompiler -fPIC -shared -I ../include -o libcuba_b200_timing.so csrc/cuba_engine.cu csrc/cuba_structure.cpp csrc/cuba_api.cpp -ldl"""
 import ctypes as C
 import os
 import sys
