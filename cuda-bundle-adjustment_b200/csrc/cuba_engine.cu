@@ -19,6 +19,7 @@
 #include "cuba_pcg2.cuh"
 #include "cuba_pcg3.cuh"
 #include "cuba_pcg4.cuh"
+#include "cuba_pcg5.cuh"
 #include "cuba_schur2.cuh"
 #include "cuba_jh4.cuh"
 #include "cuba_schur3.cuh"
@@ -67,15 +68,17 @@ struct PinnedArena {
 template <typename U>
 struct DBuf {
 	U* p = nullptr; size_t n = 0, cap = 0;
+	bool view = false;   // a window into another DBuf's allocation (fused collectives): never freed, never grown here
 	DBuf() {}
 	DBuf(const DBuf&) = delete;
 	DBuf& operator=(const DBuf&) = delete;
 	~DBuf() { release(); }
-	void release() { if (p) cudaFree(p); p = nullptr; n = 0; cap = 0; }
+	void release() { if (p && !view) cudaFree(p); p = nullptr; n = 0; cap = 0; view = false; }
+	void alias(U* q, size_t count) { release(); p = q; n = count; cap = count; view = true; }
 	// grow-only: re-initialising an engine with a problem of the same (or smaller) size allocates nothing
 	cudaError_t alloc(size_t count)
 	{
-		if (p && count <= cap) { n = count; return cudaSuccess; }
+		if (p && count <= cap && !view) { n = count; return cudaSuccess; }
 		release();
 		n = count; cap = count ? count : 1;
 		return cudaMalloc((void**)&p, sizeof(U) * cap);
@@ -104,6 +107,10 @@ struct Nccl {
 	int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
 	int (*CommDestroy)(void*) = nullptr;
 	int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+	int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+	int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+	int (*GroupStart)() = nullptr;
+	int (*GroupEnd)() = nullptr;
 	const char* (*GetErrorString)(int) = nullptr;
 	bool load(std::string& why)
 	{
@@ -115,15 +122,27 @@ struct Nccl {
 		CommInitRank = (int (*)(void**, int, UniqueId, int))dlsym(lib, "ncclCommInitRank");
 		CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
 		AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+		AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(lib, "ncclAllGather");
+		Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclBroadcast");
+		GroupStart = (int (*)())dlsym(lib, "ncclGroupStart");
+		GroupEnd = (int (*)())dlsym(lib, "ncclGroupEnd");
 		GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
-		if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce) { why = "libnccl lacks expected symbols"; return false; }
+		if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !AllGather || !Broadcast || !GroupStart || !GroupEnd) { why = "libnccl lacks expected symbols"; return false; }
 		return true;
 	}
 };
 static Nccl g_nccl;
-enum { NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+enum { NCCL_INT8 = 0, NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2 };
 
 struct Scalars { double v[8]; unsigned long long maxdiag; PcgStatus pcg; };
+
+// Every C ABI entry point runs on the engine's own device, whatever the calling thread's current device is
+// (two engines on two GPUs in one thread; a host that calls torch.cuda.set_device between calls).
+struct DevGuard {
+	int prev = -1, dev;
+	explicit DevGuard(int d) : dev(d) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; if (prev != dev) cudaSetDevice(dev); }
+	~DevGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+};
 
 struct EngineBase {
 	virtual ~EngineBase() {}
@@ -131,6 +150,7 @@ struct EngineBase {
 	int rk_type[2] = { 0, 0 };
 	double rk_delta[2] = { 0, 0 };
 	int rank = 0, world = 1;
+	int devOrdinal = 0;      // CUDA device every call of this engine runs on (set once in init)
 	void* comm = nullptr;
 	bool haveProblem = false;
 	long long launches = 0;
@@ -239,7 +259,9 @@ struct Engine : EngineBase {
 
 	~Engine() override
 	{
+		DevGuard guard(devOrdinal);
 		if (stream) cudaStreamSynchronize(stream);
+		p5CloseMappings();
 		for (auto& pe : profEvents) { cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second); }
 		for (auto ev : eventPool) cudaEventDestroy(ev);
 		if (hScal) cudaFreeHost(hScal);
@@ -258,6 +280,7 @@ struct Engine : EngineBase {
 		if (cfg.device >= 0) CUDA_TRY(cudaSetDevice(cfg.device));
 		int dev = 0;
 		CUDA_TRY(cudaGetDevice(&dev));
+		devOrdinal = dev;
 		CUDA_TRY(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev));
 		CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
 		CUDA_TRY(cudaMallocHost((void**)&hScal, sizeof(Scalars)));
@@ -343,9 +366,13 @@ struct Engine : EngineBase {
 		if (!p) return fail(CUBA_ERR_INVALID, "set_problem: null problem");
 		if (p->Pall < 0 || p->Lall < 0 || p->numP < 0 || p->numL < 0 || p->numP > p->Pall || p->numL > p->Lall || p->E2 < 0 || p->E3 < 0)
 			return fail(CUBA_ERR_INVALID, "set_problem: invalid sizes");
+		if ((p->Pall > 0 && (!p->q || !p->t || !p->cam)) || (p->Lall > 0 && !p->Xw) || (p->E2 > 0 && (!p->idx2 || !p->meas2 || !p->omega2)) ||
+			(p->E3 > 0 && (!p->idx3 || !p->meas3 || !p->omega3)))
+			return fail(CUBA_ERR_INVALID, "set_problem: null array with a non-zero count");
 		const auto t0 = std::chrono::steady_clock::now();
 		haveProblem = false;
 		hostStructureValid = false;
+		shardBoundValid = false;
 		// landmark-tile variant: 0/1 = 256 edges, 2 CTAs/SM; 2 = 256, 3 CTAs/SM; 3 = 128, 4 CTAs/SM; 4 = 128, 6 CTAs/SM
 		switch (cfg.reserved[2]) {
 		case 2: tileSize = 256; jhMinBlocks = 3; break;
@@ -428,6 +455,8 @@ struct Engine : EngineBase {
 	DBuf<sgpu::Meta> g_meta;
 	sgpu::Meta* hMeta = nullptr;
 	bool hostStructureValid = false;
+	int shardBound[9] = { 0 };    // first landmark of every rank's shard
+	bool shardBoundValid = false;
 
 	template <typename K>
 	int sortPairs(K* kin, K* kout, int* vin, int* vout, int n, int endBit)
@@ -500,6 +529,8 @@ struct Engine : EngineBase {
 		tmark("sync 1");
 		S.nhpl = hMeta->nhpl; S.lmBeg = hMeta->lmBeg; S.lmEnd = hMeta->lmEnd; S.eLocal = hMeta->kEnd - hMeta->kBeg;
 		S.hplBase = hMeta->hplBase; S.nhplLocal = hMeta->hplEnd - hMeta->hplBase;
+		for (int r = 0; r < 9; r++) shardBound[r] = hMeta->bounds[r];
+		shardBoundValid = true;
 		const int kBeg = hMeta->kBeg, kEnd = hMeta->kEnd, eL = S.eLocal, nhpl = S.nhpl;
 		CUDA_TRY(g_hplRowInd.alloc(nhpl)); CUDA_TRY(g_hplLmG.alloc(nhpl)); CUDA_TRY(g_edge2Hpl.alloc(E)); CUDA_TRY(g_hplColPtr.alloc((size_t)numL + 1));
 		KLAUNCH(k_hpl_global, E, g_keyS.p, g_valS.p, g_ff.p, g_hplG.p, E, g_hplRowInd.p, g_hplLmG.p, g_edge2Hpl.p);
@@ -608,9 +639,12 @@ struct Engine : EngineBase {
 	{
 		const int eL = S.eLocal;
 		const size_t nP = S.numP, nL = S.numL;
-		CUDA_TRY(Hpp.alloc(36 * nP)); CUDA_TRY(bp.alloc(6 * nP)); CUDA_TRY(Hll.alloc(9 * nL)); CUDA_TRY(bl.alloc(3 * nL));
+		// Hpp | bp | (chi2 slot) and Hsc | bsc are single allocations: one collective each in landmark-sharded runs
+		CUDA_TRY(Hpp.alloc(42 * nP + 2)); bp.alias(Hpp.p + 36 * nP, 6 * nP);
+		CUDA_TRY(Hll.alloc(9 * nL)); CUDA_TRY(bl.alloc(3 * nL));
 		CUDA_TRY(Hpl.alloc(18 * (size_t)S.nhplLocal)); CUDA_TRY(invHll.alloc(9 * nL));
-		CUDA_TRY(fVal.alloc(36 * (size_t)S.nfull)); CUDA_TRY(bsc.alloc(6 * nP)); CUDA_TRY(xp.alloc(6 * nP)); CUDA_TRY(xl.alloc(3 * nL));
+		CUDA_TRY(fVal.alloc(36 * (size_t)S.nfull + 6 * nP)); bsc.alias(fVal.p + 36 * (size_t)S.nfull, 6 * nP);
+		CUDA_TRY(xp.alloc(6 * nP)); CUDA_TRY(xl.alloc(3 * nL));
 		CUDA_TRY(pr.alloc(6 * nP)); CUDA_TRY(pz.alloc(6 * nP)); CUDA_TRY(pq.alloc(6 * nP)); CUDA_TRY(pp0.alloc(6 * nP)); CUDA_TRY(pp1.alloc(6 * nP));
 		CUDA_TRY(Minv.alloc(36 * nP));
 		// landmarks outside this rank's shard keep zero Hll/bl/xl (they are never touched locally)
@@ -646,6 +680,7 @@ struct Engine : EngineBase {
 		if (jhV4) { int rc = setup_jh4(); if (rc) return rc; }
 		tmark("jh4 queued");
 		if (S.numP > 0) { int rc = setup_pcg2(); if (rc) return rc; }        // host-heavy: overlaps the warp-tile kernels queued above
+		if (S.numP > 0 && S.numL > 0) { int rc = setup_pcg5(); if (rc) return rc; }
 		tmark("pcg partition (host)");
 		if (jhV4) { int rc = setup_jh4_finish(); if (rc) return rc; }
 		tmark("jh4 finish");
@@ -830,13 +865,19 @@ struct Engine : EngineBase {
 			ProfScope ps(this, CUBA_PROF_BUILD_SYSTEM);
 			int rc = launch_linearize_landmark(); if (rc) return rc;
 			rc = launch_linearize_pose(); if (rc) return rc;
-			if (world > 1 && S.numP > 0) {
-				// Hpp and bp are separate buffers: two reductions (42*numP scalars in total)
-				rc = allreduce(Hpp.p, 36 * (size_t)S.numP, true); if (rc) return rc;
-				rc = allreduce(bp.p, 6 * (size_t)S.numP, true); if (rc) return rc;
-			}
 			rc = launch_sum(chiPartial, ntiles > 0 ? nChiLin : 0, nullptr, 0, nullptr, 0, 0); if (rc) return rc;
-			if (world > 1) { rc = allreduce(&dScal.p->v[0], 1, false); if (rc) return rc; }
+			if (world > 1) {
+				// ONE collective: Hpp | bp | chi2 are contiguous (the chi2 partial rides in the slot behind bp)
+				if constexpr (sizeof(T) == 8) {
+					T* slot = Hpp.p + 42 * (size_t)S.numP;
+					CUDA_TRY(cudaMemcpyAsync(slot, &dScal.p->v[0], sizeof(double), cudaMemcpyDeviceToDevice, stream));
+					rc = allreduce(Hpp.p, 42 * (size_t)S.numP + 1, true); if (rc) return rc;
+					CUDA_TRY(cudaMemcpyAsync(&dScal.p->v[0], slot, sizeof(double), cudaMemcpyDeviceToDevice, stream));
+				} else {
+					if (S.numP > 0) { rc = allreduce(Hpp.p, 42 * (size_t)S.numP, true); if (rc) return rc; }
+					rc = allreduce(&dScal.p->v[0], 1, false); if (rc) return rc;
+				}
+			}
 		}
 		int rc = fetchScalars(); if (rc) return rc;
 		if (chi) *chi = hScal->v[0];
@@ -852,7 +893,7 @@ struct Engine : EngineBase {
 		return CUBA_OK;
 	}
 
-	int launch_chi2(int buf, int slot)
+	int launch_chi2(int buf, int slot, bool reduce = true)
 	{
 		ProfScope ps(this, CUBA_PROF_COMPUTE_ERROR);
 		if (S.eLocal > 0) {
@@ -861,7 +902,7 @@ struct Engine : EngineBase {
 			CUDA_TRY(cudaGetLastError());
 		}
 		int rc = launch_sum(chiPartial, S.eLocal > 0 ? nChiBlocks : 0, nullptr, 0, nullptr, 0, slot); if (rc) return rc;
-		if (world > 1) { rc = allreduce(&dScal.p->v[slot], 1, false); if (rc) return rc; }
+		if (world > 1 && reduce) { rc = allreduce(&dScal.p->v[slot], 1, false); if (rc) return rc; }
 		return CUBA_OK;
 	}
 
@@ -876,22 +917,13 @@ struct Engine : EngineBase {
 			launches++;
 			CUDA_TRY(cudaGetLastError());
 		}
+		if (world > 1) {
+			const int rcn = g_nccl.AllReduce(&dScal.p->maxdiag, &dScal.p->maxdiag, 1, NCCL_FLOAT64, NCCL_MAX, comm, stream);
+			if (rcn != 0) return fail(CUBA_ERR_COMM, "ncclAllReduce(max) failed");
+		}
 		int rc = fetchScalars(); if (rc) return rc;
 		double m;
 		memcpy(&m, &hScal->maxdiag, sizeof(double));
-		if (world > 1) {
-			// max over ranks: Hll is sharded.  One tiny host-side exchange is avoided by reducing on device:
-			// ncclMax is not loaded; use the sum trick on a one-hot buffer instead -> do a plain allreduce of
-			// the per-rank value into slot arrays.
-			std::vector<double> slots(world, 0.0);
-			slots[rank] = m;
-			DBuf<double> tmp;
-			CUDA_TRY(tmp.upload(slots, stream));
-			rc = allreduce(tmp.p, (size_t)world, false); if (rc) return rc;
-			CUDA_TRY(cudaMemcpyAsync(slots.data(), tmp.p, sizeof(double) * world, cudaMemcpyDeviceToHost, stream));
-			CUDA_TRY(cudaStreamSynchronize(stream));
-			for (double s : slots) m = std::max(m, s);
-		}
 		if (md) *md = m;
 		return CUBA_OK;
 	}
@@ -915,8 +947,7 @@ struct Engine : EngineBase {
 			launches++;
 			CUDA_TRY(cudaGetLastError());
 			if (world > 1) {
-				int rc = allreduce(fVal.p, 36 * (size_t)S.nfull, true); if (rc) return rc;
-				rc = allreduce(bsc.p, 6 * (size_t)S.numP, true); if (rc) return rc;
+				int rc = allreduce(fVal.p, 36 * (size_t)S.nfull + 6 * (size_t)S.numP, true); if (rc) return rc;   // Hsc | bsc: one buffer
 			}
 			return CUBA_OK;
 		}
@@ -936,8 +967,7 @@ struct Engine : EngineBase {
 			launches++;
 			CUDA_TRY(cudaGetLastError());
 			if (world > 1) {
-				int rc = allreduce(fVal.p, 36 * (size_t)S.nfull, true); if (rc) return rc;
-				rc = allreduce(bsc.p, 6 * (size_t)S.numP, true); if (rc) return rc;
+				int rc = allreduce(fVal.p, 36 * (size_t)S.nfull + 6 * (size_t)S.numP, true); if (rc) return rc;   // Hsc | bsc: one buffer
 			}
 		}
 		else if (S.numP > 0 && S.numL > 0) {
@@ -951,8 +981,7 @@ struct Engine : EngineBase {
 			launches++;
 			CUDA_TRY(cudaGetLastError());
 			if (world > 1) {
-				int rc = allreduce(fVal.p, 36 * (size_t)S.nfull, true); if (rc) return rc;
-				rc = allreduce(bsc.p, 6 * (size_t)S.numP, true); if (rc) return rc;
+				int rc = allreduce(fVal.p, 36 * (size_t)S.nfull + 6 * (size_t)S.numP, true); if (rc) return rc;   // Hsc | bsc: one buffer
 			}
 		}
 		return CUBA_OK;
@@ -1044,9 +1073,8 @@ struct Engine : EngineBase {
 	int setup_pcg2()
 	{
 		const int numP = S.numP;
-		int dev = 0, smemMax = 0;
-		CUDA_TRY(cudaGetDevice(&dev));
-		CUDA_TRY(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+		int smemMax = 0;
+		CUDA_TRY(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, devOrdinal));
 		const size_t budget = (size_t)smemMax > 8192 ? (size_t)smemMax - 6144 : 0;   // leave room for the static arrays (4.4 KB in k_pcg3)
 		const size_t matBytes = (size_t)S.nfull * (36 * sizeof(T) + 4);
 		int G = std::max((numP + 7) / 8, (int)((matBytes + budget - 1) / std::max<size_t>(budget, 1)));
@@ -1190,6 +1218,7 @@ struct Engine : EngineBase {
 		return CUBA_OK;
 	}
 	bool lastPcgTwoLevel = false;
+	bool forceBlockJacobi = false;   // retry of a trial whose two-level solve broke down
 	// policy of the default solver: block-Jacobi (k_pcg3, ~5.4 us per iteration) while it converges quickly, two-level (k_pcg4,
 	// ~9 us per iteration but 2-8x fewer of them) once a block-Jacobi solve needed more than 100 iterations -- the count grows
 	// as the LM damping falls.  The decision depends on iteration counts only, so runs stay bit-reproducible.
@@ -1230,11 +1259,279 @@ struct Engine : EngineBase {
 		return CUBA_OK;
 	}
 
+
+	// ---- k_pcg5: two-level, flag-synchronised, rows distributed over the ranks (cuba_pcg5.cuh) --------------------------
+	DBuf<int> p5CtaRow, p5NeedPtr, p5NeedCol, p5Local, p5AggRow, p5NaPtr, p5NaList, p5NeedAgg, p5CbPtr, p5CbList;
+	DBuf<unsigned char> p5RowPeers;
+	DBuf<T> p5Linv, p5R0, p5Zhat, p5RcRow, p5Rc0;
+	DBuf<float> p5AcInv;
+	DBuf<double> p5AcP, p5Lp, p5Wp, p5Ld;
+	DBuf<unsigned long long> p5Boards;
+	void* p5PeerBase[PCG5_MAXWORLD] = { nullptr };   // cudaIpc mappings of the peers' boards (own entry: the local allocation)
+	void* p5MappedFor = nullptr;                   // local allocation the mappings were exchanged for
+	size_t p5WWords = 0, p5PWords = 0, p5RWords = 0;
+	Pcg5Dims p5Dims{}, p5DimsBJ{};
+	size_t p5Smem = 0;
+	int p5G = 0, p5W = 1, p5A = 0, p5Gs = 1;
+	bool p5Ok = false, p5Dist = false, p5Cluster = false;
+	bool p5CoarseValid = false; int p5CoarseAge = 0; double p5CoarseLambda = 0;
+	size_t p5InvSmem = 0;
+	long long p5TagBound = 0;                      // conservative host-side bound on the device tag base
+
+	Pcg5Ctl* p5Ctl(void* base) const { return (Pcg5Ctl*)((unsigned long long*)base + 2 * (p5WWords + p5PWords + p5RWords)); }
+
+	void p5CloseMappings()
+	{
+		for (int r = 0; r < PCG5_MAXWORLD; r++) {
+			if (p5PeerBase[r] && r != rank) cudaIpcCloseMemHandle(p5PeerBase[r]);
+			p5PeerBase[r] = nullptr;
+		}
+		p5MappedFor = nullptr;
+	}
+
+	// Maps the boards of every peer into this process (cudaIpc over NVLink peer access); the 64-byte handles travel by
+	// ncclAllGather.  All ranks agree on the outcome (sum of per-rank success flags), so either everybody runs the distributed
+	// solve or everybody keeps the replicated one.
+	int p5Exchange(bool& ok)
+	{
+		ok = false;
+		if (p5MappedFor == (void*)p5Boards.p) { ok = true; return CUBA_OK; }
+		p5CloseMappings();
+		cudaIpcMemHandle_t mine;
+		int good = cudaIpcGetMemHandle(&mine, p5Boards.p) == cudaSuccess ? 1 : 0;
+		if (!good) cudaGetLastError();
+		DBuf<char> dh;
+		CUDA_TRY(dh.alloc(sizeof(cudaIpcMemHandle_t) * (size_t)world));
+		CUDA_TRY(cudaMemcpyAsync(dh.p + sizeof(cudaIpcMemHandle_t) * (size_t)rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, stream));
+		int rc = g_nccl.AllGather(dh.p + sizeof(cudaIpcMemHandle_t) * (size_t)rank, dh.p, sizeof(cudaIpcMemHandle_t), NCCL_INT8, comm, stream);
+		if (rc != 0) return fail(CUBA_ERR_COMM, "ncclAllGather (board handles) failed");
+		std::vector<cudaIpcMemHandle_t> all(world);
+		CUDA_TRY(cudaMemcpyAsync(all.data(), dh.p, sizeof(cudaIpcMemHandle_t) * (size_t)world, cudaMemcpyDeviceToHost, stream));
+		CUDA_TRY(cudaStreamSynchronize(stream));
+		for (int r = 0; r < world && good; r++) {
+			if (r == rank) { p5PeerBase[r] = (void*)p5Boards.p; continue; }
+			if (cudaIpcOpenMemHandle(&p5PeerBase[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); p5PeerBase[r] = nullptr; good = 0; }
+		}
+		// agreement
+		DBuf<double> flag;
+		CUDA_TRY(flag.alloc(1));
+		const double mineOk = good;
+		CUDA_TRY(cudaMemcpyAsync(flag.p, &mineOk, sizeof(double), cudaMemcpyHostToDevice, stream));
+		rc = allreduce(flag.p, 1, false); if (rc) return rc;
+		double tot = 0;
+		CUDA_TRY(cudaMemcpyAsync(&tot, flag.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
+		CUDA_TRY(cudaStreamSynchronize(stream));
+		if ((int)(tot + 0.5) != world) { p5CloseMappings(); return CUBA_OK; }
+		p5MappedFor = (void*)p5Boards.p;
+		ok = true;
+		return CUBA_OK;
+	}
+
+	// Partition of the rows over world x G virtual CTAs, aggregates aligned with the ranks, shared-memory budget, boards.
+	int setup_pcg5()
+	{
+		p5Ok = false; p5Dist = false; p5CoarseValid = false; p5CoarseAge = 0;
+		const int numP = S.numP;
+		if (numP < 1) return CUBA_OK;
+		const int mode = cfg.reserved[0];
+		if (mode == 1 || mode == 2 || mode == 3 || mode == 4) return CUBA_OK;          // an older kernel was asked for explicitly
+		const bool wantDist = world > 1 && mode != 7 && (mode == 8 || numP >= 2048);
+		const int W = wantDist ? world : 1;
+		int smemMax = 0;
+		CUDA_TRY(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, devOrdinal));
+		const size_t budget = (size_t)smemMax > 4096 ? (size_t)smemMax - 2048 : 0;   // static arrays of k_pcg5: < 1 KB
+		// CTAs per GPU: about eight rows each, never more than 42 (one thread per (row, component) pair in the row sums)
+		int G = std::max(1, std::min(numSMs, (numP / W + 7) / 8));
+		if (W * G > numP) G = std::max(1, numP / W);
+		const int maxAgg = (cfg.reserved[6] > 0 && cfg.reserved[6] < PCG4_MAXAGG) ? cfg.reserved[6] : PCG4_MAXAGG;
+		const int gs = (W * G + maxAgg - 1) / maxAgg;
+		G = std::max(gs, G / gs * gs);
+		const int Gt = W * G, A = Gt / gs;
+		if (Gt > numP || A < 1) return CUBA_OK;
+		PcgPartition PP; CoarsePartition CP;
+		build_pcg_partition(numP, S.nfull, S.fRowPtr, S.fColInd, Gt, PP);
+		build_coarse_partition(numP, PP, A, CP);
+		if (CP.gs != gs || CP.A != A || PP.maxRows * 6 > PCG5_BLOCK) return CUBA_OK;
+		build_coarse_lists(numP, S.nfull, S.fRowPtr, S.fColInd, CP);
+		// which ranks need a row's w besides its owner
+		std::vector<unsigned char> peers(numP, 0);
+		if (W > 1) {
+			std::vector<int> rowRank(numP, 0);
+			for (int c = 0; c < Gt; c++) for (int r = PP.rows[c]; r < PP.rows[c + 1]; r++) rowRank[r] = c / G;
+			for (int c = 0; c < Gt; c++)
+				for (int k = PP.nptr[c]; k < PP.nptr[c + 1]; k++) { const int j = PP.ncol[k]; if (rowRank[j] != c / G) peers[j] |= (unsigned char)(1u << (c / G)); }
+		}
+		const int Aloc = G / gs, NR = 3 + 6 * Aloc, nc = 6 * A;
+		Pcg5Dims d{};
+		d.needMax = PP.needMax; d.maxRows = PP.maxRows; d.nc = nc; d.maxNeedAgg = CP.maxNeedAgg;
+		d.npv = std::max(G * 9, W * NR); d.nls = NR;
+		const size_t per = 36 * sizeof(T) + 4;
+		const size_t wantCache = PP.blkMax > PCG5_REGBLK ? (size_t)(PP.blkMax - PCG5_REGBLK) : 0;
+		{
+			d.capBlocks = 0; d.zhInSmem = 0; d.sliceInSmem = 0;
+			const size_t base = Pcg5Layout<T>(d).total + 64;
+			if (base > budget) return CUBA_OK;
+			const size_t zhBytes = (size_t)d.needMax * 36 * sizeof(T), slBytes = (size_t)d.maxNeedAgg * 6 * nc * sizeof(float);
+			size_t used = base + wantCache * per;
+			if (used + zhBytes <= budget) { d.zhInSmem = 1; used += zhBytes; }
+			if (used + slBytes <= budget) { d.sliceInSmem = 1; used += slBytes; }
+			const size_t fixed = used - wantCache * per;
+			d.capBlocks = (int)std::min(wantCache, (budget - fixed) / per);
+		}
+		p5Dims = d;
+		p5DimsBJ = d; p5DimsBJ.nc = 0; p5DimsBJ.maxNeedAgg = 0; p5DimsBJ.zhInSmem = 0; p5DimsBJ.sliceInSmem = 0; p5DimsBJ.nls = 3; p5DimsBJ.npv = std::max(G * 3, W * 3);
+		p5Smem = std::max(Pcg5Layout<T>(p5Dims).total, Pcg5Layout<T>(p5DimsBJ).total);
+		if (p5Smem > (size_t)smemMax - 1024) return CUBA_OK;
+		CUDA_TRY(cudaFuncSetAttribute(k_pcg5<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p5Smem));
+		int perSM = 0;
+		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_pcg5<T>, PCG5_BLOCK, p5Smem));
+		if (perSM < 1) return CUBA_OK;
+		if (getenv("CUBA_PCG_VERBOSE")) fprintf(stderr, "pcg5: world %d G %d gs %d A %d needMax %d maxRows %d blkMax %d maxNeedAgg %d zhInSmem %d sliceInSmem %d cap %d smem %zu\n",
+			W, G, gs, A, d.needMax, d.maxRows, PP.blkMax, d.maxNeedAgg, d.zhInSmem, d.sliceInSmem, d.capBlocks, p5Smem);
+		// coarse inverse: packed block triangle in the shared memory of one CTA (A <= 37) or of an 8-CTA cluster
+		p5Cluster = A > PCG4_MAXAGG1;
+		const size_t nblkPz = (size_t)A * (A + 1) / 2;
+		p5InvSmem = p5Cluster ? (((nblkPz + PCG4_CL - 1) / PCG4_CL + 2 * (size_t)A) * 36 * sizeof(double) + 2 * nblkPz + 16) : ((nblkPz + 2 * (size_t)A) * 36 * sizeof(double));
+		if (p5InvSmem + 1024 > (size_t)smemMax) return CUBA_OK;
+		if (p5Cluster) CUDA_TRY(cudaFuncSetAttribute(k_coarse_chol_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(p5InvSmem, pcg4Cluster ? pcg4InvSmem : 0)));
+		else CUDA_TRY(cudaFuncSetAttribute(k_coarse_invert<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(p5InvSmem, (!pcg4Cluster && pcg4Ok) ? pcg4InvSmem : 0)));
+		CUDA_TRY(p5CtaRow.upload(PP.rows, stream, arena)); CUDA_TRY(p5NeedPtr.upload(PP.nptr, stream, arena)); CUDA_TRY(p5NeedCol.upload(PP.ncol, stream, arena));
+		CUDA_TRY(p5Local.upload(PP.local, stream, arena)); CUDA_TRY(p5RowPeers.upload(peers, stream, arena));
+		CUDA_TRY(p5AggRow.upload(CP.aggRow, stream, arena)); CUDA_TRY(p5NaPtr.upload(CP.naPtr, stream, arena)); CUDA_TRY(p5NaList.upload(CP.naList, stream, arena));
+		CUDA_TRY(p5NeedAgg.upload(CP.needAgg, stream, arena)); CUDA_TRY(p5CbPtr.upload(CP.cbPtr, stream, arena)); CUDA_TRY(p5CbList.upload(CP.cbList, stream, arena));
+		CUDA_TRY(cRowOf.upload(CP.rowOf, stream, arena));
+		const size_t nP = (size_t)numP;
+		CUDA_TRY(p5Linv.alloc(36 * nP)); CUDA_TRY(p5R0.alloc(6 * nP)); CUDA_TRY(p5Zhat.alloc(36 * nP)); CUDA_TRY(p5RcRow.alloc(6 * nP)); CUDA_TRY(p5Rc0.alloc(std::max(nc, 1)));
+		CUDA_TRY(cZx.alloc(36 * nP)); CUDA_TRY(cU.alloc(36 * (size_t)S.nfull)); CUDA_TRY(cInfo.alloc(1));
+		CUDA_TRY(fHat.alloc(36 * (size_t)S.nfull));
+		CUDA_TRY(p5AcP.alloc(nblkPz * 36)); CUDA_TRY(p5AcInv.alloc((size_t)nc * nc)); CUDA_TRY(p5Lp.alloc(nblkPz * 36)); CUDA_TRY(p5Wp.alloc(nblkPz * 36)); CUDA_TRY(p5Ld.alloc((size_t)A * 36));
+		// boards (16-byte words): [2 solve halves][2 pass parities] of w, of the per-CTA partials and of the rank summaries, then the control block
+		const size_t wW = 4 * 6 * nP, pW = 4 * (size_t)PCG5_REPL * G * 9, rW = 4 * (size_t)PCG5_REPL * W * NR;
+		const size_t words2 = 2 * (wW + pW + rW) + (sizeof(Pcg5Ctl) + 7) / 8 + 2;
+		const bool fresh = !p5Boards.p || words2 > p5Boards.cap || wW != p5WWords || pW != p5PWords || rW != p5RWords;
+		if (fresh) {
+			// the tag protocol needs boards that start out as zeros; a layout change invalidates every mapping and every tag
+			if (p5MappedFor) { CUDA_TRY(cudaStreamSynchronize(stream)); p5CloseMappings(); }
+			CUDA_TRY(p5Boards.alloc(std::max(words2, (size_t)(1u << 18))));
+			CUDA_TRY(cudaMemsetAsync(p5Boards.p, 0, sizeof(unsigned long long) * p5Boards.cap, stream));
+			p5WWords = wW; p5PWords = pW; p5RWords = rW;
+			p5TagBound = 0;
+		}
+		p5G = G; p5W = W; p5A = A; p5Gs = gs;
+		if (W > 1) {
+			bool ok = false;
+			int rc = p5Exchange(ok); if (rc) return rc;
+			if (!ok) {
+				if (rank == 0) fprintf(stderr, "cuba_b200: cudaIpc mapping of the peers' PCG boards failed; keeping the replicated PCG\n");
+				return CUBA_OK;
+			}
+			p5Dist = true;
+		} else p5PeerBase[rank] = (void*)p5Boards.p;
+		p5Ok = true;
+		return CUBA_OK;
+	}
+
+	// coarse matrix Ac = Z^T S Z of the current system and its inverse (fp32), for the aggregates behind (cbPtr, cbList)
+	int launch_coarse_setup(int A, bool cluster, size_t invSmem, const int* cbPtr, const int* cbList, double* AcP, float* AcInv, double* Lp, double* Ld, double* Wp)
+	{
+		const int nblkP = A * (A + 1) / 2;
+		KLAUNCH(k_coarse_project<T>, 36LL * S.nfull, fVal.p, cRowOf.p, fColInd.p, S.nfull, cZx.p, cU.p);
+		KLAUNCH(k_coarse_assemble, (long long)nblkP * 36, cbPtr, cbList, cU.p, nblkP, AcP);
+		if (cluster) {
+			// Cholesky in the shared memory of an 8-CTA cluster, then the triangular inverse (one CTA per block column) and W^T W on the whole chip
+			k_coarse_chol_cluster<<<PCG4_CL, 1024, invSmem, stream>>>(AcP, A, Lp, Ld, AcInv, cInfo.p);
+			k_coarse_trinv<<<A, 256, (size_t)A * 36 * sizeof(double), stream>>>(Lp, Ld, A, Wp, cInfo.p);
+			k_coarse_wtw<<<(nblkP * 36 + 255) / 256, 256, 0, stream>>>(Wp, A, AcInv, cInfo.p);
+			launches += 2;
+		}
+		else k_coarse_invert<T><<<1, 1024, invSmem, stream>>>(AcP, A, AcInv, cInfo.p);
+		launches++;
+		CUDA_TRY(cudaGetLastError());
+		return CUBA_OK;
+	}
+
+	int launch_pcg5(bool twoLevel)
+	{
+		ProfScope ps(this, CUBA_PROF_DECOMP_NUMERICAL);
+		const int numP = S.numP, A = twoLevel ? p5A : 0;
+		const int maxIters = cfg.pcg_max_iters > 0 ? cfg.pcg_max_iters : std::max(200, 40 * numP);
+		// tags are 32 bits: long before the device tag base can wrap, every rank (same arithmetic everywhere) clears its boards
+		p5TagBound += (long long)maxIters + 8;
+		if (p5TagBound > (1LL << 31)) {
+			if (p5Dist) { int rc0 = allreduce(&dScal.p->v[7], 1, false); if (rc0) return rc0; }   // nobody still writes into a peer's boards
+			CUDA_TRY(cudaMemsetAsync(p5Boards.p, 0, sizeof(unsigned long long) * p5Boards.cap, stream));
+			if (p5Dist) { int rc0 = allreduce(&dScal.p->v[7], 1, false); if (rc0) return rc0; }
+			p5TagBound = (long long)maxIters + 8;
+		}
+		if (twoLevel) KLAUNCH(k_coarse_basis<T>, numP, pose[cur].p, numP, cZx.p);
+		Pcg5PrepArgs<T> pa;
+		pa.fRowPtr = fRowPtr; pa.fColInd = fColInd; pa.fVal = fVal; pa.b = bsc; pa.Zx = cZx; pa.numP = numP; pa.A = A; pa.aggRow = p5AggRow;
+		pa.Linv = p5Linv; pa.R0 = p5R0; pa.Zhat = p5Zhat; pa.rcRow = p5RcRow; pa.rc0 = p5Rc0; pa.ctl = p5Ctl(p5Boards.p);
+		k_pcg5_prep_rows<T><<<(numP + 127) / 128, 128, 0, stream>>>(pa);
+		launches++;
+		if (twoLevel) {
+			k_pcg5_prep_rc<T><<<(6 * A + 127) / 128, 128, 0, stream>>>(pa);
+			launches++;
+			// The coarse inverse is rebuilt only now and then (see launch_pcg4: any SPD stand-in keeps M^-1 a valid preconditioner).
+			const int refreshEvery = cfg.reserved[4] > 0 ? cfg.reserved[4] : 8;
+			const double lamRatio = (p5CoarseValid && p5CoarseLambda > 0 && curLambda > 0) ? std::max(curLambda / p5CoarseLambda, p5CoarseLambda / curLambda) : 1.0;
+			if (!p5CoarseValid || p5CoarseAge >= refreshEvery || lamRatio > 300.0) {
+				int rc = launch_coarse_setup(A, p5Cluster, p5InvSmem, p5CbPtr, p5CbList, p5AcP, p5AcInv, p5Lp, p5Ld, p5Wp); if (rc) return rc;
+				p5CoarseValid = true; p5CoarseAge = 0; p5CoarseLambda = curLambda;
+			}
+			p5CoarseAge++;
+		}
+		CUDA_TRY(cudaGetLastError());
+		Pcg5Args<T> a;
+		a.fRowPtr = fRowPtr; a.fColInd = fColInd; a.fLocal = p5Local; a.fVal = fVal; a.fHat = fHat;
+		a.ctaRow = p5CtaRow; a.needPtr = p5NeedPtr; a.needCol = p5NeedCol;
+		a.numP = numP; a.G = p5G; a.rank = p5Dist ? rank : 0; a.world = p5W;
+		a.Linv = p5Linv; a.R0 = p5R0; a.Zhat = p5Zhat; a.rc0 = p5Rc0; a.x = xp;
+		a.dims = twoLevel ? p5Dims : p5DimsBJ;
+		a.dims.capBlocks = p5Dims.capBlocks;
+		a.maxIters = maxIters;
+		const double tol = cfg.pcg_tol > 0 ? cfg.pcg_tol : (sizeof(T) == 8 ? 1e-11 : 1e-6);
+		a.tol2 = tol * tol;
+		a.status = &dScal.p->pcg;
+		a.AcInv = p5AcInv; a.naPtr = p5NaPtr; a.naList = p5NaList; a.needAgg = p5NeedAgg; a.A = A; a.gs = p5Gs;
+		for (int r = 0; r < PCG5_MAXWORLD; r++) { a.peerW[r] = nullptr; a.peerR[r] = nullptr; a.peerCtl[r] = nullptr; }
+		for (int r = 0; r < p5W; r++) {
+			unsigned long long* base = (unsigned long long*)p5PeerBase[p5Dist ? r : rank];
+			a.peerW[r] = base; a.peerR[r] = base + 2 * (p5WWords + p5PWords); a.peerCtl[r] = p5Ctl(base);
+		}
+		a.wBoard = p5Boards.p; a.pBoard = p5Boards.p + 2 * p5WWords; a.rBoard = p5Boards.p + 2 * (p5WWords + p5PWords);
+		a.rowPeers = p5RowPeers; a.ctl = p5Ctl(p5Boards.p);
+		a.timing = nullptr;
+#ifdef CUBA_PCG_TIMING
+		CUDA_TRY(pcgTiming.alloc(8 * (size_t)p5G));
+		a.timing = pcgTiming.p;
+#endif
+		if (p5Dist) CUDA_TRY(cudaMemsetAsync(xp.p, 0, sizeof(T) * 6 * (size_t)numP, stream));     // rows of the other ranks: summed in below
+		void* args[] = { (void*)&a };
+		CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_pcg5<T>, dim3(p5G), dim3(PCG5_BLOCK), args, p5Smem, stream));
+		k_pcg5_commit<<<1, 1, 0, stream>>>(p5Ctl(p5Boards.p));
+		launches += 2;
+		CUDA_TRY(cudaGetLastError());
+		if (p5Dist) { int rc = allreduce(xp.p, 6 * (size_t)numP, true); if (rc) return rc; }
+		lastPcgTwoLevel = twoLevel;
+		return CUBA_OK;
+	}
+
 	int launch_pcg()
 	{
 		lastPcgTwoLevel = false;
-		// 0: automatic (block-Jacobi k_pcg3 while quick, two-level k_pcg4 afterwards); 3: always two-level; 4: always k_pcg3
-		if (pcg4Ok && (cfg.reserved[0] == 3 || (cfg.reserved[0] == 0 && tlActive))) return launch_pcg4();
+		// 0 (also 7, 8): automatic = block-Jacobi while a solve converges quickly, two-level afterwards -- k_pcg5 for the two-level solves
+		// (and, when the rows are distributed over the ranks, for every solve), k_pcg3 for the quick block-Jacobi ones on one GPU;
+		// 5: always two-level k_pcg5; 6: always block-Jacobi k_pcg5; 3: always k_pcg4; 4: always k_pcg3; 2: k_pcg2; 1: k_pcg
+		{
+			const int m = cfg.reserved[0];
+			const bool two = tlActive && !forceBlockJacobi;
+			if (p5Ok && (m == 5 || m == 6)) return launch_pcg5(m == 5 && !forceBlockJacobi);
+			if (p5Ok && (m == 0 || m == 7 || m == 8) && (p5Dist || two)) return launch_pcg5(two);
+			if ((m == 0 || m == 7 || m == 8) && !(pcg4Ok && two)) return launch_pcg2(pcg3Ok);
+			if ((m == 0 || m == 7 || m == 8) && pcg4Ok && two) return launch_pcg4();
+		}
+		if (pcg4Ok && cfg.reserved[0] == 3 && !forceBlockJacobi) return launch_pcg4();
 		if (cfg.reserved[0] == 0 || cfg.reserved[0] == 3 || cfg.reserved[0] == 4) return launch_pcg2(pcg3Ok);  // k_pcg3: flag-synchronised exchange (k_pcg2 beyond ~85 rows per CTA)
 		if (cfg.reserved[0] == 2) return launch_pcg2(false);   // k_pcg2: one grid barrier per iteration
 		ProfScope ps(this, CUBA_PROF_DECOMP_NUMERICAL);
@@ -1316,10 +1613,10 @@ struct Engine : EngineBase {
 				CUDA_TRY(cudaGetLastError());
 			}
 		}
-		int rc = launch_chi2(cur ^ 1, 1); if (rc) return rc;
+		int rc = launch_chi2(cur ^ 1, 1, false); if (rc) return rc;
 		// scale = sum over [xp;xl] of x (lambda x + b): pose part is replicated, landmark part is sharded
 		rc = launch_sum(scalePartialL, nScaleLandmark, scalePartialP, S.numP > 0 ? nPoseBlocks : 0, nullptr, 0, 2); if (rc) return rc;
-		if (world > 1) { rc = allreduce(&dScal.p->v[2], 1, false); if (rc) return rc; }
+		if (world > 1) { rc = allreduce(&dScal.p->v[1], 2, false); if (rc) return rc; }   // trial chi2 and the landmark part of the scale: adjacent slots
 		rc = fetchScalars(); if (rc) return rc;
 		trialValid = true;
 		if (chi) *chi = hScal->v[1];
@@ -1344,6 +1641,7 @@ struct Engine : EngineBase {
 		double nu = 2, lambda = 0, F = 0;
 		int n = 0;
 		tlActive = false; coarseValid = false; coarseAge = 0;     // results never depend on what the engine solved before
+		p5CoarseValid = false; p5CoarseAge = 0; forceBlockJacobi = false;
 		bool haveF = false;
 		for (int it = 0; it < niter; it++) {
 			double chi0 = 0;
@@ -1361,10 +1659,28 @@ struct Engine : EngineBase {
 			for (; q < maxq && rho < 0; q++) {
 				trials++;
 				int iters = 0, ok = 1;
-				rc = stage_solve(lambda, nullptr, nullptr); if (rc) return rc;
 				double Fhat = 0, scale = 0;
-				rc = stage_update(lambda, &Fhat, &scale); if (rc) return rc;
-				if (S.numP > 0 && S.numL > 0) { iters = hScal->pcg.iters; ok = hScal->pcg.status == 0; note_pcg_iters(iters); }
+				for (int attempt = 0; attempt < 2; attempt++) {
+					rc = stage_solve(lambda, nullptr, nullptr); if (rc) return rc;
+					rc = stage_update(lambda, &Fhat, &scale); if (rc) return rc;
+					if (!(S.numP > 0 && S.numL > 0)) break;
+					const PcgStatus& ps = hScal->pcg;
+					iters += ps.iters;
+					if (ps.status == 3) return fail(CUBA_ERR_COMM, "PCG: a CTA or a peer GPU stopped answering (flag exchange timed out)");
+					// The reference's direct solve fails only when the factorisation does (cuda_linear_solver.cpp:406-410).  Here: a solve
+					// that ran into the iteration cap is still used when its residual fell far enough for an LM step; a breakdown of a
+					// two-level solve (the fp32 coarse inverse lost definiteness) is retried once with block-Jacobi alone.
+					const double loose = sizeof(T) == 8 ? 1e-6 : 1e-3;
+					ok = ps.status == 0 || (ps.status == 1 && ps.rz0 > 0 && ps.rz <= loose * loose * ps.rz0);
+					if (ps.status == 2 && lastPcgTwoLevel && attempt == 0) {
+						forceBlockJacobi = true; coarseValid = false; p5CoarseValid = false;
+						rc = stage_commit(0); if (rc) return rc;
+						continue;
+					}
+					break;
+				}
+				forceBlockJacobi = false;
+				if (S.numP > 0 && S.numL > 0) note_pcg_iters(hScal->pcg.iters);
 				pcgIters += iters; if (!ok) pcgFailed++;
 				scale += 1e-3;
 				rho = ok ? (F - Fhat) / scale : -1;
@@ -1388,6 +1704,7 @@ struct Engine : EngineBase {
 			if (q == maxq || rho <= 0 || !std::isfinite(lambda)) break;
 		}
 		if (nstats) *nstats = n;
+		resolveProfile();   // the stream is idle (every trial ends with a fetch): recycle the profile events instead of hoarding them
 		return CUBA_OK;
 	}
 
@@ -1398,14 +1715,29 @@ struct Engine : EngineBase {
 		g_d2hBytes += (long long)(sizeof(T) * (hp.size() + hx.size()));
 		CUDA_TRY(cudaMemcpyAsync(hp.data(), pose[cur].p, sizeof(T) * hp.size(), cudaMemcpyDeviceToHost, stream));
 		if (world > 1 && S.numL > 0) {
-			// gather the sharded landmarks: zero foreign entries, sum over ranks
-			DBuf<T> tmp;
-			CUDA_TRY(tmp.alloc((size_t)S.Lall * 4));
-			CUDA_TRY(cudaMemsetAsync(tmp.p, 0, sizeof(T) * 4 * (size_t)S.Lall, stream));
-			if (S.lmEnd > S.lmBeg)
-				CUDA_TRY(cudaMemcpyAsync(tmp.p + 4 * (size_t)S.lmBeg, Xw[cur].p + 4 * (size_t)S.lmBeg, sizeof(T) * 4 * (size_t)(S.lmEnd - S.lmBeg), cudaMemcpyDeviceToDevice, stream));
-			int rc = allreduce(tmp.p, 4 * (size_t)S.Lall, true); if (rc) return rc;
-			CUDA_TRY(cudaMemcpyAsync(hx.data(), tmp.p, sizeof(T) * hx.size(), cudaMemcpyDeviceToHost, stream));
+			// all-gather of the sharded landmarks: every rank broadcasts its own range in place (one grouped NCCL call).
+			// The trial buffer is free between LM iterations and serves as the gather target.
+			T* tmp = Xw[cur ^ 1].p;
+			trialValid = false;
+			CUDA_TRY(cudaMemcpyAsync(tmp, Xw[cur].p, sizeof(T) * 4 * (size_t)S.Lall, cudaMemcpyDeviceToDevice, stream));
+			if (shardBoundValid) {
+				const int dt = sizeof(T) == 8 ? NCCL_FLOAT64 : NCCL_FLOAT32;
+				g_nccl.GroupStart();
+				int rcn = 0;
+				for (int r = 0; r < world; r++) {
+					const int b0 = std::min(shardBound[r], S.numL), b1 = std::min(shardBound[r + 1], S.numL);     // fixed landmarks never change
+					if (b1 > b0) rcn |= g_nccl.Broadcast(tmp + 4 * (size_t)b0, tmp + 4 * (size_t)b0, 4 * (size_t)(b1 - b0), dt, r, comm, stream);
+				}
+				rcn |= g_nccl.GroupEnd();
+				if (rcn != 0) return fail(CUBA_ERR_COMM, "ncclBroadcast (landmark gather) failed");
+			} else {
+				// host-built structure (debug path): zero the foreign entries, sum over ranks
+				CUDA_TRY(cudaMemsetAsync(tmp, 0, sizeof(T) * 4 * (size_t)S.Lall, stream));
+				if (S.lmEnd > S.lmBeg)
+					CUDA_TRY(cudaMemcpyAsync(tmp + 4 * (size_t)S.lmBeg, Xw[cur].p + 4 * (size_t)S.lmBeg, sizeof(T) * 4 * (size_t)(S.lmEnd - S.lmBeg), cudaMemcpyDeviceToDevice, stream));
+				int rc = allreduce(tmp, 4 * (size_t)S.Lall, true); if (rc) return rc;
+			}
+			CUDA_TRY(cudaMemcpyAsync(hx.data(), tmp, sizeof(T) * hx.size(), cudaMemcpyDeviceToHost, stream));
 			CUDA_TRY(cudaStreamSynchronize(stream));
 		} else {
 			CUDA_TRY(cudaMemcpyAsync(hx.data(), Xw[cur].p, sizeof(T) * hx.size(), cudaMemcpyDeviceToHost, stream));
@@ -1593,9 +1925,9 @@ int cuba_engine_create(const cuba_config* cfg, cuba_engine** out)
 	return CUBA_OK;
 }
 
-int cuba_engine_destroy(cuba_engine* e) { delete e; return CUBA_OK; }
+int cuba_engine_destroy(cuba_engine* e) { delete e; return CUBA_OK; }   // ~Engine switches to its own device itself
 
-#define ENGINE_OR_FAIL(e) if (!(e) || !(e)->impl) return fail(CUBA_ERR_INVALID, "null engine")
+#define ENGINE_OR_FAIL(e) if (!(e) || !(e)->impl) return fail(CUBA_ERR_INVALID, "null engine"); DevGuard _devGuard((e)->impl->devOrdinal)
 
 int cuba_engine_set_robust_kernel(cuba_engine* e, int edge_type, int kernel_type, double delta)
 {
@@ -1619,7 +1951,7 @@ int cuba_comm_unique_id(void* out128)
 int cuba_engine_set_comm(cuba_engine* e, int rank, int world, const void* uid)
 {
 	ENGINE_OR_FAIL(e);
-	if (world < 1 || rank < 0 || rank >= world) return fail(CUBA_ERR_INVALID, "set_comm: bad rank/world");
+	if (world < 1 || rank < 0 || rank >= world || world > PCG5_MAXWORLD) return fail(CUBA_ERR_INVALID, "set_comm: bad rank/world (at most 8 ranks)");
 	if (e->impl->haveProblem) return fail(CUBA_ERR_STATE, "set_comm must precede set_problem");
 	e->impl->rank = rank; e->impl->world = world;
 	if (world == 1) return CUBA_OK;
@@ -1652,6 +1984,7 @@ int cuba_engine_get_profile(cuba_engine* e, double* sec) { ENGINE_OR_FAIL(e); if
 int cuba_debug_get_pcg_timing(cuba_engine* e, long long* out, int maxCtas)
 {
 	if (!e || !e->impl) return -1;
+	DevGuard guard(e->impl->devOrdinal);
 	return e->impl->dbg_pcg_timing(out, maxCtas);
 }
 int cuba_get_transfer_bytes(long long* h2d, long long* d2h) { if (h2d) *h2d = g_h2dBytes; if (d2h) *d2h = g_d2hBytes; return CUBA_OK; }

@@ -27,6 +27,7 @@ struct Meta {            // small device->host record, one copy per sync point
 	long long nmul;      // number of real block products (without the diagonal dummies)
 	int nblk;
 	int npe;             // pose-major entries
+	int bounds[9];       // first landmark of every rank's shard (world <= 8), bounds[world] = Lall
 };
 
 // (iL, iP) sort keys of the user-order edges; validates the indices.
@@ -105,6 +106,10 @@ __global__ void k_shard_meta(const int* __restrict__ lmPtrG, int Lall, int E, in
 	int b1 = bound(rank + 1);
 	if (b1 < b0) b1 = b0;
 	meta->lmBeg = b0; meta->lmEnd = b1; meta->kBeg = lmPtrG[b0]; meta->kEnd = lmPtrG[b1];
+	{
+		int prev = 0;
+		for (int r = 0; r <= world && r < 9; r++) { int b = bound(r); if (b < prev) b = prev; meta->bounds[r] = b; prev = b; }
+	}
 	const int nh = E > 0 ? hplG[E - 1] + ff[E - 1] : 0;
 	meta->nhpl = nh;
 	meta->hplBase = meta->kBeg < E ? hplG[meta->kBeg] : nh;

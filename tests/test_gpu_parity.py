@@ -143,10 +143,11 @@ def test_against_compiled_reference(pkg, problems, name, kernel):
     eng.close()
 
 
-@pytest.mark.parametrize("variant", [0, 3, 4, 2, 1])
+@pytest.mark.parametrize("variant", [0, 5, 6, 3, 4, 2, 1])
 def test_all_pcg_kernels_solve_the_same_system(pkg, oracle, problems, variant):
-    """automatic policy (0), two-level k_pcg4 (3), k_pcg3 (4, flag-synchronised), k_pcg2 (single barrier) and k_pcg (first
-    generation) against the direct solve"""
+    """automatic policy (0), k_pcg5 two-level (5) and block-Jacobi (6) (flag-synchronised, the kernel that also runs distributed
+    over the ranks), two-level k_pcg4 (3), k_pcg3 (4, flag-synchronised), k_pcg2 (single barrier) and k_pcg (first generation)
+    against the direct solve"""
     prob = problems("kitti07_shaped"); rk = KERNELS["huber"]
     eng = make_engine(pkg, prob, rk, pcg_variant=variant)
     o = oracle.Oracle(prob, *rk)
@@ -327,12 +328,13 @@ def test_jh_landmark_kernels_agree(pkg, oracle, problems, name):
             assert relerr(a, b) < STAGE_TOL, nme
 
 
+@pytest.mark.parametrize("two_level", [3, 5])
 @pytest.mark.parametrize("name", ["kitti07_shaped", "kitti00_shaped"])
-def test_two_level_pcg_converges_faster_to_the_same_solution(pkg, problems, name):
+def test_two_level_pcg_converges_faster_to_the_same_solution(pkg, problems, name, two_level):
     """k_pcg4 (block-Jacobi + rigid-aggregate coarse correction) vs k_pcg3 (block-Jacobi) on the same reduced system at a low
     damping: same solution to the CG tolerance, several times fewer iterations"""
     prob = problems(name); rk = KERNELS["huber"]
-    a = make_engine(pkg, prob, rk, pcg_variant=3); b = make_engine(pkg, prob, rk, pcg_variant=4)
+    a = make_engine(pkg, prob, rk, pcg_variant=two_level); b = make_engine(pkg, prob, rk, pcg_variant=4)
     a.linearize(); b.linearize()
     lam = 1e-8 * a.max_diagonal()
     ia, oka = a.solve(lam); ib, okb = b.solve(lam)
