@@ -5,15 +5,29 @@
 //   index assignment     cpp:142-200  (ascending id, free first, fixed appended, edge-less vertices skipped)
 //   edge flattening      cpp:202-243  (monocular ids first, then stereo; both-fixed edges dropped)
 //   finalize/getChiSqs   cpp:512-543  (write-back of q,t,Xw into the caller's vertices, per-edge chi2)
-// Differences, on purpose: edges are kept in insertion order (the reference iterates an unordered_set, so
-// its order depends on heap addresses); the per-pose cameras are rebuilt on every initialize() (the
-// reference never clears cameras_); removing a vertex copies its edge set before erasing from it.
+// Differences, on purpose:
+//   * edges are kept in insertion order (the reference iterates an unordered_set, so its order depends on heap addresses);
+//   * the per-pose cameras are rebuilt on every initialize() (the reference never clears cameras_);
+//   * removing a vertex copies its edge set before erasing from it;
+//   * initialize() is built for repeated local-BA calls: vertices are looked up through hash maps and walked in a cached
+//     ascending-id order (re-sorted only after an add/remove), removals are O(1) tombstones compacted at the next initialize(),
+//     the flat arrays live in page-locked memory (the engine's H2D copies are plain DMA) and the edge pass is split over a few
+//     host threads; the pointer -> chi2 map the reference rebuilds in every optimize() (cpp:541-542) is built on the first
+//     chiSquared() call instead.
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
+
+#include <cuda_runtime.h>
 
 #include "../../include/cuba_b200.h"
 #include "../../include/cuda_bundle_adjustment.h"
@@ -23,6 +37,40 @@ namespace cuba
 
 namespace
 {
+
+// grow-only host array in page-locked memory (pageable when no CUDA device is usable: initialize() itself needs no GPU)
+template <typename T>
+class HostBuf
+{
+public:
+	HostBuf() {}
+	HostBuf(const HostBuf&) = delete;
+	HostBuf& operator=(const HostBuf&) = delete;
+	~HostBuf() { release(); }
+	void resize(size_t n)
+	{
+		if (n > cap_) {
+			release();
+			cap_ = n + n / 8 + 16;
+			void* q = nullptr;
+			if (cudaMallocHost(&q, cap_ * sizeof(T)) == cudaSuccess) { p_ = static_cast<T*>(q); pinned_ = true; }
+			else { cudaGetLastError(); p_ = static_cast<T*>(std::malloc(cap_ * sizeof(T))); pinned_ = false; if (!p_) throw std::bad_alloc(); }
+		}
+		n_ = n;
+	}
+	T* data() { return p_; }
+	const T* data() const { return p_; }
+	size_t size() const { return n_; }
+	T& operator[](size_t i) { return p_[i]; }
+	const T& operator[](size_t i) const { return p_[i]; }
+private:
+	void release()
+	{
+		if (p_) { if (pinned_) cudaFreeHost(p_); else std::free(p_); }
+		p_ = nullptr; cap_ = 0; n_ = 0;
+	}
+	T* p_ = nullptr; size_t n_ = 0, cap_ = 0; bool pinned_ = false;
+};
 
 class Impl : public CudaBundleAdjustment
 {
@@ -34,19 +82,19 @@ public:
 	}
 	~Impl() override { if (engine_) cuba_engine_destroy(engine_); }
 
-	void addPoseVertex(PoseVertex* v) override { poses_.insert({ v->id, v }); }
-	void addLandmarkVertex(LandmarkVertex* v) override { landmarks_.insert({ v->id, v }); }
+	void addPoseVertex(PoseVertex* v) override { if (poses_.insert({ v->id, v }).second) orderDirty_ = true; }
+	void addLandmarkVertex(LandmarkVertex* v) override { if (landmarks_.insert({ v->id, v }).second) orderDirty_ = true; }
 
 	void addMonocularEdge(MonoEdge* e) override
 	{
-		if (monoPos_.count(e)) return;
-		monoPos_[e] = mono_.size(); mono_.push_back(e);
+		if (!member_.insert(e).second) return;
+		mono_.push_back(e);
 		e->vertexP->edges.insert(e); e->vertexL->edges.insert(e);
 	}
 	void addStereoEdge(StereoEdge* e) override
 	{
-		if (stereoPos_.count(e)) return;
-		stereoPos_[e] = stereo_.size(); stereo_.push_back(e);
+		if (!member_.insert(e).second) return;
+		stereo_.push_back(e);
 		e->vertexP->edges.insert(e); e->vertexL->edges.insert(e);
 	}
 
@@ -60,6 +108,7 @@ public:
 		const std::vector<BaseEdge*> es(it->second->edges.begin(), it->second->edges.end());
 		for (auto e : es) removeEdge(e);
 		poses_.erase(it);
+		orderDirty_ = true;
 	}
 	void removeLandmarkVertex(LandmarkVertex* v) override
 	{
@@ -68,18 +117,21 @@ public:
 		const std::vector<BaseEdge*> es(it->second->edges.begin(), it->second->edges.end());
 		for (auto e : es) removeEdge(e);
 		landmarks_.erase(it);
+		orderDirty_ = true;
 	}
+	// O(1): the slot in the insertion-ordered list becomes a tombstone, dropped by the next initialize()
 	void removeEdge(BaseEdge* e) override
 	{
 		if (auto p = e->poseVertex()) p->edges.erase(e);
 		if (auto l = e->landmarkVertex()) l->edges.erase(e);
-		if (e->dim() == 2) eraseFrom(mono_, monoPos_, static_cast<MonoEdge*>(e));
-		if (e->dim() == 3) eraseFrom(stereo_, stereoPos_, static_cast<StereoEdge*>(e));
+		if (!member_.erase(e)) return;
+		tombstones_[e]++;
+		(e->dim() == 2 ? deadMono_ : deadStereo_)++;
 	}
 
 	size_t nposes() const override { return poses_.size(); }
 	size_t nlandmarks() const override { return landmarks_.size(); }
-	size_t nedges() const override { return mono_.size() + stereo_.size(); }
+	size_t nedges() const override { return mono_.size() + stereo_.size() - deadMono_ - deadStereo_; }
 
 	void setRobustKernels(RobustKernelType kernelType, double delta, EdgeType edgeType) override
 	{
@@ -89,21 +141,26 @@ public:
 	void initialize() override
 	{
 		const auto t0 = std::chrono::steady_clock::now();
-		vP_.clear(); vL_.clear(); activeMono_.clear(); activeStereo_.clear();
-		std::vector<PoseVertex*> fixedP; std::vector<LandmarkVertex*> fixedL;
-		for (const auto& kv : poses_) {
-			PoseVertex* v = kv.second;
-			if (v->edges.empty()) continue;
-			if (!v->fixed) { v->iP = static_cast<int>(vP_.size()); vP_.push_back(v); } else fixedP.push_back(v);
+		compactEdges();
+		if (orderDirty_) {
+			orderP_.clear(); orderL_.clear();
+			orderP_.reserve(poses_.size()); orderL_.reserve(landmarks_.size());
+			for (const auto& kv : poses_) orderP_.push_back(kv.second);
+			for (const auto& kv : landmarks_) orderL_.push_back(kv.second);
+			std::sort(orderP_.begin(), orderP_.end(), [](const PoseVertex* a, const PoseVertex* b) { return a->id < b->id; });
+			std::sort(orderL_.begin(), orderL_.end(), [](const LandmarkVertex* a, const LandmarkVertex* b) { return a->id < b->id; });
+			orderDirty_ = false;
 		}
-		for (const auto& kv : landmarks_) {
-			LandmarkVertex* v = kv.second;
-			if (v->edges.empty()) continue;
-			if (!v->fixed) { v->iL = static_cast<int>(vL_.size()); vL_.push_back(v); } else fixedL.push_back(v);
-		}
-		numP_ = static_cast<int>(vP_.size()); numL_ = static_cast<int>(vL_.size());
-		for (auto v : fixedP) { v->iP = static_cast<int>(vP_.size()); vP_.push_back(v); }
-		for (auto v : fixedL) { v->iL = static_cast<int>(vL_.size()); vL_.push_back(v); }
+		// index assignment: ascending id, free vertices first, fixed ones appended, vertices without edges skipped
+		vP_.clear(); vL_.clear();
+		vP_.reserve(orderP_.size()); vL_.reserve(orderL_.size());
+		size_t nFixedP = 0, nFixedL = 0;
+		for (PoseVertex* v : orderP_) { if (v->edges.empty()) continue; if (v->fixed) nFixedP++; else { v->iP = static_cast<int>(vP_.size()); vP_.push_back(v); } }
+		numP_ = static_cast<int>(vP_.size());
+		if (nFixedP) for (PoseVertex* v : orderP_) if (v->fixed && !v->edges.empty()) { v->iP = static_cast<int>(vP_.size()); vP_.push_back(v); }
+		for (LandmarkVertex* v : orderL_) { if (v->edges.empty()) continue; if (v->fixed) nFixedL++; else { v->iL = static_cast<int>(vL_.size()); vL_.push_back(v); } }
+		numL_ = static_cast<int>(vL_.size());
+		if (nFixedL) for (LandmarkVertex* v : orderL_) if (v->fixed && !v->edges.empty()) { v->iL = static_cast<int>(vL_.size()); vL_.push_back(v); }
 
 		q_.resize(4 * vP_.size()); t_.resize(3 * vP_.size()); cam_.resize(5 * vP_.size()); Xw_.resize(3 * vL_.size());
 		for (size_t i = 0; i < vP_.size(); i++) {
@@ -115,21 +172,70 @@ public:
 		}
 		for (size_t i = 0; i < vL_.size(); i++) for (int k = 0; k < 3; k++) Xw_[3 * i + k] = vL_[i]->Xw.data()[k];
 
-		idx2_.clear(); meas2_.clear(); om2_.clear(); idx3_.clear(); meas3_.clear(); om3_.clear();
-		for (auto e : mono_) {
-			if (e->vertexP->fixed && e->vertexL->fixed) continue;
-			activeMono_.push_back(e);
-			idx2_.push_back(e->vertexP->iP); idx2_.push_back(e->vertexL->iL);
-			meas2_.push_back(e->measurement.data()[0]); meas2_.push_back(e->measurement.data()[1]);
-			om2_.push_back(e->information);
+		// edges: every list entry is written at its own position by a few threads; only if an edge with both ends fixed
+		// turned up (they are dropped, cpp:210-211) the arrays are closed up afterwards
+		idx2_.resize(2 * mono_.size()); meas2_.resize(2 * mono_.size()); om2_.resize(mono_.size());
+		idx3_.resize(2 * stereo_.size()); meas3_.resize(3 * stereo_.size()); om3_.resize(stereo_.size());
+		auto am = std::make_shared<std::vector<const BaseEdge*>>(mono_.size());
+		auto as = std::make_shared<std::vector<const BaseEdge*>>(stereo_.size());
+		const size_t n2 = mono_.size(), n3 = stereo_.size(), total = n2 + n3;
+		unsigned nthreads = static_cast<unsigned>(std::min<size_t>(8, total / 65536 + 1));
+		nthreads = std::max(1u, std::min(nthreads, std::max(1u, std::thread::hardware_concurrency())));
+		std::vector<size_t> dropped(nthreads, 0);
+		auto work = [&](unsigned tix) {
+			const size_t b = total * tix / nthreads, e = total * (tix + 1) / nthreads;
+			size_t drop = 0;
+			for (size_t k = b; k < e; k++) {
+				if (k < n2) {
+					const MonoEdge* ed = mono_[k];
+					const PoseVertex* vp = ed->vertexP; const LandmarkVertex* vl = ed->vertexL;
+					if (vp->fixed && vl->fixed) drop++;
+					(*am)[k] = ed;
+					idx2_[2 * k] = vp->iP; idx2_[2 * k + 1] = vl->iL;
+					meas2_[2 * k] = ed->measurement.data()[0]; meas2_[2 * k + 1] = ed->measurement.data()[1];
+					om2_[k] = ed->information;
+				} else {
+					const size_t j = k - n2;
+					const StereoEdge* ed = stereo_[j];
+					const PoseVertex* vp = ed->vertexP; const LandmarkVertex* vl = ed->vertexL;
+					if (vp->fixed && vl->fixed) drop++;
+					(*as)[j] = ed;
+					idx3_[2 * j] = vp->iP; idx3_[2 * j + 1] = vl->iL;
+					for (int c = 0; c < 3; c++) meas3_[3 * j + c] = ed->measurement.data()[c];
+					om3_[j] = ed->information;
+				}
+			}
+			dropped[tix] = drop;
+		};
+		if (nthreads == 1) work(0);
+		else {
+			std::vector<std::thread> pool;
+			for (unsigned tix = 1; tix < nthreads; tix++) pool.emplace_back(work, tix);
+			work(0);
+			for (auto& th : pool) th.join();
 		}
-		for (auto e : stereo_) {
-			if (e->vertexP->fixed && e->vertexL->fixed) continue;
-			activeStereo_.push_back(e);
-			idx3_.push_back(e->vertexP->iP); idx3_.push_back(e->vertexL->iL);
-			for (int k = 0; k < 3; k++) meas3_.push_back(e->measurement.data()[k]);
-			om3_.push_back(e->information);
+		size_t ndrop = 0;
+		for (size_t d : dropped) ndrop += d;
+		if (ndrop) {
+			size_t w = 0;
+			for (size_t k = 0; k < n2; k++) {
+				const MonoEdge* ed = mono_[k];
+				if (ed->vertexP->fixed && ed->vertexL->fixed) continue;
+				(*am)[w] = ed; idx2_[2 * w] = idx2_[2 * k]; idx2_[2 * w + 1] = idx2_[2 * k + 1];
+				meas2_[2 * w] = meas2_[2 * k]; meas2_[2 * w + 1] = meas2_[2 * k + 1]; om2_[w] = om2_[k]; w++;
+			}
+			am->resize(w); idx2_.resize(2 * w); meas2_.resize(2 * w); om2_.resize(w);
+			w = 0;
+			for (size_t j = 0; j < n3; j++) {
+				const StereoEdge* ed = stereo_[j];
+				if (ed->vertexP->fixed && ed->vertexL->fixed) continue;
+				(*as)[w] = ed; idx3_[2 * w] = idx3_[2 * j]; idx3_[2 * w + 1] = idx3_[2 * j + 1];
+				for (int c = 0; c < 3; c++) meas3_[3 * w + c] = meas3_[3 * j + c];
+				om3_[w] = om3_[j]; w++;
+			}
+			as->resize(w); idx3_.resize(2 * w); meas3_.resize(3 * w); om3_.resize(w);
 		}
+		activeMono_ = am; activeStereo_ = as;
 		stats_.clear();
 		uploaded_ = false;
 		initSeconds_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -166,12 +272,11 @@ public:
 		}
 		for (size_t i = 0; i < vL_.size(); i++) for (int k = 0; k < 3; k++) vL_[i]->Xw.data()[k] = Xw_[3 * i + k];
 
-		// getChiSqs()
-		chi_.assign(om2_.size() + om3_.size(), 0.0);
-		if (!chi_.empty()) check(cuba_engine_get_chi2(engine_, chi_.data()));
-		chiOf_.clear();
-		for (size_t i = 0; i < activeMono_.size(); i++) chiOf_[activeMono_[i]] = chi_[i];
-		for (size_t i = 0; i < activeStereo_.size(); i++) chiOf_[activeStereo_[i]] = chi_[activeMono_.size() + i];
+		// getChiSqs(): the values now, the pointer -> value map when somebody asks (chiSquared)
+		chi_.resize(om2_.size() + om3_.size());
+		if (chi_.size()) check(cuba_engine_get_chi2(engine_, chi_.data()));
+		chiMono_ = activeMono_; chiStereo_ = activeStereo_;
+		chiIndexValid_ = false;
 
 		double sec[CUBA_PROF_NUM] = { 0 };
 		check(cuba_engine_get_profile(engine_, sec));
@@ -184,7 +289,8 @@ public:
 
 	void clear() override
 	{
-		poses_.clear(); landmarks_.clear(); mono_.clear(); stereo_.clear(); monoPos_.clear(); stereoPos_.clear();
+		poses_.clear(); landmarks_.clear(); mono_.clear(); stereo_.clear(); member_.clear(); tombstones_.clear();
+		deadMono_ = deadStereo_ = 0; orderDirty_ = true;
 		stats_.clear(); initialized_ = false; uploaded_ = false;
 	}
 
@@ -192,22 +298,37 @@ public:
 	const TimeProfile& timeProfile() const override { return profile_; }
 	double chiSquared(const BaseEdge* e) const override
 	{
-		auto it = chiOf_.find(e);
-		return it == chiOf_.end() ? 0.0 : it->second;
+		if (!chiIndexValid_) {
+			chiIndex_.clear();
+			const size_t n2 = chiMono_ ? chiMono_->size() : 0, n3 = chiStereo_ ? chiStereo_->size() : 0;
+			chiIndex_.reserve(n2 + n3);
+			for (size_t i = 0; i < n2; i++) chiIndex_[(*chiMono_)[i]] = i;
+			for (size_t i = 0; i < n3; i++) chiIndex_[(*chiStereo_)[i]] = n2 + i;
+			chiIndexValid_ = true;
+		}
+		auto it = chiIndex_.find(e);
+		return it == chiIndex_.end() || it->second >= chi_.size() ? 0.0 : chi_[it->second];
 	}
 
 private:
 	struct Kernel { int type; double delta; };
 
-	template <class E>
-	static void eraseFrom(std::vector<E*>& vec, std::unordered_map<const E*, size_t>& pos, E* e)
+	// drops the tombstoned slots (earliest occurrences first: an edge removed and added again keeps its new position)
+	void compactEdges()
 	{
-		auto it = pos.find(e);
-		if (it == pos.end()) return;
-		const size_t i = it->second;
-		pos.erase(it);
-		vec.erase(vec.begin() + i);               // keeps insertion order
-		for (size_t k = i; k < vec.size(); k++) pos[vec[k]] = k;
+		if (tombstones_.empty()) return;
+		auto sweep = [this](auto& vec) {
+			size_t w = 0;
+			for (size_t k = 0; k < vec.size(); k++) {
+				auto it = tombstones_.find(vec[k]);
+				if (it != tombstones_.end()) { if (--it->second == 0) tombstones_.erase(it); continue; }
+				vec[w++] = vec[k];
+			}
+			vec.resize(w);
+		};
+		sweep(mono_); sweep(stereo_);
+		tombstones_.clear();
+		deadMono_ = deadStereo_ = 0;
 	}
 
 	void ensureEngine()
@@ -226,28 +347,32 @@ private:
 		if (rc != CUBA_OK) throw std::runtime_error(std::string("cuba_b200: ") + cuba_last_error());
 	}
 
-	std::map<int, PoseVertex*> poses_;
-	std::map<int, LandmarkVertex*> landmarks_;
-	std::vector<MonoEdge*> mono_;
+	std::unordered_map<int, PoseVertex*> poses_;
+	std::unordered_map<int, LandmarkVertex*> landmarks_;
+	std::vector<PoseVertex*> orderP_;          // ascending id, valid while !orderDirty_
+	std::vector<LandmarkVertex*> orderL_;
+	bool orderDirty_ = true;
+	std::vector<MonoEdge*> mono_;              // insertion order, may hold tombstoned slots until the next initialize()
 	std::vector<StereoEdge*> stereo_;
-	std::unordered_map<const MonoEdge*, size_t> monoPos_;
-	std::unordered_map<const StereoEdge*, size_t> stereoPos_;
+	std::unordered_set<const BaseEdge*> member_;
+	std::unordered_map<const BaseEdge*, int> tombstones_;
+	size_t deadMono_ = 0, deadStereo_ = 0;
 	Kernel kernels_[2];
 
 	std::vector<PoseVertex*> vP_;
 	std::vector<LandmarkVertex*> vL_;
-	std::vector<MonoEdge*> activeMono_;
-	std::vector<StereoEdge*> activeStereo_;
+	std::shared_ptr<const std::vector<const BaseEdge*>> activeMono_, activeStereo_, chiMono_, chiStereo_;
 	int numP_ = 0, numL_ = 0;
-	std::vector<double> q_, t_, cam_, Xw_, meas2_, om2_, meas3_, om3_, chi_;
-	std::vector<int32_t> idx2_, idx3_;
+	HostBuf<double> q_, t_, cam_, Xw_, meas2_, om2_, meas3_, om3_, chi_;
+	HostBuf<int32_t> idx2_, idx3_;
 	bool initialized_ = false, uploaded_ = false;
 	double initSeconds_ = 0;
 
 	cuba_engine* engine_ = nullptr;
 	BatchStatistics stats_;
 	TimeProfile profile_;
-	std::unordered_map<const BaseEdge*, double> chiOf_;
+	mutable std::unordered_map<const BaseEdge*, size_t> chiIndex_;
+	mutable bool chiIndexValid_ = false;
 };
 
 } // namespace

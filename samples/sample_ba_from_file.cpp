@@ -17,81 +17,21 @@
 
 #include <cuda_bundle_adjustment.h>
 
-struct Storage {
-	std::vector<std::unique_ptr<cuba::PoseVertex>> poses;
-	std::vector<std::unique_ptr<cuba::LandmarkVertex>> landmarks;
-	std::vector<std::unique_ptr<cuba::MonoEdge>> mono;
-	std::vector<std::unique_ptr<cuba::StereoEdge>> stereo;
-};
-
-template <typename T>
-static std::vector<T> readArray(FILE* f, size_t n)
-{
-	std::vector<T> v(n);
-	if (n && fread(v.data(), sizeof(T), n, f) != n) { fprintf(stderr, "short read\n"); exit(2); }
-	return v;
-}
-
-static cuba::CudaBundleAdjustment::Ptr readGraph(const std::string& path, Storage& st)
-{
-	FILE* f = fopen(path.c_str(), "rb");
-	if (!f) { fprintf(stderr, "cannot open %s\n", path.c_str()); exit(2); }
-	char magic[8];
-	if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "CUBAGRF1", 8) != 0) { fprintf(stderr, "bad magic\n"); exit(2); }
-	const auto n = readArray<int64_t>(f, 4);
-	const size_t nP = n[0], nL = n[1], nM = n[2], nS = n[3];
-	const auto pid = readArray<int32_t>(f, nP), pfix = readArray<int32_t>(f, nP);
-	const auto q = readArray<double>(f, 4 * nP), t = readArray<double>(f, 3 * nP), cam = readArray<double>(f, 5 * nP);
-	const auto lid = readArray<int32_t>(f, nL), lfix = readArray<int32_t>(f, nL);
-	const auto Xw = readArray<double>(f, 3 * nL);
-	const auto mP = readArray<int32_t>(f, nM), mL = readArray<int32_t>(f, nM);
-	const auto mMeas = readArray<double>(f, 2 * nM), mInfo = readArray<double>(f, nM);
-	const auto sP = readArray<int32_t>(f, nS), sL = readArray<int32_t>(f, nS);
-	const auto sMeas = readArray<double>(f, 3 * nS), sInfo = readArray<double>(f, nS);
-	fclose(f);
-
-	auto optimizer = cuba::CudaBundleAdjustment::create();
-	for (size_t i = 0; i < nP; i++) {
-		cuba::CameraParams c;
-		c.fx = cam[5 * i]; c.fy = cam[5 * i + 1]; c.cx = cam[5 * i + 2]; c.cy = cam[5 * i + 3]; c.bf = cam[5 * i + 4];
-		cuba::PoseVertex::Quaternion qq;
-		for (int k = 0; k < 4; k++) qq.coeffs().data()[k] = q[4 * i + k];
-		cuba::PoseVertex::Translation tt;
-		for (int k = 0; k < 3; k++) tt.data()[k] = t[3 * i + k];
-		st.poses.emplace_back(new cuba::PoseVertex(pid[i], qq, tt, c, pfix[i] != 0));
-		optimizer->addPoseVertex(st.poses.back().get());
-	}
-	for (size_t i = 0; i < nL; i++) {
-		cuba::LandmarkVertex::Point3D X;
-		for (int k = 0; k < 3; k++) X.data()[k] = Xw[3 * i + k];
-		st.landmarks.emplace_back(new cuba::LandmarkVertex(lid[i], X, lfix[i] != 0));
-		optimizer->addLandmarkVertex(st.landmarks.back().get());
-	}
-	for (size_t i = 0; i < nM; i++) {
-		cuba::MonoEdge::Measurement m;
-		m.data()[0] = mMeas[2 * i]; m.data()[1] = mMeas[2 * i + 1];
-		st.mono.emplace_back(new cuba::MonoEdge(m, mInfo[i], optimizer->poseVertex(mP[i]), optimizer->landmarkVertex(mL[i])));
-		optimizer->addMonocularEdge(st.mono.back().get());
-	}
-	for (size_t i = 0; i < nS; i++) {
-		cuba::StereoEdge::Measurement m;
-		for (int k = 0; k < 3; k++) m.data()[k] = sMeas[3 * i + k];
-		st.stereo.emplace_back(new cuba::StereoEdge(m, sInfo[i], optimizer->poseVertex(sP[i]), optimizer->landmarkVertex(sL[i])));
-		optimizer->addStereoEdge(st.stereo.back().get());
-	}
-	return optimizer;
-}
+#include "cubagraph_reader.h"
 
 int main(int argc, char** argv)
 {
-	if (argc < 2) { printf("Usage: sample_ba_from_file input.cubagraph [--json] [--huber] [--iters N] [--no-warmup]\n"); return 0; }
+	if (argc < 2) { printf("Usage: sample_ba_from_file input.cubagraph [--json] [--huber] [--iters N] [--no-warmup] [--repeat K] [--dump state.bin]\n"); return 0; }
 	bool json = false, huber = false, warmup = true;
-	int iters = 10;
+	int iters = 10, repeat = 1;
+	const char* dump = nullptr;
 	for (int i = 2; i < argc; i++) {
 		if (!strcmp(argv[i], "--json")) json = true;
 		else if (!strcmp(argv[i], "--huber")) huber = true;
 		else if (!strcmp(argv[i], "--no-warmup")) warmup = false;
 		else if (!strcmp(argv[i], "--iters") && i + 1 < argc) iters = atoi(argv[++i]);
+		else if (!strcmp(argv[i], "--repeat") && i + 1 < argc) repeat = atoi(argv[++i]);     // timed windows (bench.py's e2e_cpp leg)
+		else if (!strcmp(argv[i], "--dump") && i + 1 < argc) dump = argv[++i];               // final q,t,Xw in file order (comparison report)
 	}
 	Storage st;
 	auto optimizer = readGraph(argv[1], st);
@@ -101,14 +41,39 @@ int main(int argc, char** argv)
 	}
 	if (warmup) { optimizer->initialize(); optimizer->optimize(1); }   // writes its result back, like the reference
 
-	const auto t0 = std::chrono::steady_clock::now();
-	optimizer->initialize();
-	optimizer->optimize(iters);
-	const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	// the timed window of the reference: initialize() + optimize(n) (samples/sample_ba_from_file.cpp:52-57).  With --repeat K the
+	// window is measured K times on the SAME input: the estimate the window starts from is restored (untimed) in between.
+	std::vector<double> q0, t0v, X0, secs;
+	if (repeat > 1) {
+		for (auto& v : st.poses) { for (int k = 0; k < 4; k++) q0.push_back(v->q.coeffs().data()[k]); for (int k = 0; k < 3; k++) t0v.push_back(v->t.data()[k]); }
+		for (auto& v : st.landmarks) for (int k = 0; k < 3; k++) X0.push_back(v->Xw.data()[k]);
+	}
+	double sec = 0;
+	for (int rep = 0; rep < repeat; rep++) {
+		if (rep > 0) {
+			for (size_t i = 0; i < st.poses.size(); i++) { for (int k = 0; k < 4; k++) st.poses[i]->q.coeffs().data()[k] = q0[4 * i + k]; for (int k = 0; k < 3; k++) st.poses[i]->t.data()[k] = t0v[3 * i + k]; }
+			for (size_t i = 0; i < st.landmarks.size(); i++) for (int k = 0; k < 3; k++) st.landmarks[i]->Xw.data()[k] = X0[3 * i + k];
+		}
+		const auto t0 = std::chrono::steady_clock::now();
+		optimizer->initialize();
+		optimizer->optimize(iters);
+		sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		secs.push_back(sec);
+	}
+	if (dump) {
+		FILE* f = fopen(dump, "wb");
+		if (!f) { fprintf(stderr, "cannot write %s\n", dump); return 2; }
+		for (auto& v : st.poses) fwrite(v->q.coeffs().data(), sizeof(double), 4, f);
+		for (auto& v : st.poses) fwrite(v->t.data(), sizeof(double), 3, f);
+		for (auto& v : st.landmarks) fwrite(v->Xw.data(), sizeof(double), 3, f);
+		fclose(f);
+	}
 
 	if (json) {
-		printf("{\"nposes\": %zu, \"nlandmarks\": %zu, \"nedges\": %zu, \"seconds\": %.6f, \"chi2\": [",
+		printf("{\"nposes\": %zu, \"nlandmarks\": %zu, \"nedges\": %zu, \"seconds\": %.6f, \"seconds_all\": [",
 			optimizer->nposes(), optimizer->nlandmarks(), optimizer->nedges(), sec);
+		for (size_t i = 0; i < secs.size(); i++) printf("%s%.6f", i ? ", " : "", secs[i]);
+		printf("], \"chi2\": [");
 		const auto& s = optimizer->batchStatistics();
 		for (size_t i = 0; i < s.size(); i++) printf("%s%.17g", i ? ", " : "", s[i].chi2);
 		double chiSum = 0;

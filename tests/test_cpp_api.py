@@ -49,3 +49,23 @@ def test_cpp_api_matches_oracle(tmp_path_factory, pkg, oracle):
     last_row = int(np.nonzero(prob.pose_rows == len(g["pose_id"]) - 1)[0][0])
     assert np.allclose(res["t_last"], ot[last_row], rtol=1e-9, atol=1e-12)
     assert set(res["profile"]) == set(pkg.PROFILE_ITEMS)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,kernel", [("small", "huber"), ("ba_kitti_07", "none")])
+def test_comparison_report(pkg, name, kernel, capsys):
+    """tests/compare_with_reference.py = the reference's sample_comparison_with_g2o.cpp:62-136 printout (chi2 columns side by
+    side, RMSE of q/t/Xw) with the CPU oracle and the compiled reference GPU build beside this engine's drop-in class"""
+    import io
+    from conftest import have_fixture
+    import compare_with_reference as cmp
+    if name.startswith("ba_") and not have_fixture(name):
+        pytest.skip("fixture not extracted")
+    buf = io.StringIO()
+    r = cmp.compare(name, kernel, with_cpu=True, out=buf)
+    text = buf.getvalue()
+    assert "=== Objective function value" in text and "=== RMSE between" in text
+    assert r["chi2_rel_cpu"] < 1e-10 and max(r["rmse_cpu"].values()) < 1e-8
+    if "chi2_rel_ref" in r:
+        assert r["chi2_rel_ref"] < 1e-10 and max(r["rmse_ref"].values()) < 1e-8
+    print(text)
