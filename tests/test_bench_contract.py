@@ -29,6 +29,13 @@ def test_jh_algorithmic_bytes_match_the_survey():
     assert stage - kernel == 1321 * 42 * 8
 
 
+def test_schur_algorithmic_bytes_match_the_survey():
+    """B_S = nHpl 18s + L 12s + L 9s + nblk 36s + P 48s, ba_kitti_00 fp64 ~ 115.5 MB"""
+    b = _bench()
+    k00 = dict(nhpl=560658, numL=133383, nblk=41307, numP=1321)
+    assert b.schur_bytes(k00, 8) == 560658 * 144 + 133383 * 168 + 41307 * 288 + 1321 * 384 == 115546776
+
+
 def test_bench_refuses_to_run_without_a_gpu():
     """no CPU fallback: on a box without a CUDA device the engine arm exits with an error instead of measuring something else"""
     import torch
