@@ -1269,7 +1269,7 @@ struct Engine : EngineBase {
 	DBuf<unsigned long long> p5Boards;
 	void* p5PeerBase[PCG5_MAXWORLD] = { nullptr };   // cudaIpc mappings of the peers' boards (own entry: the local allocation)
 	void* p5MappedFor = nullptr;                   // local allocation the mappings were exchanged for
-	size_t p5WWords = 0, p5PWords = 0, p5RWords = 0;
+	size_t p5WWords = 0, p5PWords = 0, p5RWords = 0, p5CWords = 0;
 	Pcg5Dims p5Dims{}, p5DimsBJ{};
 	size_t p5Smem = 0;
 	int p5G = 0, p5W = 1, p5A = 0, p5Gs = 1;
@@ -1278,7 +1278,7 @@ struct Engine : EngineBase {
 	size_t p5InvSmem = 0;
 	long long p5TagBound = 0;                      // conservative host-side bound on the device tag base
 
-	Pcg5Ctl* p5Ctl(void* base) const { return (Pcg5Ctl*)((unsigned long long*)base + 2 * (p5WWords + p5PWords + p5RWords)); }
+	Pcg5Ctl* p5Ctl(void* base) const { return (Pcg5Ctl*)((unsigned long long*)base + 2 * (p5WWords + p5PWords + p5RWords + p5CWords)); }
 
 	void p5CloseMappings()
 	{
@@ -1364,30 +1364,30 @@ struct Engine : EngineBase {
 		const int Aloc = G / gs, NR = 3 + 6 * Aloc, nc = 6 * A;
 		Pcg5Dims d{};
 		d.needMax = PP.needMax; d.maxRows = PP.maxRows; d.nc = nc; d.maxNeedAgg = CP.maxNeedAgg;
-		d.npv = std::max(G * 9, W * NR); d.nls = NR;
+		d.npv = std::max(std::max(G * 9, W * NR), 6 * CP.maxNeedAgg); d.nls = NR;
+		d.sliceRows = (nc + G - 1) / G;
 		const size_t per = 36 * sizeof(T) + 4;
 		const size_t wantCache = PP.blkMax > PCG5_REGBLK ? (size_t)(PP.blkMax - PCG5_REGBLK) : 0;
 		{
-			d.capBlocks = 0; d.zhInSmem = 0; d.sliceInSmem = 0;
+			d.capBlocks = 0; d.zhInSmem = 0;
 			const size_t base = Pcg5Layout<T>(d).total + 64;
 			if (base > budget) return CUBA_OK;
-			const size_t zhBytes = (size_t)d.needMax * 36 * sizeof(T), slBytes = (size_t)d.maxNeedAgg * 6 * nc * sizeof(float);
+			const size_t zhBytes = (size_t)d.needMax * 36 * sizeof(T);
 			size_t used = base + wantCache * per;
 			if (used + zhBytes <= budget) { d.zhInSmem = 1; used += zhBytes; }
-			if (used + slBytes <= budget) { d.sliceInSmem = 1; used += slBytes; }
 			const size_t fixed = used - wantCache * per;
 			d.capBlocks = (int)std::min(wantCache, (budget - fixed) / per);
 		}
 		p5Dims = d;
-		p5DimsBJ = d; p5DimsBJ.nc = 0; p5DimsBJ.maxNeedAgg = 0; p5DimsBJ.zhInSmem = 0; p5DimsBJ.sliceInSmem = 0; p5DimsBJ.nls = 3; p5DimsBJ.npv = std::max(G * 3, W * 3);
+		p5DimsBJ = d; p5DimsBJ.nc = 0; p5DimsBJ.maxNeedAgg = 0; p5DimsBJ.zhInSmem = 0; p5DimsBJ.sliceRows = 0; p5DimsBJ.nls = 3; p5DimsBJ.npv = std::max(G * 3, W * 3);
 		p5Smem = std::max(Pcg5Layout<T>(p5Dims).total, Pcg5Layout<T>(p5DimsBJ).total);
 		if (p5Smem > (size_t)smemMax - 1024) return CUBA_OK;
 		CUDA_TRY(cudaFuncSetAttribute(k_pcg5<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p5Smem));
 		int perSM = 0;
 		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_pcg5<T>, PCG5_BLOCK, p5Smem));
 		if (perSM < 1) return CUBA_OK;
-		if (getenv("CUBA_PCG_VERBOSE")) fprintf(stderr, "pcg5: world %d G %d gs %d A %d needMax %d maxRows %d blkMax %d maxNeedAgg %d zhInSmem %d sliceInSmem %d cap %d smem %zu\n",
-			W, G, gs, A, d.needMax, d.maxRows, PP.blkMax, d.maxNeedAgg, d.zhInSmem, d.sliceInSmem, d.capBlocks, p5Smem);
+		if (getenv("CUBA_PCG_VERBOSE")) fprintf(stderr, "pcg5: world %d G %d gs %d A %d needMax %d maxRows %d blkMax %d maxNeedAgg %d zhInSmem %d sliceRows %d cap %d smem %zu\n",
+			W, G, gs, A, d.needMax, d.maxRows, PP.blkMax, d.maxNeedAgg, d.zhInSmem, d.sliceRows, d.capBlocks, p5Smem);
 		// coarse inverse: packed block triangle in the shared memory of one CTA (A <= 37) or of an 8-CTA cluster
 		p5Cluster = A > PCG4_MAXAGG1;
 		const size_t nblkPz = (size_t)A * (A + 1) / 2;
@@ -1406,15 +1406,15 @@ struct Engine : EngineBase {
 		CUDA_TRY(fHat.alloc(36 * (size_t)S.nfull));
 		CUDA_TRY(p5AcP.alloc(nblkPz * 36)); CUDA_TRY(p5AcInv.alloc((size_t)nc * nc)); CUDA_TRY(p5Lp.alloc(nblkPz * 36)); CUDA_TRY(p5Wp.alloc(nblkPz * 36)); CUDA_TRY(p5Ld.alloc((size_t)A * 36));
 		// boards (16-byte words): [2 solve halves][2 pass parities] of w, of the per-CTA partials and of the rank summaries, then the control block
-		const size_t wW = 4 * 6 * nP, pW = 4 * (size_t)PCG5_REPL * G * 9, rW = 4 * (size_t)PCG5_REPL * W * NR;
-		const size_t words2 = 2 * (wW + pW + rW) + (sizeof(Pcg5Ctl) + 7) / 8 + 2;
-		const bool fresh = !p5Boards.p || words2 > p5Boards.cap || wW != p5WWords || pW != p5PWords || rW != p5RWords;
+		const size_t wW = 4 * 6 * nP, pW = 4 * (size_t)PCG5_REPL * G * 9, rW = 4 * (size_t)PCG5_REPL * W * NR, cW = 4 * (size_t)PCG5_REPL * nc;
+		const size_t words2 = 2 * (wW + pW + rW + cW) + (sizeof(Pcg5Ctl) + 7) / 8 + 2;
+		const bool fresh = !p5Boards.p || words2 > p5Boards.cap || wW != p5WWords || pW != p5PWords || rW != p5RWords || cW != p5CWords;
 		if (fresh) {
 			// the tag protocol needs boards that start out as zeros; a layout change invalidates every mapping and every tag
 			if (p5MappedFor) { CUDA_TRY(cudaStreamSynchronize(stream)); p5CloseMappings(); }
 			CUDA_TRY(p5Boards.alloc(std::max(words2, (size_t)(1u << 18))));
 			CUDA_TRY(cudaMemsetAsync(p5Boards.p, 0, sizeof(unsigned long long) * p5Boards.cap, stream));
-			p5WWords = wW; p5PWords = pW; p5RWords = rW;
+			p5WWords = wW; p5PWords = pW; p5RWords = rW; p5CWords = cW;
 			p5TagBound = 0;
 		}
 		p5G = G; p5W = W; p5A = A; p5Gs = gs;
@@ -1500,6 +1500,7 @@ struct Engine : EngineBase {
 			a.peerW[r] = base; a.peerR[r] = base + 2 * (p5WWords + p5PWords); a.peerCtl[r] = p5Ctl(base);
 		}
 		a.wBoard = p5Boards.p; a.pBoard = p5Boards.p + 2 * p5WWords; a.rBoard = p5Boards.p + 2 * (p5WWords + p5PWords);
+		a.cBoard = p5Boards.p + 2 * (p5WWords + p5PWords + p5RWords);
 		a.rowPeers = p5RowPeers; a.ctl = p5Ctl(p5Boards.p);
 		a.timing = nullptr;
 #ifdef CUBA_PCG_TIMING

@@ -15,6 +15,13 @@
 //                       peer (one NVLink hop), everybody adds the summaries in rank order -> bit-identical scalars on all GPUs,
 //                       hence identical iteration counts and exit passes without any host involvement.
 //                   No NCCL call inside the solve.  world == 1 skips the rank hop.
+//   coarse level  = c = (Z^T S Z)^-1 rc is computed ONCE per GPU and pass: every CTA holds the whole coarse residual rc (advanced by
+//                   the CG recurrences from the published Z^^T w), multiplies it with ITS few rows of the explicit inverse (shared
+//                   memory, fp32) and publishes the result on a third LL board; consumers poll the six entries of each aggregate
+//                   their columns belong to.  One more L2 hop per pass, but the work is balanced: with k_pcg4's scheme (every CTA
+//                   multiplies the rows of all its needed aggregates itself) the CTAs next to loop closures of the real ba_kitti_00
+//                   needed 18 aggregates = 108 rows x 444 columns from L2 per pass and everybody waited for them (22.6 k of 40 k
+//                   cycles per pass, profiles/r02_pcg5_phase_ticks_v1.log).
 //   tags          = tagBase + pass, tagBase advanced by every solve (device-resident Pcg5Ctl): boards are never cleared;
 //                   boards are double-buffered by pass parity and by solve parity (a peer may start the next solve while a
 //                   slow CTA here still reads the last pass of this one).
@@ -38,7 +45,8 @@ constexpr int PCG5_TPR = 16;                       // threads per row of the coa
 struct Pcg5Ctl { unsigned int tagBase; unsigned int solve; int abort; int nbad; unsigned int advance; int pad[3]; };
 
 struct Pcg5Dims {
-	int capBlocks, needMax, maxRows, nc, maxNeedAgg, zhInSmem, sliceInSmem;
+	int capBlocks, needMax, maxRows, nc, maxNeedAgg, zhInSmem;
+	int sliceRows; // rows of the inverse coarse matrix this CTA multiplies: ceil(nc / G)
 	int npv;      // max(G * NP, world * NR): polled partial / summary words
 	int nls;      // NR: words of a rank summary
 };
@@ -64,7 +72,7 @@ struct Pcg5Layout {
 		zh = take(d.zhInSmem ? (size_t)d.needMax * 36 * sizeof(T) : 0, 8);
 		pv = take((size_t)d.npv * sizeof(double), 8);
 		ls = take((size_t)d.nls * sizeof(double), 8);
-		ai = take(d.sliceInSmem ? (size_t)d.maxNeedAgg * 6 * d.nc * sizeof(float) : 0, 8);
+		ai = take((size_t)d.sliceRows * d.nc * sizeof(float), 16);
 		loc = take((size_t)d.capBlocks * sizeof(int), 4);
 		rowPtr = take(((size_t)d.maxRows + 1) * sizeof(int), 4);
 		woff = take((size_t)d.needMax * 6 * sizeof(int), 4);
@@ -99,6 +107,7 @@ struct Pcg5Args {
 	unsigned long long* wBoard;      // ... [6 numP][2]
 	unsigned long long* pBoard;      // ... [REPL][G * NP][2]
 	unsigned long long* rBoard;      // ... [REPL][world * NR][2]
+	unsigned long long* cBoard;      // ... [REPL][nc][2]   coarse correction c = Ac^-1 rc of the current pass
 	unsigned long long* peerW[PCG5_MAXWORLD];   // the same boards of every rank (own entry = local pointer)
 	unsigned long long* peerR[PCG5_MAXWORLD];
 	Pcg5Ctl* peerCtl[PCG5_MAXWORLD];
@@ -244,7 +253,9 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 	const unsigned int tagBase = a.ctl->tagBase, half = a.ctl->solve & 1u;
 	const int nbad = a.ctl->nbad;
 	const size_t wStride = n6, pStride = (size_t)PCG5_REPL * G * NP, rStride = (size_t)PCG5_REPL * world * NR;   // words (16 B) per parity
-	const size_t wHalf = 2 * (size_t)half * wStride, pHalf = 2 * (size_t)half * pStride, rHalf = 2 * (size_t)half * rStride;
+	const size_t cStride = (size_t)PCG5_REPL * nc;
+	const size_t wHalf = 2 * (size_t)half * wStride, pHalf = 2 * (size_t)half * pStride, rHalf = 2 * (size_t)half * rStride, cHalf = 2 * (size_t)half * cStride;
+	const int srow0 = lc * a.dims.sliceRows, srow1 = srow0 + a.dims.sliceRows < nc ? srow0 + a.dims.sliceRows : nc;   // own rows of Ac^-1
 	const int rep = lc % PCG5_REPL;
 
 	if (tid == 0) s_abort = 0;
@@ -267,11 +278,7 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 	if (coarse) {
 		if (a.dims.zhInSmem)
 			for (int wi = tid; wi < nneed * 36; wi += PCG5_BLOCK) s_zh[wi] = __ldcg(a.Zhat + 36 * (size_t)a.needCol[need0 + wi / 36] + (wi % 36));
-		if (a.dims.sliceInSmem)
-			for (int wi = tid; wi < nagg * 6 * nc; wi += PCG5_BLOCK) {
-				const int rowi = wi / nc, q = wi - rowi * nc;
-				s_ai[wi] = __ldg(a.AcInv + (size_t)(s_alist[rowi / 6] * 6 + (rowi % 6)) * nc + q);
-			}
+		for (int wi = tid; wi < (srow1 - srow0) * nc; wi += PCG5_BLOCK) s_ai[wi] = __ldg(a.AcInv + (size_t)srow0 * nc + wi);
 	}
 
 	// ---- A^_ij = L_i^-1 S_ij L_j^-T for the own rows: the first PCG5_REGBLK blocks stay in REGISTERS for the whole solve
@@ -450,24 +457,25 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 			PCG_T(t4);
 			const T* s_v = s_r;                                   // the vector A^ is applied to
 			if (coarse) {
-				// ---- c_a = (Ac^-1 rc)_a for the needed aggregates: PCG5_TPR threads per row, fixed-order butterfly ----
-				for (int rb = 0; rb < nagg * 6; rb += PCG5_BLOCK / PCG5_TPR) {
-					const int rowi = rb + tid / PCG5_TPR, sub = tid % PCG5_TPR;
-					T s = T(0);
-					if (rowi < nagg * 6) {
-						if (a.dims.sliceInSmem) {
-							const float* Arow = s_ai + (size_t)rowi * nc;
-							for (int q = sub; q < nc; q += PCG5_TPR) s += (T)Arow[q] * s_rc[q];
-						} else {
-							const int la = rowi / 6, comp = rowi - 6 * la;
-							const float* Arow = a.AcInv + (size_t)(s_alist[la] * 6 + comp) * nc;
-							for (int q = sub; q < nc; q += PCG5_TPR) s += (T)__ldg(Arow + q) * s_rc[q];
-						}
-					}
-#pragma unroll
-					for (int o = 1; o < PCG5_TPR; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-					if (rowi < nagg * 6 && sub == 0) s_c[rowi] = s;
+				// ---- c = Ac^-1 rc: this CTA's rows (one warp per row, fixed-order butterfly), published for the whole GPU ----
+				const unsigned int ctag = tagBase + (unsigned int)(k + 2);
+				const int cpar = (k + 2) & 1;
+				unsigned long long* cB = a.cBoard + 2 * (cHalf + (size_t)cpar * cStride);
+				for (int rowi = srow0 + wid; rowi < srow1; rowi += PCG5_BLOCK / 32) {
+					const float* Arow = s_ai + (size_t)(rowi - srow0) * nc;
+					T sacc = T(0);
+					for (int q = lane; q < nc; q += 32) sacc += (T)Arow[q] * s_rc[q];
+					sacc = warp_sum(sacc);
+					if (lane < PCG5_REPL) ll_store(cB + 2 * ((size_t)lane * nc + rowi), (double)sacc, ctag);
 				}
+				{
+					const unsigned long long* cR = cB + 2 * ((size_t)rep * nc);
+					const bool ok = ll_poll_many(nagg * 6, [&](int i) { return cR + 2 * (size_t)(s_alist[i / 6] * 6 + (i % 6)); }, s_pv, ctag, a.ctl);
+					if (!ok) s_abort = 1;
+				}
+				__syncthreads();
+				if (s_abort) { status = 3; break; }
+				for (int i = tid; i < nagg * 6; i += PCG5_BLOCK) s_c[i] = (T)s_pv[i];
 				__syncthreads();
 				// ---- u_j = r_j + Z^_j c_a(j) for every needed column ----
 				for (int wi = tid; wi < nneed * 6; wi += PCG5_BLOCK) {

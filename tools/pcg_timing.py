@@ -19,8 +19,10 @@ L = pkg.load_library()
 L.cuba_debug_get_pcg_timing.restype = C.c_int
 L.cuba_debug_get_pcg_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
 VARIANT = int(os.environ.get("PCG_VARIANT", "0"))
-names = ["poll", "sync_after_poll", "scalars", "update+sync", "spmv", "reduce+sync", "publish"] if VARIANT != 3 else \
+names = ["poll", "sync_after_poll", "scalars", "update+sync", "spmv", "reduce+sync", "publish"] if VARIANT not in (3, 5, 6) else \
     ["loads+scalars", "rc+owners+gather", "coarse slices", "u", "spmv+restrict", "reduce+publish", "grid barrier"]
+if VARIANT in (5, 6):   # k_pcg5
+    names = ["poll w + partials", "local sums (+rank hop) + scalars", "advance r,s,p,y,rc", "coarse slices + u", "spmv + row sums", "publish w + warp sums", "publish partials"]
 for workload in sys.argv[1:] or ["kitti00_shaped"]:
     path = os.path.join(ROOT, "oracle", "_ref", "fixtures", workload + ".cubagraph")
     g = pkg.graphio.read_graph(path) if workload.startswith("ba_") else pkg.synth.make_config(workload)
