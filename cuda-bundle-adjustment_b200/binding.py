@@ -51,7 +51,7 @@ _SYMBOLS = [
     "cuba_engine_optimize", "cuba_engine_get_state", "cuba_engine_get_chi2", "cuba_engine_get_profile",
     "cuba_engine_get_launch_count", "cuba_get_transfer_bytes", "cuba_stage_linearize", "cuba_stage_max_diagonal", "cuba_stage_solve", "cuba_stage_update",
     "cuba_stage_commit", "cuba_stage_chi2", "cuba_debug_get_hpl_structure", "cuba_debug_get_hsc_structure",
-    "cuba_debug_get_system", "cuba_debug_get_schur", "cuba_debug_get_delta", "cuba_debug_build_structure_host", "cuba_debug_pcg_partition", "cuba_bench_stage",
+    "cuba_debug_get_system", "cuba_debug_get_schur", "cuba_debug_get_delta", "cuba_debug_build_structure_host", "cuba_debug_pcg_partition", "cuba_debug_pcg5_plan", "cuba_bench_stage",
 ]
 
 
@@ -101,6 +101,7 @@ def load_library():
         "cuba_debug_get_delta": [vp, vp, vp],
         "cuba_debug_build_structure_host": [C.POINTER(_Problem), i, i, C.POINTER(_Sizes), vp, vp, vp, vp, vp, vp, vp, vp],
         "cuba_debug_pcg_partition": [C.POINTER(_Problem), i, i, vp],
+        "cuba_debug_pcg5_plan": [C.POINTER(_Problem), i, i, i, vp],
         "cuba_bench_stage": [vp, i, i, i, d, C.POINTER(d)],
     }
     for name, args in sig.items():
@@ -163,6 +164,16 @@ def pcg_partition_host(prob, n_ctas=148, max_aggregates=74):
     info = np.zeros(8, np.int32)
     _check(L.cuba_debug_pcg_partition(C.byref(P), int(n_ctas), int(max_aggregates), _p(info)))
     return dict(zip(("G", "gs", "A", "needMax", "maxRows", "blkMax", "maxNeedAgg", "coarse_list_size"), (int(v) for v in info)))
+
+
+def pcg5_plan_host(prob, world=1, num_sms=148, max_aggregates=74):
+    """Plan of the row-distributed two-level PCG on the CPU (rows over world x G virtual CTAs, rank-aligned aggregates, halo masks);
+    the library verifies its invariants and raises CubaError if one fails."""
+    L = load_library()
+    P, keep = _problem_struct(prob)
+    info = np.zeros(8, np.int32)
+    _check(L.cuba_debug_pcg5_plan(C.byref(P), int(world), int(num_sms), int(max_aggregates), _p(info)))
+    return dict(zip(("ok", "G", "gs", "A", "needMax", "maxRows", "maxNeedAgg", "halo_rows"), (int(v) for v in info)))
 
 
 class Engine:

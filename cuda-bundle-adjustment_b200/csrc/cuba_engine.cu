@@ -23,6 +23,7 @@
 #include "cuba_schur2.cuh"
 #include "cuba_jh4.cuh"
 #include "cuba_schur3.cuh"
+#include "cuba_schur5.cuh"
 #include "cuba_structure.h"
 #include "cuba_structure_gpu.cuh"
 
@@ -205,6 +206,11 @@ struct Engine : EngineBase {
 	DBuf<TileInfo> tileInfo;
 	// tile-local Schur (cuba_schur2.cuh)
 	bool useSchur2 = true;
+	bool useSchur5 = false;  // landmark tiles + DMMA (cuba_schur5.cuh), fp64 only
+	int s5Ntiles = 0;
+	DBuf<int> s5TileLm;
+	DBuf<TileInfo> s5TileInfo;
+	DBuf<int4> s5SegRec;
 	int s2Nseg = 0;
 	DBuf<unsigned long long> s2_key, s2_keyS, s2_key3, s2_key3S;
 	DBuf<int> s2_val, s2_valS, s2_head, s2_segId, s2_segStart, s2_segTile, s2_segDest, s2_val3, s2_val3S, s2_segRank, s2_rankDest, s2_tileSegPtr, s2_destSegPtr, s2_p2i, s2_p2j;
@@ -668,14 +674,32 @@ struct Engine : EngineBase {
 		jh3Grid = std::max(1, std::min(ntiles, numSMs * 4));
 		// the tile-local Schur pair is correct but (round 1) slower than k_schur: 387 vs 267 us on kitti00_shaped -> opt-in
 		useSchur2 = cfg.reserved[3] == 2 && S.numP > 0 && S.numL > 0 && ntiles > 0;
-		// 0 = k_schur3 (six lanes per product; default), 4 = k_schur4 (same + cooperative cp.async block loads: slower, kept for the record),
-		// 1 = k_schur (lane per product), 2 = tile-local pair
-		useSchur3 = cfg.reserved[3] == 0 || cfg.reserved[3] == 4;
+		// 0 = landmark tiles on the fp64 tensor pipe (k_schur_tiles_mma + k_schur_reduce; default for fp64), 3 = k_schur3 (six lanes per
+		// product; default for fp32), 4 = k_schur4 (same + cooperative cp.async block loads: slower, kept for the record),
+		// 1 = k_schur (lane per product), 2 = tile-local pair without tensor cores
+		useSchur5 = cfg.reserved[3] == 0 && cfg.reserved[1] != 1 && sizeof(T) == 8 && S.numP > 0 && S.numL > 0 && ntiles > 0 && S.eLocal > 0;
+		useSchur3 = cfg.reserved[3] == 0 || cfg.reserved[3] == 3 || cfg.reserved[3] == 4;
 		if (useSchur3 && S.nmulLocal > 0) {
 			CUDA_TRY(prodL.alloc((size_t)S.nmulLocal));
 			KLAUNCH(schur3::k_prod_landmark, S.nmulLocal, prodI.p, hplLm.p, (int)S.nmulLocal, prodL.p);
 		}
-		if (useSchur2) { int rc = setup_schur2(); if (rc) return rc; }
+		if (useSchur5) {
+			// the Schur stage cuts its own, larger landmark tiles (windows of 448 edges)
+			const int tb5 = std::min(S.lmBeg, S.numL), te5 = std::min(S.lmEnd, S.numL) + (S.lmEnd > S.numL ? 1 : 0);
+			s5Ntiles = (S.eLocal + schur5::WINDOW - 1) / schur5::WINDOW;
+			CUDA_TRY(s5TileLm.alloc((size_t)s5Ntiles + 1)); CUDA_TRY(s5TileInfo.alloc((size_t)s5Ntiles));
+			KLAUNCH(sgpu::k_tiles, s5Ntiles + 1, tilePtr.p, tb5, te5, schur5::WINDOW, s5Ntiles, s5TileLm.p);
+			k_tile_info3<<<s5Ntiles, 128, 0, stream>>>(tilePtr.p, s5TileLm.p, e_ip.p, e_hpl.p, S.eLocal, S.nhplLocal, s5Ntiles, s5TileInfo.p);
+			launches++;
+			CUDA_TRY(cudaGetLastError());
+			int rc = setup_schur2(s5TileInfo.p, s5Ntiles); if (rc) return rc;
+			if (useSchur5) {
+				CUDA_TRY(s5SegRec.alloc((size_t)std::max(s2Nseg, 1)));
+				KLAUNCH(schur5::k_seg_records, s2Nseg, s2_segStart.p, s2_segDest.p, s2_segRank.p, blkRow.p, blkCol.p, s2Nseg, s5SegRec.p);
+				CUDA_TRY(cudaFuncSetAttribute(schur5::k_schur_tiles_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(schur5::Smem)));
+			}
+		}
+		else if (useSchur2) { int rc = setup_schur2(tileInfo.p, ntiles); if (rc) return rc; }
 		tmark("alloc + tile info queued");
 		if (jhV4) { int rc = setup_jh4(); if (rc) return rc; }
 		tmark("jh4 queued");
@@ -931,12 +955,20 @@ struct Engine : EngineBase {
 	int launch_schur(T lambda)
 	{
 		ProfScope ps(this, CUBA_PROF_SCHUR_COMPLEMENT);
-		if (useSchur2) {
+		if (useSchur2 || useSchur5) {
 			schur2::TileArgs<T> ta;
 			ta.Hpl = Hpl; ta.Hll = Hll; ta.bl = bl; ta.info = tileInfo; ta.hplLm = hplLm;
 			ta.tileSegPtr = s2_tileSegPtr; ta.segStart = s2_segStart; ta.segDest = s2_segDest; ta.segRank = s2_segRank; ta.p2i = s2_p2i; ta.p2j = s2_p2j;
 			ta.blkRow = blkRow; ta.blkCol = blkCol; ta.numL = S.numL; ta.lambda = lambda; ta.invHll = invHll; ta.partial = s2_partial;
-			schur2::k_schur_tiles<T><<<ntiles, schur2::TL, 0, stream>>>(ta);
+			if (useSchur5) {
+				if constexpr (sizeof(T) == 8) {
+					schur5::Args sa;
+					sa.Hpl = Hpl; sa.Hll = Hll; sa.bl = bl; sa.info = s5TileInfo; sa.hplLm = hplLm; sa.tileSegPtr = s2_tileSegPtr; sa.segRec = s5SegRec;
+					sa.p2i = s2_p2i; sa.p2j = s2_p2j; sa.numL = S.numL; sa.lambda = lambda; sa.invHll = invHll; sa.partial = s2_partial;
+					schur5::k_schur_tiles_mma<<<s5Ntiles, schur5::WARPS * 32, sizeof(schur5::Smem), stream>>>(sa);
+				}
+			}
+			else schur2::k_schur_tiles<T><<<ntiles, schur2::TL, 0, stream>>>(ta);
 			launches++;
 			CUDA_TRY(cudaGetLastError());
 			schur2::ReduceArgs<T> ra;
@@ -1036,14 +1068,14 @@ struct Engine : EngineBase {
 	}
 
 	// (tile, destination) segments of the block products for the tile-local Schur kernels
-	int setup_schur2()
+	int setup_schur2(const TileInfo* tinfo, int nt)
 	{
 		using namespace schur2;
 		const int N = (int)S.nmulLocal, nblk = S.nblk;
-		if (N <= 0) { useSchur2 = false; return CUBA_OK; }
+		if (N <= 0) { useSchur2 = false; useSchur5 = false; return CUBA_OK; }
 		CUDA_TRY(s2_key.alloc(N)); CUDA_TRY(s2_keyS.alloc(N)); CUDA_TRY(s2_val.alloc(N)); CUDA_TRY(s2_valS.alloc(N));
 		CUDA_TRY(s2_head.alloc(N)); CUDA_TRY(s2_segId.alloc(N)); CUDA_TRY(s2_counts.alloc(1));
-		KLAUNCH(schur2::k_keys, N, prodPtr.p, nblk, prodI.p, N, tileInfo.p, ntiles, s2_key.p, s2_val.p);
+		KLAUNCH(schur2::k_keys, N, prodPtr.p, nblk, prodI.p, N, tinfo, nt, s2_key.p, s2_val.p);
 		int rc = sortPairs(s2_key.p, s2_keyS.p, s2_val.p, s2_valS.p, N, 64); if (rc) return rc;
 		KLAUNCH(schur2::k_heads, N, s2_keyS.p, N, s2_head.p);
 		rc = exclusiveSum(s2_head.p, s2_segId.p, N); if (rc) return rc;
@@ -1057,11 +1089,11 @@ struct Engine : EngineBase {
 		CUDA_TRY(s2_segStart.alloc((size_t)nseg + 1)); CUDA_TRY(s2_segTile.alloc(nseg)); CUDA_TRY(s2_segDest.alloc(nseg));
 		CUDA_TRY(s2_key3.alloc(nseg)); CUDA_TRY(s2_key3S.alloc(nseg)); CUDA_TRY(s2_val3.alloc(nseg)); CUDA_TRY(s2_val3S.alloc(nseg));
 		CUDA_TRY(s2_segRank.alloc(nseg)); CUDA_TRY(s2_rankDest.alloc(nseg));
-		CUDA_TRY(s2_tileSegPtr.alloc((size_t)ntiles + 1)); CUDA_TRY(s2_destSegPtr.alloc((size_t)nblk + 1));
+		CUDA_TRY(s2_tileSegPtr.alloc((size_t)nt + 1)); CUDA_TRY(s2_destSegPtr.alloc((size_t)nblk + 1));
 		CUDA_TRY(s2_p2i.alloc(N)); CUDA_TRY(s2_p2j.alloc(N));
 		KLAUNCH(schur2::k_segments, N + 1, s2_keyS.p, s2_valS.p, s2_head.p, s2_segId.p, prodI.p, prodJ.p, N, nseg, hc.nvalid,
 			s2_segStart.p, s2_segTile.p, s2_segDest.p, s2_p2i.p, s2_p2j.p, s2_key3.p, s2_val3.p);
-		KLAUNCH(schur2::k_ptr_from_field, ntiles + 1, s2_segTile.p, nseg, ntiles, s2_tileSegPtr.p);
+		KLAUNCH(schur2::k_ptr_from_field, nt + 1, s2_segTile.p, nseg, nt, s2_tileSegPtr.p);
 		rc = sortPairs(s2_key3.p, s2_key3S.p, s2_val3.p, s2_val3S.p, nseg, 32 + sgpu::bits_for((unsigned long long)std::max(nblk, 1))); if (rc) return rc;
 		KLAUNCH(schur2::k_rank, nseg, s2_key3S.p, s2_val3S.p, nseg, s2_segRank.p, s2_rankDest.p);
 		KLAUNCH(schur2::k_ptr_from_field, nblk + 1, s2_rankDest.p, nseg, nblk, s2_destSegPtr.p);
@@ -1340,27 +1372,15 @@ struct Engine : EngineBase {
 		int smemMax = 0;
 		CUDA_TRY(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, devOrdinal));
 		const size_t budget = (size_t)smemMax > 4096 ? (size_t)smemMax - 2048 : 0;   // static arrays of k_pcg5: < 1 KB
-		// CTAs per GPU: about eight rows each, never more than 42 (one thread per (row, component) pair in the row sums)
-		int G = std::max(1, std::min(numSMs, (numP / W + 7) / 8));
-		if (W * G > numP) G = std::max(1, numP / W);
+		// rows over world x G virtual CTAs (about eight rows each, never more than 42: one thread per (row, component) pair in the
+		// row sums), rank-aligned aggregates, halo masks: cuba_structure.cpp (CPU-tested through cuba_debug_pcg5_plan)
 		const int maxAgg = (cfg.reserved[6] > 0 && cfg.reserved[6] < PCG4_MAXAGG) ? cfg.reserved[6] : PCG4_MAXAGG;
-		const int gs = (W * G + maxAgg - 1) / maxAgg;
-		G = std::max(gs, G / gs * gs);
-		const int Gt = W * G, A = Gt / gs;
-		if (Gt > numP || A < 1) return CUBA_OK;
-		PcgPartition PP; CoarsePartition CP;
-		build_pcg_partition(numP, S.nfull, S.fRowPtr, S.fColInd, Gt, PP);
-		build_coarse_partition(numP, PP, A, CP);
-		if (CP.gs != gs || CP.A != A || PP.maxRows * 6 > PCG5_BLOCK) return CUBA_OK;
-		build_coarse_lists(numP, S.nfull, S.fRowPtr, S.fColInd, CP);
-		// which ranks need a row's w besides its owner
-		std::vector<unsigned char> peers(numP, 0);
-		if (W > 1) {
-			std::vector<int> rowRank(numP, 0);
-			for (int c = 0; c < Gt; c++) for (int r = PP.rows[c]; r < PP.rows[c + 1]; r++) rowRank[r] = c / G;
-			for (int c = 0; c < Gt; c++)
-				for (int k = PP.nptr[c]; k < PP.nptr[c + 1]; k++) { const int j = PP.ncol[k]; if (rowRank[j] != c / G) peers[j] |= (unsigned char)(1u << (c / G)); }
-		}
+		Pcg5Plan plan;
+		build_pcg5_plan(numP, S.nfull, S.fRowPtr, S.fColInd, W, numSMs, maxAgg, PCG5_BLOCK / 6, plan);
+		if (!plan.ok) return CUBA_OK;
+		const int G = plan.G, gs = plan.gs, A = plan.A;
+		const PcgPartition& PP = plan.P; const CoarsePartition& CP = plan.C;
+		const std::vector<unsigned char>& peers = plan.rowPeers;
 		const int Aloc = G / gs, NR = 3 + 6 * Aloc, nc = 6 * A;
 		Pcg5Dims d{};
 		d.needMax = PP.needMax; d.maxRows = PP.maxRows; d.nc = nc; d.maxNeedAgg = CP.maxNeedAgg;
@@ -2062,6 +2082,28 @@ int cuba_debug_pcg_partition(const cuba_problem* p, int nCtas, int maxAgg, int32
 	const char* bad = check_pcg_partition(S.numP, S.nfull, S.fRowPtr, S.fColInd, P, C);
 	if (bad) return fail(CUBA_ERR_INVALID, std::string("pcg_partition self-check: ") + bad);
 	if (info) { info[0] = P.G; info[1] = C.gs; info[2] = C.A; info[3] = P.needMax; info[4] = P.maxRows; info[5] = P.blkMax; info[6] = C.maxNeedAgg; info[7] = (int32_t)C.cbList.size(); }
+	return CUBA_OK;
+}
+
+/* host side of the row-distributed PCG plan on the CPU (no device needed): info[8] = ok, G, gs, A, needMax, maxRows, maxNeedAgg,
+ * number of rows some other rank needs (halo rows) */
+int cuba_debug_pcg5_plan(const cuba_problem* p, int world, int numSMs, int maxAgg, int32_t* info)
+{
+	if (!p || world < 1 || world > 8 || numSMs < 1 || maxAgg < 1) return fail(CUBA_ERR_INVALID, "pcg5_plan: bad arguments");
+	Structure S;
+	const char* err = "";
+	if (!build_structure(p->Pall, p->numP, p->Lall, p->numL, p->E2, p->idx2, p->E3, p->idx3, 0, 1, TILE, S, &err)) return fail(CUBA_ERR_INVALID, err);
+	Pcg5Plan plan;
+	build_pcg5_plan(S.numP, S.nfull, S.fRowPtr, S.fColInd, world, numSMs, maxAgg, PCG5_BLOCK / 6, plan);
+	if (info) for (int i = 0; i < 8; i++) info[i] = 0;
+	if (!plan.ok) return CUBA_OK;
+	const char* bad = check_pcg5_plan(S.numP, S.nfull, S.fRowPtr, S.fColInd, plan);
+	if (bad) return fail(CUBA_ERR_INVALID, std::string("pcg5_plan self-check: ") + bad);
+	if (info) {
+		int halo = 0;
+		for (unsigned char m : plan.rowPeers) if (m) halo++;
+		info[0] = 1; info[1] = plan.G; info[2] = plan.gs; info[3] = plan.A; info[4] = plan.P.needMax; info[5] = plan.P.maxRows; info[6] = plan.C.maxNeedAgg; info[7] = halo;
+	}
 	return CUBA_OK;
 }
 

@@ -54,7 +54,7 @@ struct Pcg5Dims {
 // shared-memory carve-up, one definition for the host (size) and the device (pointers)
 template <typename T>
 struct Pcg5Layout {
-	size_t blk, r, s, u, p, y, cc, rc, sc, c, zh, pv, ls, ai, loc, rowPtr, woff, own, nagg, alist, diag, total;
+	size_t blk, r, s, u, p, y, cc, rc, sc, c, zh, pv, ls, sq, ai, loc, rowPtr, woff, own, nagg, alist, diag, total;
 	__host__ __device__ explicit Pcg5Layout(const Pcg5Dims& d)
 	{
 		size_t o = 0;
@@ -72,6 +72,7 @@ struct Pcg5Layout {
 		zh = take(d.zhInSmem ? (size_t)d.needMax * 36 * sizeof(T) : 0, 8);
 		pv = take((size_t)d.npv * sizeof(double), 8);
 		ls = take((size_t)d.nls * sizeof(double), 8);
+		sq = take((size_t)9 * d.maxRows * 6 * sizeof(double), 8);   // partial inner products of the (row, component) threads
 		ai = take((size_t)d.sliceRows * d.nc * sizeof(float), 16);
 		loc = take((size_t)d.capBlocks * sizeof(int), 4);
 		rowPtr = take(((size_t)d.maxRows + 1) * sizeof(int), 4);
@@ -235,7 +236,6 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 	int* s_nagg = reinterpret_cast<int*>(smem_raw + lay.nagg);
 	int* s_alist = reinterpret_cast<int*>(smem_raw + lay.alist);
 	int* s_diag = reinterpret_cast<int*>(smem_raw + lay.diag);
-	__shared__ double s_red[PCG5_BLOCK / 32][9];
 	__shared__ int s_abort;
 
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -374,6 +374,14 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 				__syncthreads();
 				PCG_T(t1);
 				if (s_abort) { status = 3; break; }
+				double gnew, delta, rnew;
+				if (world == 1) {
+					// ---- one GPU: every warp adds the three scalars over the CTAs itself (same order everywhere), no barrier;
+					//      the restricted Z^^T w of an aggregate is summed by the thread that advances that coarse entry ----
+					double v0 = 0, v1 = 0, v2 = 0;
+					for (int c = lane; c < G; c += 32) { v0 += s_pv[c * NP]; v1 += s_pv[c * NP + 1]; v2 += s_pv[c * NP + 2]; }
+					gnew = warp_sum(v0); delta = warp_sum(v1); rnew = warp_sum(v2);
+				} else {
 				// ---- this GPU's summary: gamma, delta, rho over its CTAs (one warp each), Z^^T w per local aggregate ----
 				if (wid < 3) {
 					double v = 0;
@@ -389,8 +397,7 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 						s_ls[3 + q] = v;
 					}
 				__syncthreads();
-				double gnew, delta, rnew;
-				if (world > 1) {
+				{
 					// ---- rank hop: designated CTAs push the summary to every rank's board (replica by replica), everybody polls ----
 					const size_t rOff = rHalf + (size_t)par * rStride;
 					for (int pr = lc; pr < world * PCG5_REPL; pr += G) {
@@ -405,8 +412,7 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 					if (s_abort) { status = 3; break; }
 					gnew = 0; delta = 0; rnew = 0;
 					for (int r = 0; r < world; r++) { gnew += s_pv[r * NR]; delta += s_pv[r * NR + 1]; rnew += s_pv[r * NR + 2]; }
-				} else {
-					gnew = s_ls[0]; delta = s_ls[1]; rnew = s_ls[2];
+				}
 				}
 				PCG_T(t2);
 				if (!(gnew == gnew) || !(delta == delta) || !(rnew == rnew)) { status = 2; break; }
@@ -445,7 +451,13 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 				if (coarse)
 					for (int q = tid; q < nc; q += PCG5_BLOCK) {
 						// global aggregate q/6 = rank r, local aggregate al
-						const double wcv = world > 1 ? s_pv[(q / (6 * Aloc)) * NR + 3 + (q % (6 * Aloc))] : s_ls[3 + q];
+						double wcv;
+						if (world > 1) wcv = s_pv[(q / (6 * Aloc)) * NR + 3 + (q % (6 * Aloc))];
+						else {
+							const int al = q / 6, comp = q - 6 * al;
+							wcv = 0;
+							for (int c = al * a.gs; c < (al + 1) * a.gs; c++) wcv += s_pv[c * NP + 3 + comp];
+						}
 						const T sc = (T)wcv + (T)beta * s_sc[q];
 						s_sc[q] = sc;
 						s_rc[q] -= (T)alpha * sc;
@@ -470,13 +482,16 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 				}
 				{
 					const unsigned long long* cR = cB + 2 * ((size_t)rep * nc);
-					const bool ok = ll_poll_many(nagg * 6, [&](int i) { return cR + 2 * (size_t)(s_alist[i / 6] * 6 + (i % 6)); }, s_pv, ctag, a.ctl);
+					double* cdst = sizeof(T) == 8 ? reinterpret_cast<double*>(s_c) : s_pv;
+					const bool ok = ll_poll_many(nagg * 6, [&](int i) { return cR + 2 * (size_t)(s_alist[i / 6] * 6 + (i % 6)); }, cdst, ctag, a.ctl);
 					if (!ok) s_abort = 1;
 				}
 				__syncthreads();
 				if (s_abort) { status = 3; break; }
-				for (int i = tid; i < nagg * 6; i += PCG5_BLOCK) s_c[i] = (T)s_pv[i];
-				__syncthreads();
+				if (sizeof(T) != 8) {
+					for (int i = tid; i < nagg * 6; i += PCG5_BLOCK) s_c[i] = (T)s_pv[i];
+					__syncthreads();
+				}
 				// ---- u_j = r_j + Z^_j c_a(j) for every needed column ----
 				for (int wi = tid; wi < nneed * 6; wi += PCG5_BLOCK) {
 					const int c = wi / 6, comp = wi - 6 * c;
@@ -564,7 +579,10 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 			for (int o = 1; o < tpp; o <<= 1) wacc += __shfl_xor_sync(0xffffffffu, wacc, o);
 			PCG_T(t6);
 			// ---- publish w (own board + the boards of the ranks that need the row), partial inner products, Z^^T w ----
-			double pq[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+			// The nine quantities of the (row, component) threads go to shared memory; afterwards warp w adds quantity w (warp 0
+			// also the ninth) in a fixed order and its first REPL lanes publish the replicas.
+			const int nact = nrows * 6;                           // active threads: tid = pair * tpp
+			double* s_q = reinterpret_cast<double*>(smem_raw + lay.sq);   // [9][nact]; read below, rewritten only after the next pass's barriers
 			if (tid < nrows * 6 * tpp && (tid % tpp) == 0) {
 				const int pair = tid / tpp;
 				const int li = pair / 6, comp = pair - 6 * li;
@@ -582,32 +600,26 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 						ll_store(a.peerW[pr] + 2 * slot, (double)wv1, otag);
 					}
 				}
-				pq[0] = (double)ri * (double)ui;
-				pq[1] = (double)wv1 * (double)ui;
-				pq[2] = (double)ri * (double)ri;
+				s_q[pair] = (double)ri * (double)ui;
+				s_q[nact + pair] = (double)wv1 * (double)ui;
+				s_q[2 * nact + pair] = (double)ri * (double)ri;
 				if (coarse) {
 					const T* Zh = a.dims.zhInSmem ? s_zh + 36 * (size_t)dl + comp : a.Zhat + 36 * (size_t)(row0 + li) + comp;
 #pragma unroll
-					for (int q = 0; q < 6; q++) pq[3 + q] = (double)(Zh[6 * q] * wv1);   // (Z^^T w)(q) = sum_comp Z^(comp,q) w(comp)
+					for (int q = 0; q < 6; q++) s_q[(3 + q) * nact + pair] = (double)(Zh[6 * q] * wv1);   // (Z^^T w)(q) = sum_comp Z^(comp,q) w(comp)
 				}
-			}
-#pragma unroll
-			for (int q = 0; q < 9; q++) if (q < 3 || coarse) pq[q] = warp_sum(pq[q]);
-			if (lane == 0) {
-#pragma unroll
-				for (int q = 0; q < 9; q++) s_red[wid][q] = pq[q];
 			}
 			__syncthreads();
 			PCG_T(t7);
-			if (tid < NP * PCG5_REPL) {                          // thread (replica, word)
-				const int rp = tid / NP, word = tid - rp * NP;
+			for (int word = wid; word < NP; word += PCG5_BLOCK / 32) {
 				double v = 0;
-				for (int w = 0; w < PCG5_BLOCK / 32; w++) v += s_red[w][word];
-				ll_store(a.pBoard + 2 * (pHalf + (size_t)opar * pStride + ((size_t)rp * G + lc) * NP + word), v, otag);
+				for (int i = lane; i < nact; i += 32) v += s_q[word * nact + i];
+				v = warp_sum(v);
+				if (lane < PCG5_REPL) ll_store(a.pBoard + 2 * (pHalf + (size_t)opar * pStride + ((size_t)lane * G + lc) * NP + word), v, otag);
 			}
 			PCG_T(t8);
 			PCG_ACC(3, t4, t5); PCG_ACC(4, t5, t6); PCG_ACC(5, t6, t7); PCG_ACC(6, t7, t8);
-			// s_red / s_cc are rewritten only after the next pass's __syncthreads
+			// s_q / s_cc are rewritten only after the next pass's __syncthreads
 		}
 	}
 	// a rank that gave up tells the others, so that nobody waits for its words

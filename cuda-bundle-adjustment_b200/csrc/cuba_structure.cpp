@@ -352,4 +352,61 @@ const char* check_pcg_partition(int numP, int nfull, const std::vector<int>& fRo
 	return nullptr;
 }
 
+void build_pcg5_plan(int numP, int nfull, const std::vector<int>& fRowPtr, const std::vector<int>& fColInd, int world, int numSMs, int maxAgg,
+	int maxRowsPerCta, Pcg5Plan& plan)
+{
+	plan = Pcg5Plan();
+	plan.world = world;
+	if (numP < 1 || world < 1 || world > 8) return;
+	// CTAs per GPU: about eight rows each
+	int G = std::max(1, std::min(numSMs, (numP / world + 7) / 8));
+	if (world * G > numP) G = std::max(1, numP / world);
+	const int gs = (world * G + maxAgg - 1) / maxAgg;
+	G = std::max(gs, G / gs * gs);
+	const int Gt = world * G, A = Gt / gs;
+	if (Gt > numP || A < 1 || G > numSMs) return;
+	build_pcg_partition(numP, nfull, fRowPtr, fColInd, Gt, plan.P);
+	build_coarse_partition(numP, plan.P, A, plan.C);
+	if (plan.C.gs != gs || plan.C.A != A || plan.P.maxRows > maxRowsPerCta) return;
+	build_coarse_lists(numP, nfull, fRowPtr, fColInd, plan.C);
+	plan.rowPeers.assign(numP, 0);
+	if (world > 1) {
+		std::vector<int> rowRank(numP, 0);
+		for (int c = 0; c < Gt; c++) for (int r = plan.P.rows[c]; r < plan.P.rows[c + 1]; r++) rowRank[r] = c / G;
+		for (int c = 0; c < Gt; c++)
+			for (int k = plan.P.nptr[c]; k < plan.P.nptr[c + 1]; k++) {
+				const int j = plan.P.ncol[k];
+				if (rowRank[j] != c / G) plan.rowPeers[j] |= (unsigned char)(1u << (c / G));
+			}
+	}
+	plan.G = G; plan.gs = gs; plan.A = A;
+	plan.ok = true;
+}
+
+const char* check_pcg5_plan(int numP, int nfull, const std::vector<int>& fRowPtr, const std::vector<int>& fColInd, const Pcg5Plan& plan)
+{
+	if (!plan.ok) return "plan not ok";
+	const int G = plan.G, W = plan.world, Gt = G * W, gs = plan.gs;
+	if (plan.P.G != Gt) return "virtual CTA count";
+	if (G % gs != 0 || plan.A * gs != Gt) return "aggregates do not tile the ranks";
+	const char* bad = check_pcg_partition(numP, nfull, fRowPtr, fColInd, plan.P, plan.C);
+	if (bad) return bad;
+	// every aggregate lies inside one rank
+	for (int a = 0; a < plan.A; a++) {
+		const int c0 = a * gs, c1 = c0 + gs - 1;
+		if (c0 / G != c1 / G) return "aggregate straddles two ranks";
+	}
+	// rowPeers: exactly the ranks (not the owner) with a CTA that needs the row
+	std::vector<int> rowRank(numP, 0);
+	for (int c = 0; c < Gt; c++) for (int r = plan.P.rows[c]; r < plan.P.rows[c + 1]; r++) rowRank[r] = c / G;
+	std::vector<unsigned> want(numP, 0);
+	for (int i = 0; i < numP; i++)
+		for (int n = fRowPtr[i]; n < fRowPtr[i + 1]; n++) { const int j = fColInd[n]; if (rowRank[j] != rowRank[i]) want[j] |= 1u << rowRank[i]; }
+	for (int j = 0; j < numP; j++) {
+		if ((unsigned)plan.rowPeers[j] != want[j]) return "rowPeers differs from the ranks whose rows couple to the row";
+		if (plan.rowPeers[j] & (1u << rowRank[j])) return "rowPeers names the owner";
+	}
+	return nullptr;
+}
+
 }  // namespace cuba_b200

@@ -99,4 +99,20 @@ void build_coarse_lists(int numP, int nfull, const std::vector<int>& fRowPtr, co
 const char* check_pcg_partition(int numP, int nfull, const std::vector<int>& fRowPtr, const std::vector<int>& fColInd,
 	const PcgPartition& P, const CoarsePartition& C);
 
+// Plan of the row-distributed two-level PCG (k_pcg5): rows cut into world x G contiguous ranges ("virtual CTAs"), G per GPU;
+// aggregates = groups of gs consecutive virtual CTAs with gs | G, so that no aggregate straddles two ranks; rowPeers[j] = bit
+// mask of the ranks (other than the owner) whose CTAs need row j's w entries.  ok == false: the system is too small / the row
+// ranges too long for the kernel (the engine then keeps the older kernels).
+struct Pcg5Plan {
+	bool ok = false;
+	int world = 1, G = 0, gs = 1, A = 0;
+	PcgPartition P;
+	CoarsePartition C;
+	std::vector<unsigned char> rowPeers;
+};
+void build_pcg5_plan(int numP, int nfull, const std::vector<int>& fRowPtr, const std::vector<int>& fColInd, int world, int numSMs, int maxAgg,
+	int maxRowsPerCta, Pcg5Plan& plan);
+// invariants of a plan (nullptr when everything holds)
+const char* check_pcg5_plan(int numP, int nfull, const std::vector<int>& fRowPtr, const std::vector<int>& fColInd, const Pcg5Plan& plan);
+
 }  // namespace cuba_b200

@@ -210,6 +210,11 @@ int cuba_debug_build_structure_host(const cuba_problem* p, int rank, int world, 
  * info[8] = G, gs, A, needMax, maxRows, blkMax, maxNeedAgg, size of the coarse lists.  No device needed. */
 int cuba_debug_pcg_partition(const cuba_problem* p, int nCtas, int maxAgg, int32_t* info);
 
+/* CPU-only check of the plan of the row-distributed two-level PCG (k_pcg5; csrc/cuba_structure.cpp): rows over world x G virtual
+ * CTAs, aggregates aligned with the ranks, halo masks.  info[8] = ok (0: system too small for this kernel), G, gs, A, needMax,
+ * maxRows, maxNeedAgg, number of halo rows.  No device needed. */
+int cuba_debug_pcg5_plan(const cuba_problem* p, int world, int numSMs, int maxAgg, int32_t* info);
+
 /* ---- micro-benchmark hooks for bench.py / profiles (device-resident data, CUDA-event timed) ---- */
 /* Runs the named stage `reps` times back to back and returns the average device milliseconds per
  * repetition.  stage: 0 linearize (landmark pass + pose pass), 1 landmark pass only, 2 pose pass only,

@@ -118,6 +118,24 @@ def test_pcg_partition_host_logic(pkg, problems, name, n_ctas, max_agg):
     assert prob.numP <= info["coarse_list_size"] <= s["nblk_full"]
 
 
+@pytest.mark.parametrize("name", ["small", "kitti07_shaped", "kitti00_shaped"])
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_row_distributed_pcg_plan(pkg, problems, name, world):
+    """plan of k_pcg5 for `world` GPUs (csrc/cuba_structure.cpp::build_pcg5_plan, the engine's own code): rows over world x G
+    virtual CTAs, aggregates that never straddle two ranks, and the halo masks -- for every row exactly the ranks, other than
+    its owner, whose rows couple to it.  The library checks the invariants; here: sizes and that the halo grows with the cut count"""
+    prob = problems(name)
+    info = pkg.pcg5_plan_host(prob, world)
+    if not info["ok"]:
+        assert world * 8 > prob.numP or name == "small"
+        return
+    assert info["G"] % info["gs"] == 0 and info["A"] == world * info["G"] // info["gs"] <= 74
+    assert info["maxRows"] * 6 <= 256 and world * info["G"] <= prob.numP
+    assert (info["halo_rows"] == 0) == (world == 1)
+    if world > 1:
+        assert info["halo_rows"] >= world - 1
+
+
 def test_pcg_partition_rejects_bad_arguments(pkg, problems):
     with pytest.raises(pkg.CubaError):
         pkg.pcg_partition_host(problems("tiny"), 0, 74)
