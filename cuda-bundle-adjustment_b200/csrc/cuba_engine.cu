@@ -211,7 +211,8 @@ struct Engine : EngineBase {
 	DBuf<int> s5TileLm;
 	DBuf<TileInfo> s5TileInfo;
 	DBuf<int4> s5SegRec;
-	int s2Nseg = 0;
+	DBuf<unsigned int> s5Off;
+	int s2Nseg = 0, s2Nvalid = 0;
 	DBuf<unsigned long long> s2_key, s2_keyS, s2_key3, s2_key3S;
 	DBuf<int> s2_val, s2_valS, s2_head, s2_segId, s2_segStart, s2_segTile, s2_segDest, s2_val3, s2_val3S, s2_segRank, s2_rankDest, s2_tileSegPtr, s2_destSegPtr, s2_p2i, s2_p2j;
 	DBuf<schur2::Counts> s2_counts;
@@ -674,10 +675,12 @@ struct Engine : EngineBase {
 		jh3Grid = std::max(1, std::min(ntiles, numSMs * 4));
 		// the tile-local Schur pair is correct but (round 1) slower than k_schur: 387 vs 267 us on kitti00_shaped -> opt-in
 		useSchur2 = cfg.reserved[3] == 2 && S.numP > 0 && S.numL > 0 && ntiles > 0;
-		// 0 = landmark tiles on the fp64 tensor pipe (k_schur_tiles_mma + k_schur_reduce; default for fp64), 3 = k_schur3 (six lanes per
-		// product; default for fp32), 4 = k_schur4 (same + cooperative cp.async block loads: slower, kept for the record),
-		// 1 = k_schur (lane per product), 2 = tile-local pair without tensor cores
-		useSchur5 = cfg.reserved[3] == 0 && cfg.reserved[1] != 1 && sizeof(T) == 8 && S.numP > 0 && S.numL > 0 && ntiles > 0 && S.eLocal > 0;
+		// 0 / 3 = k_schur3 (destination-sorted products, six lanes per product; default), 5 = landmark tiles on the fp64 tensor pipe
+		// (k_schur_tiles_mma + k_schur_reduce, cuba_schur5.cuh: 12 % faster on the banded 5 M-edge graph, on par on kitti00_shaped,
+		// 2x slower on the real ba_kitti_00 whose loop closures leave 4.4 products per (tile, destination) segment -> opt-in),
+		// 4 = k_schur4 (k_schur3 + cooperative cp.async block loads: slower, kept for the record), 1 = k_schur (lane per product),
+		// 2 = tile-local pair without tensor cores
+		useSchur5 = cfg.reserved[3] == 5 && cfg.reserved[1] != 1 && sizeof(T) == 8 && S.numP > 0 && S.numL > 0 && ntiles > 0 && S.eLocal > 0;
 		useSchur3 = cfg.reserved[3] == 0 || cfg.reserved[3] == 3 || cfg.reserved[3] == 4;
 		if (useSchur3 && S.nmulLocal > 0) {
 			CUDA_TRY(prodL.alloc((size_t)S.nmulLocal));
@@ -695,7 +698,9 @@ struct Engine : EngineBase {
 			int rc = setup_schur2(s5TileInfo.p, s5Ntiles); if (rc) return rc;
 			if (useSchur5) {
 				CUDA_TRY(s5SegRec.alloc((size_t)std::max(s2Nseg, 1)));
-				KLAUNCH(schur5::k_seg_records, s2Nseg, s2_segStart.p, s2_segDest.p, s2_segRank.p, blkRow.p, blkCol.p, s2Nseg, s5SegRec.p);
+				KLAUNCH(schur5::k_seg_records, s2Nseg, s2_segStart.p, s2_segDest.p, s2_segRank.p, s2_segTile.p, blkRow.p, blkCol.p, s5TileInfo.p, s2_p2i.p, s2_p2j.p, s2Nseg, s5SegRec.p);
+				CUDA_TRY(s5Off.alloc((size_t)std::max(s2Nvalid, 1)));
+				KLAUNCH(schur5::k_prod_offsets, s2Nvalid, s2_segStart.p, s2_segTile.p, s5TileInfo.p, s2_p2i.p, s2_p2j.p, s2Nseg, s2Nvalid, s5Off.p);
 				CUDA_TRY(cudaFuncSetAttribute(schur5::k_schur_tiles_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(schur5::Smem)));
 			}
 		}
@@ -963,7 +968,7 @@ struct Engine : EngineBase {
 			if (useSchur5) {
 				if constexpr (sizeof(T) == 8) {
 					schur5::Args sa;
-					sa.Hpl = Hpl; sa.Hll = Hll; sa.bl = bl; sa.info = s5TileInfo; sa.hplLm = hplLm; sa.tileSegPtr = s2_tileSegPtr; sa.segRec = s5SegRec;
+					sa.Hpl = Hpl; sa.Hll = Hll; sa.bl = bl; sa.info = s5TileInfo; sa.hplLm = hplLm; sa.tileSegPtr = s2_tileSegPtr; sa.segRec = s5SegRec; sa.off = s5Off;
 					sa.p2i = s2_p2i; sa.p2j = s2_p2j; sa.numL = S.numL; sa.lambda = lambda; sa.invHll = invHll; sa.partial = s2_partial;
 					schur5::k_schur_tiles_mma<<<s5Ntiles, schur5::WARPS * 32, sizeof(schur5::Smem), stream>>>(sa);
 				}
@@ -1085,7 +1090,7 @@ struct Engine : EngineBase {
 		CUDA_TRY(cudaMemcpyAsync(&hc, s2_counts.p, sizeof(hc), cudaMemcpyDeviceToHost, stream));
 		CUDA_TRY(cudaStreamSynchronize(stream));
 		const int nseg = hc.nseg;
-		s2Nseg = nseg;
+		s2Nseg = nseg; s2Nvalid = hc.nvalid;
 		CUDA_TRY(s2_segStart.alloc((size_t)nseg + 1)); CUDA_TRY(s2_segTile.alloc(nseg)); CUDA_TRY(s2_segDest.alloc(nseg));
 		CUDA_TRY(s2_key3.alloc(nseg)); CUDA_TRY(s2_key3S.alloc(nseg)); CUDA_TRY(s2_val3.alloc(nseg)); CUDA_TRY(s2_val3S.alloc(nseg));
 		CUDA_TRY(s2_segRank.alloc(nseg)); CUDA_TRY(s2_rankDest.alloc(nseg));

@@ -20,14 +20,16 @@
 namespace cuba_b200 {
 namespace schur5 {
 
-constexpr int TL = 512;            // Hpl blocks staged per tile (one 6x3 array per block: 72 KB)
+constexpr int TL = 512;            // Hpl blocks staged per tile
+constexpr int BS = 21;             // doubles per staged block: V (6x3, column-major) followed by u (3)
 constexpr int WINDOW = 448;        // edges per tile window of the structure builder: leaves 64 slots for the last landmark's tail
 constexpr int WARPS = 8;
 
 struct Smem {
-	double V[TL * 18];             // V = Hpl chol(inv(Hll + lambda I)): C_ij = sum_l V_il V_jl^T needs ONE staged array
-	double u[TL * 3];              // u = L_l^T bl_l of each staged BLOCK's landmark: the bsc contribution is V_il u_l
-	double L[TL * 6];              // lower Cholesky factor of the inverse, 00,10,20,11,21,22
+	double V[TL * BS];             // per block: V = Hpl chol(inv(Hll + lambda I)) and u = L^T bl of its landmark:
+	                               // C_ij = sum_l V_il V_jl^T needs ONE staged array, the bsc contribution is V_il u_l
+	double zero[2];                // what the padding lanes of a fragment read
+	double L[TL * 6];              // lower Cholesky factor of the inverse per landmark, 00,10,20,11,21,22
 	int lm[TL];                    // local landmark of each block
 };
 
@@ -47,20 +49,37 @@ __device__ __forceinline__ void chol3(const double B[6], double L[6])
 	L[5] = sqrt(B[5] - L[2] * L[2] - L[4] * L[4]);
 }
 
-// per (tile, destination) segment: first product, product count, rank among the destination-sorted partials, diagonal destination
-__global__ void k_seg_records(const int* __restrict__ segStart, const int* __restrict__ segDest, const int* __restrict__ segRank,
-	const int* __restrict__ blkRow, const int* __restrict__ blkCol, int nseg, int4* rec)
+// per (tile, destination) segment: first product, product count, rank among the destination-sorted partials,
+// flags: bit 0 = diagonal destination, bit 1 = some block of the segment lies past the staged range (slow path)
+__global__ void k_seg_records(const int* __restrict__ segStart, const int* __restrict__ segDest, const int* __restrict__ segRank, const int* __restrict__ segTile,
+	const int* __restrict__ blkRow, const int* __restrict__ blkCol, const TileInfo* __restrict__ info, const int* __restrict__ p2i, const int* __restrict__ p2j,
+	int nseg, int4* rec)
 {
 	const int s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= nseg) return;
-	const int k = segDest[s];
-	rec[s] = make_int4(segStart[s], segStart[s + 1] - segStart[s], segRank[s], blkRow[k] == blkCol[k] ? 1 : 0);
+	const int k = segDest[s], h0 = info[segTile[s]].h0;
+	int flags = blkRow[k] == blkCol[k] ? 1 : 0;
+	for (int n = segStart[s]; n < segStart[s + 1]; n++) if (p2i[n] - h0 >= TL || p2j[n] - h0 >= TL) { flags |= 2; break; }
+	rec[s] = make_int4(segStart[s], segStart[s + 1] - segStart[s], segRank[s], flags);
+}
+// operand offsets of every product inside its tile's staged array, in doubles: (block - h0) * BS, both in one word
+__global__ void k_prod_offsets(const int* __restrict__ segStart, const int* __restrict__ segTile, const TileInfo* __restrict__ info,
+	const int* __restrict__ p2i, const int* __restrict__ p2j, int nseg, int nprod, unsigned int* off)
+{
+	const int n = blockIdx.x * blockDim.x + threadIdx.x;
+	if (n >= nprod) return;
+	int lo = 0, hi = nseg - 1;                   // segment of product n: last s with segStart[s] <= n
+	while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (segStart[mid] <= n) lo = mid; else hi = mid - 1; }
+	const int h0 = info[segTile[lo]].h0;
+	const int bi = p2i[n] - h0, bj = p2j[n] - h0;
+	const unsigned int oi = bi < TL ? (unsigned)(bi * BS) : 0u, oj = bj < TL ? (unsigned)(bj * BS) : 0u;   // (slow segments do not use them)
+	off[n] = oi | (oj << 16);
 }
 
 struct Args {
 	const double* Hpl; const double* Hll; const double* bl;
 	const TileInfo* info; const int* hplLm;
-	const int* tileSegPtr; const int4* segRec; const int* p2i; const int* p2j;
+	const int* tileSegPtr; const int4* segRec; const unsigned int* off; const int* p2i; const int* p2j;
 	int numL; double lambda;
 	double* invHll; double* partial;
 };
@@ -78,9 +97,11 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_schur_tiles_mma(const Args a)
 	for (int i = tid; i < nbs * 9; i += WARPS * 32) {
 		double x, y;
 		ld2(a.Hpl + 18 * (size_t)ti.h0 + 2 * i, x, y);
-		sm.V[2 * i] = x; sm.V[2 * i + 1] = y;
+		const int b = i / 9, e = 2 * (i - 9 * b);
+		sm.V[BS * b + e] = x; sm.V[BS * b + e + 1] = y;
 	}
 	for (int i = tid; i < nbs; i += WARPS * 32) sm.lm[i] = a.hplLm[ti.h0 + i] - ti.l0;
+	if (tid < 2) sm.zero[tid] = 0.0;
 	for (int j = tid; j < nl; j += WARPS * 32) {
 		const double* H = a.Hll + 9 * (size_t)(ti.l0 + j);
 		double B[6];
@@ -96,7 +117,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_schur_tiles_mma(const Args a)
 	}
 	if (nb <= 0) return;
 	__syncthreads();
-	// V = Hpl L in place: one (block, row) pair per thread step; (A L)(r,k) = sum_{m>=k} A(r,m) L(m,k)
+	// V = Hpl L in place: one (block, row) pair per thread step; (A L)(r,k) = sum_{m>=k} A(r,m) L(m,k); row 0's thread adds u
 	for (int w = tid; w < nbs * 6; w += WARPS * 32) {
 		const int b = w / 6, r = w - 6 * b;
 		const int lml = sm.lm[b];
@@ -109,16 +130,17 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_schur_tiles_mma(const Args a)
 			const double B[6] = { iv[0], iv[3], iv[6], iv[4], iv[7], iv[8] };
 			chol3(B, L);
 		}
-		const double a0 = sm.V[18 * b + r], a1 = sm.V[18 * b + 6 + r], a2 = sm.V[18 * b + 12 + r];
-		sm.V[18 * b + r] = a0 * L[0] + a1 * L[1] + a2 * L[2];
-		sm.V[18 * b + 6 + r] = a1 * L[3] + a2 * L[4];
-		sm.V[18 * b + 12 + r] = a2 * L[5];
+		double* Vb = sm.V + BS * b;
+		const double a0 = Vb[r], a1 = Vb[6 + r], a2 = Vb[12 + r];
+		Vb[r] = a0 * L[0] + a1 * L[1] + a2 * L[2];
+		Vb[6 + r] = a1 * L[3] + a2 * L[4];
+		Vb[12 + r] = a2 * L[5];
 		if (r == 0) {
 			const double* bb = a.bl + 3 * (size_t)(ti.l0 + lml);
 			const double b0 = bb[0], b1 = bb[1], b2 = bb[2];
-			sm.u[3 * b] = L[0] * b0 + L[1] * b1 + L[2] * b2;      // (L^T b)(k) = sum_m L(m,k) b(m)
-			sm.u[3 * b + 1] = L[3] * b1 + L[4] * b2;
-			sm.u[3 * b + 2] = L[5] * b2;
+			Vb[18] = L[0] * b0 + L[1] * b1 + L[2] * b2;           // (L^T b)(k) = sum_m L(m,k) b(m)
+			Vb[19] = L[3] * b1 + L[4] * b2;
+			Vb[20] = L[5] * b2;
 		}
 	}
 	__syncthreads();
@@ -128,60 +150,53 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_schur_tiles_mma(const Args a)
 	const int fo = q * 6 + g;                            // offset of element (g, q) in a column-major 6x3 block
 	const int s0 = a.tileSegPtr[t], s1 = a.tileSegPtr[t + 1];
 	// Software pipeline over this warp's segments (s, s + WARPS, ...): the record of the segment after next and the first 32
-	// product indices of the next segment are in flight while the current segment is multiplied -- with ~9 products per segment
-	// the two dependent L2 round trips (record -> indices) would otherwise cost more than the products themselves.
+	// operand offsets of the next segment are in flight while the current segment is multiplied -- with ~9 products per segment
+	// the two dependent L2 round trips (record -> offsets) would otherwise cost more than the products themselves.
 	const int4 none = make_int4(0, 0, 0, 0);
 	int4 rec = s0 + wid < s1 ? __ldg(a.segRec + s0 + wid) : none;
 	int4 recN = s0 + wid + WARPS < s1 ? __ldg(a.segRec + s0 + wid + WARPS) : none;
-	int curI = -1, curJ = -1;
-	if (s0 + wid < s1 && lane < rec.y) { curI = __ldg(a.p2i + rec.x + lane) - ti.h0; curJ = __ldg(a.p2j + rec.x + lane) - ti.h0; }
+	unsigned int cur = 0;
+	if (s0 + wid < s1 && lane < rec.y) cur = __ldg(a.off + rec.x + lane);
+	// operand addresses of this lane: base + (offset of the product's block) * mul -- padding lanes read sm.zero
+	const double* aBase = inAB ? sm.V + fo : sm.zero;
+	const int aMul = inAB ? 1 : 0;
 	for (int s = s0 + wid; s < s1; s += WARPS) {
 		const int4 recNN = s + 2 * WARPS < s1 ? __ldg(a.segRec + s + 2 * WARPS) : none;
-		int nxtI = -1, nxtJ = -1;
-		if (s + WARPS < s1 && lane < recN.y) { nxtI = __ldg(a.p2i + recN.x + lane) - ti.h0; nxtJ = __ldg(a.p2j + recN.x + lane) - ti.h0; }
-		const bool diag = rec.w != 0;
+		unsigned int nxt = 0;
+		if (s + WARPS < s1 && lane < recN.y) nxt = __ldg(a.off + recN.x + lane);
+		const bool diag = (rec.w & 1) != 0;
+		// column 6 of the B fragment carries u on diagonal destinations (there the product pairs a block with itself)
+		const bool useU = diag && g == 6 && q < 3;
+		const double* bBase = inAB ? sm.V + fo : (useU ? sm.V + 18 + q : sm.zero);
+		const int bMul = (inAB || useU) ? 1 : 0;
 		// four independent accumulator pairs (products u, u+1, u+2, u+3 of every group of four): the chains of dependent
 		// shuffle -> shared load -> DMMA overlap; the grouping is fixed, so the sum is reproducible
 		double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
 		const int n0 = rec.x, n1 = rec.x + rec.y;
-		// operand address of this lane inside a staged block: V(g,q) for the 6x3 part, u(q) in column 6 of diagonal destinations
-		const bool useU = diag && g == 6 && q < 3;
-		const double* aBase = sm.V + (inAB ? fo : 0);
-		const double* bBase = inAB ? sm.V + fo : sm.u + (q < 3 ? q : 0);
-		const int bMul = inAB ? 18 : 3;
-		const bool bSelJ = inAB, bUse = inAB || useU;
-		bool slow = false;
-		for (int nb0 = n0; nb0 < n1; nb0 += 32) {
-			// 32 products' block indices at a time, broadcast lane by lane
-			const int nn = n1 - nb0 < 32 ? n1 - nb0 : 32;
-			int myI = curI, myJ = curJ;                          // the first 32 were prefetched
-			if (nb0 > n0) { myI = -1; myJ = -1; if (lane < nn) { myI = __ldg(a.p2i + nb0 + lane) - ti.h0; myJ = __ldg(a.p2j + nb0 + lane) - ti.h0; } }
-			if (__any_sync(0xffffffffu, myI >= TL || myJ >= TL)) slow = true;
-			// branch-free: every lane loads one A and one B operand from a valid shared-memory address and zeroes what it must not use
-#define CUBA_S5_STEP(U, C0, C1)                                                                        \
-			{                                                                                          \
-				const int bi = __shfl_sync(0xffffffffu, myI, (U)), bj = __shfl_sync(0xffffffffu, myJ, (U));   \
-				const bool st = (unsigned)bi < (unsigned)TL && (unsigned)bj < (unsigned)TL;            \
-				const int ci = st ? bi : 0, cj = st ? bj : 0;                                          \
-				const double la = aBase[18 * ci];                                                      \
-				const double lb = bBase[bMul * (bSelJ ? cj : ci)];                                     \
-				dmma884(C0, C1, (st && inAB) ? la : 0.0, (st && bUse) ? lb : 0.0);                     \
-			}
-			int u = 0;
-			for (; u + 4 <= nn; u += 4) {
-				CUBA_S5_STEP(u, c0, c1) CUBA_S5_STEP(u + 1, d0, d1) CUBA_S5_STEP(u + 2, e0, e1) CUBA_S5_STEP(u + 3, f0, f1)
-			}
-			for (; u < nn; u++) CUBA_S5_STEP(u, c0, c1)
+		if (!(rec.w & 2)) {
+			for (int nb0 = n0; nb0 < n1; nb0 += 32) {
+				const int nn = n1 - nb0 < 32 ? n1 - nb0 : 32;
+				unsigned int my = cur;                            // the first 32 were prefetched
+				if (nb0 > n0) { my = 0; if (lane < nn) my = __ldg(a.off + nb0 + lane); }
+#define CUBA_S5_STEP(U, C0, C1)                                                                   \
+				{                                                                                 \
+					const unsigned int o = __shfl_sync(0xffffffffu, my, (U));                     \
+					dmma884(C0, C1, aBase[(o & 0xffffu) * aMul], bBase[(o >> 16) * bMul]);        \
+				}
+				int u = 0;
+				for (; u + 4 <= nn; u += 4) {
+					CUBA_S5_STEP(u, c0, c1) CUBA_S5_STEP(u + 1, d0, d1) CUBA_S5_STEP(u + 2, e0, e1) CUBA_S5_STEP(u + 3, f0, f1)
+				}
+				for (; u < nn; u++) CUBA_S5_STEP(u, c0, c1)
 #undef CUBA_S5_STEP
-		}
-		c0 = (c0 + d0) + (e0 + f0); c1 = (c1 + d1) + (e1 + f1);
-		if (slow) {
-			// products with a block past the staged range (a landmark with more observations than the window's slack):
-			// operands straight from global memory, V(g,q) = sum_{m>=q} Hpl(g,m) L(m,q)
+			}
+			c0 = (c0 + d0) + (e0 + f0); c1 = (c1 + d1) + (e1 + f1);
+		} else {
+			// a segment with a block past the staged range (a landmark with more observations than the window's slack):
+			// every operand straight from global memory, V(g,q) = sum_{m>=q} Hpl(g,m) L(m,q)
 			for (int n = n0; n < n1; n++) {
-				const int bi = __ldg(a.p2i + n) - ti.h0, bj = __ldg(a.p2j + n) - ti.h0;
-				if (bi < TL && bj < TL) continue;
-				const int lmg = a.hplLm[ti.h0 + bi];
+				const int bi = __ldg(a.p2i + n), bj = __ldg(a.p2j + n);
+				const int lmg = a.hplLm[bi];
 				const double* iv = a.invHll + 9 * (size_t)lmg;
 				const double B[6] = { iv[0], iv[3], iv[6], iv[4], iv[7], iv[8] };
 				double L[6];
@@ -189,8 +204,8 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_schur_tiles_mma(const Args a)
 				const double lq0 = q == 0 ? L[0] : 0.0, lq1 = q == 0 ? L[1] : (q == 1 ? L[3] : 0.0), lq2 = q == 0 ? L[2] : (q == 1 ? L[4] : L[5]);
 				double av = 0.0, bv = 0.0;
 				if (inAB) {
-					const double* gi = a.Hpl + 18 * (size_t)(ti.h0 + bi);
-					const double* gj = a.Hpl + 18 * (size_t)(ti.h0 + bj);
+					const double* gi = a.Hpl + 18 * (size_t)bi;
+					const double* gj = a.Hpl + 18 * (size_t)bj;
 					av = gi[g] * lq0 + gi[6 + g] * lq1 + gi[12 + g] * lq2;
 					bv = gj[g] * lq0 + gj[6 + g] * lq1 + gj[12 + g] * lq2;
 				} else if (useU) {
@@ -206,7 +221,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_schur_tiles_mma(const Args a)
 			if (q < 3) { out[(2 * q) * 6 + g] = c0; out[(2 * q + 1) * 6 + g] = c1; }
 			else out[36 + g] = c0;
 		}
-		rec = recN; recN = recNN; curI = nxtI; curJ = nxtJ;
+		rec = recN; recN = recNN; cur = nxt;
 	}
 }
 

@@ -72,18 +72,22 @@ typedef struct cuba_config {
 	int use_fp32;          /* 0 = fp64 (default); 1 = reference's USE_FLOAT32 behaviour           */
 	int pcg_max_iters;     /* <=0: default                                         */
 	double pcg_tol;        /* stop when sqrt(r'z / r0'z0) <= pcg_tol; <=0: default 1e-11 (fp64)    */
-	int deterministic;     /* 1 (default): fixed-order reductions, bit-reproducible run to run     */
-	int reserved[7];       /* reserved[0]: reduced-system solver.  0 (default) = automatic: block-Jacobi PCG (k_pcg3: shared-memory
-	                          resident, flag-synchronised exchange, no barrier in the iteration) while it converges within
-	                          reserved[5] iterations, two-level PCG afterwards (k_pcg4: block-Jacobi + coarse correction over
-	                          rigid motions of pose aggregates, cuba_pcg4.cuh); 3 = always k_pcg4; 4 = always k_pcg3;
-	                          2 = k_pcg2 (one grid barrier per iteration); 1 = k_pcg (first generation)
+	int deterministic;     /* kept for layout compatibility; every kernel sums in a fixed order: results are bit-reproducible run to run */
+	int reserved[7];       /* reserved[0]: reduced-system solver.  0 (default) = automatic: block-Jacobi PCG while a solve converges within
+	                          reserved[5] iterations (k_pcg3 on one GPU: shared-memory resident, flag-synchronised exchange, no barrier
+	                          in the iteration), two-level PCG afterwards (k_pcg5, cuba_pcg5.cuh: block-Jacobi + coarse correction
+	                          over rigid motions of pose aggregates in the same flag-synchronised protocol).  With several ranks and
+	                          >= 2048 free poses k_pcg5 runs with the block rows DISTRIBUTED over the ranks (NVLink peer boards);
+	                          7 = never distribute (replicated solve), 8 = always distribute.  5 = always two-level k_pcg5,
+	                          6 = always block-Jacobi k_pcg5, 3 = always k_pcg4 (two-level, one grid barrier per iteration),
+	                          4 = always k_pcg3, 2 = k_pcg2 (one grid barrier per iteration), 1 = k_pcg (first generation)
 	                          reserved[1]: 1 = build the index structures on the host (cuba_structure.cpp) instead of
 	                          on the device (cuba_structure_gpu.cuh, default); both give identical structures
 	                          reserved[2]: J+H landmark kernel, 0 = k_linearize_landmark4 (warp tiles, default; 8/9 = 5/6 CTAs per SM,
 	                          7 = three pipeline stages), 6 = k_linearize_landmark3, 5 = ..._landmark2, 1-4 = first generation
 	                          reserved[3]: Schur kernel, 0 = k_schur3 (six lanes per product, default), 1 = k_schur (lane per product),
-	                          2 = tile-local pair (cuba_schur2.cuh), 4 = k_schur4 (cooperative loads; slower)
+	                          2 = tile-local pair (cuba_schur2.cuh), 4 = k_schur4 (cooperative loads; slower), 5 = landmark tiles on the
+	                          fp64 tensor pipe (cuba_schur5.cuh, DMMA m8n8k4; wins only on banded graphs)
 	                          reserved[4]: two-level PCG: solves between rebuilds of the coarse matrix (<=0: 8)
 	                          reserved[5]: automatic solver: block-Jacobi iteration count that switches to two-level (<=0: 100)
 	                          reserved[6]: two-level PCG: upper bound on the number of pose aggregates (<=0: 74; <= 37 uses the one-CTA inverse) */

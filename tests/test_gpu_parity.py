@@ -298,14 +298,14 @@ def test_device_and_host_structure_builders_agree(pkg, problems, name):
 
 @pytest.mark.parametrize("name", ["small", "kitti07_shaped", "ba_kitti_00"])
 def test_schur_kernels_agree(pkg, oracle, problems, name):
-    """landmark tiles on the fp64 tensor pipe (cuba_schur5.cuh, default) vs k_schur3 (six lanes per product) vs k_schur4
+    """k_schur3 (six lanes per product, default) vs landmark tiles on the fp64 tensor pipe (cuba_schur5.cuh, DMMA) vs k_schur4
     (+ cooperative loads, same bits as k_schur3) vs k_schur (lane per product) vs the tile-local pair without tensor cores
     (cuba_schur2.cuh) vs the oracle"""
     if name.startswith("ba_") and not have_fixture(name):
         pytest.skip("reference fixture absent")
     prob = problems(name); rk = KERNELS["huber"]
     a = make_engine(pkg, prob, rk, schur_variant=2); b = make_engine(pkg, prob, rk, schur_variant=3); c = make_engine(pkg, prob, rk, schur_variant=1)
-    d = make_engine(pkg, prob, rk, schur_variant=4); e = make_engine(pkg, prob, rk)
+    d = make_engine(pkg, prob, rk, schur_variant=4); e = make_engine(pkg, prob, rk, schur_variant=5)
     o = oracle.Oracle(prob, *rk)
     a.linearize(); b.linearize(); c.linearize(); d.linearize(); e.linearize(); o.compute_errors(); o.build_system()
     for lam in (1e3, 1.0):
