@@ -189,7 +189,23 @@ class Runner:
             prob = dataclasses.replace(prob, q=q, t=t, Xw=Xw)
         prob = pin_problem(prob)
         stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=self.local)
-        # ---------------- e2e: host buffers -> set_problem (H2D + structure) -> optimize -> get_state (D2H)
+        # ---------------- e2e with structure reuse (the product's default: an unchanged topology keeps every device structure)
+        reuse_ms = []
+        eng.initialize(prob)
+        for i in range(2 + steps):
+            self.barrier()
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            eng.initialize(prob)
+            eng.optimize(LM_ITERS)
+            eng.state()
+            b.record(stream)
+            self.barrier()
+            if i >= 2:
+                reuse_ms.append(self.max_over_ranks(a.elapsed_time(b)))
+        reuses = eng.structure_reuses()
+        # ---------------- e2e: host buffers -> set_problem (H2D + FULL structure build, like the reference) -> optimize -> get_state (D2H)
+        eng.set_structure_reuse(False)
         e2e_ms, e2e_iters, h2d0, d2h0 = [], LM_ITERS, 0, 0
         for i in range(warmup + steps):
             if i == warmup:
@@ -237,7 +253,9 @@ class Runner:
                "launches": launches,
                "e2e": {"value": E * e2e_iters / e2e_t, "unit": "edge-iterations/s", "ms_per_step": 1e3 * e2e_t,
                        "h2d_bytes_per_step": (h2d1 - h2d0) // max(steps, 1), "d2h_bytes_per_step": (d2h1 - d2h0) // max(steps, 1),
-                       "window": "set_problem(H2D from pinned host buffers + structure build) + optimize(10) + get_state(D2H) == reference's initialize()+optimize(10)"},
+                       "window": "set_problem(H2D from pinned host buffers + full structure build, structure reuse switched OFF) + optimize(10) + get_state(D2H) == reference's initialize()+optimize(10)"},
+               "e2e_reuse": {"value": E * e2e_iters / (float(np.mean(reuse_ms)) * 1e-3), "unit": "edge-iterations/s", "ms_per_step": float(np.mean(reuse_ms)), "structure_reuses": reuses,
+                             "window": "the same window with the engine's default structure reuse: the topology is unchanged between calls, so set_problem only uploads values (SURVEY 8 f-2)"},
                "profile_ms_e2e_step": {k: round(1e3 * v, 4) for k, v in prof.items()}, "prob": prob}
         # ---------------- roofline of the J+H landmark-pass kernel + per-stage device times (L2 flushed between reps)
         if stages:
@@ -269,7 +287,7 @@ def cpu_reference_chi2(prob, rk):
     return chi, prob.nedges * len(chi) / dt, dt
 
 
-def run_e2e_cpp(pkg, workload, graph, robust, steps, warmup):
+def run_e2e_cpp(pkg, workload, graph, robust, steps, warmup, reuse=True):
     """initialize()+optimize(10) through cuba::CudaBundleAdjustment: the sample binary times the window itself (--repeat)"""
     tmp = tempfile.mkdtemp(prefix="cuba_bench_")
     exe = os.path.join(tmp, "sample_ba_from_file")
@@ -281,8 +299,11 @@ def run_e2e_cpp(pkg, workload, graph, robust, steps, warmup):
         if not workload.startswith("ba_"):
             path = os.path.join(tmp, workload + ".cubagraph")
             pkg.graphio.write_graph(path, graph)
+        env = dict(os.environ)
+        if not reuse:
+            env["CUBA_NO_STRUCTURE_REUSE"] = "1"
         res = subprocess.run([exe, path, "--json", "--repeat", str(warmup + steps)] + (["--huber"] if robust == "huber" else []),
-                             capture_output=True, text=True, timeout=900)
+                             capture_output=True, text=True, timeout=900, env=env)
         if res.returncode != 0:
             return {"error": res.stderr[-300:]}
         r = json.loads(res.stdout)
@@ -290,6 +311,7 @@ def run_e2e_cpp(pkg, workload, graph, robust, steps, warmup):
         sec = float(np.mean(secs))
         return {"value": r["nedges"] * len(r["chi2"]) / sec, "unit": "edge-iterations/s", "ms_per_step": 1e3 * sec, "final_chi2": r["chi2"][-1],
                 "profile_ms": {k: round(1e3 * v, 4) for k, v in r["profile"].items()},
+                "structure_reuse": bool(reuse),
                 "window": "cuba::CudaBundleAdjustment::initialize() + optimize(10) (pointer graph -> flat arrays -> C ABI), wall clock inside samples/sample_ba_from_file --repeat"}
     except Exception as ex:   # the C++ leg must never take the bench line down
         return {"error": str(ex)[-300:]}
@@ -439,7 +461,7 @@ def main():
                        "parallelism": "landmark-sharded x%d%s" % (world, ", reduced system row-distributed over the ranks (k_pcg5, NVLink peer boards)" if world > 1 and sizes["numP"] >= 2048 else ""),
                        "protocol": "reference: warm-up optimize(1) written back, then initialize()+optimize(10)" if args.protocol_warmup else "initialize()+optimize(10) from the generated estimate",
                        "pcg_iterations_per_step": m["pcg_iterations_per_step"], "final_chi2": m["final_chi2"]},
-            "e2e": m["e2e"], "gpu_launches": m["launches"], "clocks": clocks.summary(), "roofline": m["roofline"], "stage_ms": m["stage_ms"],
+            "e2e": m["e2e"], "e2e_reuse": m["e2e_reuse"], "gpu_launches": m["launches"], "clocks": clocks.summary(), "roofline": m["roofline"], "stage_ms": m["stage_ms"],
             "profile_ms_e2e_step": m["profile_ms_e2e_step"],
             "pcg": {"iterations_per_step": m["pcg_iterations_per_step"], "ms_per_step": m["pcg_ms_per_step"], "us_per_iteration": m["pcg_us_per_iteration"]},
             "chi2_per_iteration": m["chi2"], "chi2_rel_diff_vs_oracle": chi_rel, "oracle": oracle_kind}
@@ -453,7 +475,8 @@ def main():
 
     # ---------------- e2e through the drop-in C++ class (one GPU)
     if world == 1 and rank == 0 and not args.no_cpp and not args.fp32:
-        line["e2e_cpp"] = run_e2e_cpp(pkg, args.workload, graph, args.robust, args.steps, args.warmup)
+        line["e2e_cpp"] = run_e2e_cpp(pkg, args.workload, graph, args.robust, args.steps, args.warmup, reuse=False)
+        line["e2e_cpp_reuse"] = run_e2e_cpp(pkg, args.workload, graph, args.robust, args.steps, args.warmup, reuse=True)
 
     # ---------------- the other BASELINE configs, each measured here (one GPU) / the KITTI-sized graph beside the 10 M-edge one (several GPUs)
     if not args.no_configs and not explicit and not args.fp32:

@@ -47,7 +47,7 @@ _lib = None
 
 _SYMBOLS = [
     "cuba_last_error", "cuba_version", "cuba_engine_create", "cuba_engine_destroy", "cuba_engine_set_robust_kernel",
-    "cuba_comm_unique_id", "cuba_engine_set_comm", "cuba_engine_set_problem", "cuba_engine_set_state", "cuba_engine_get_sizes", "cuba_engine_reset_state", "cuba_engine_get_stream", "cuba_engine_flush_l2",
+    "cuba_comm_unique_id", "cuba_engine_set_comm", "cuba_engine_set_problem", "cuba_engine_set_structure_reuse", "cuba_engine_get_structure_reuses", "cuba_engine_set_state", "cuba_engine_get_sizes", "cuba_engine_reset_state", "cuba_engine_get_stream", "cuba_engine_flush_l2",
     "cuba_engine_optimize", "cuba_engine_get_state", "cuba_engine_get_chi2", "cuba_engine_get_profile",
     "cuba_engine_get_launch_count", "cuba_get_transfer_bytes", "cuba_stage_linearize", "cuba_stage_max_diagonal", "cuba_stage_solve", "cuba_stage_update",
     "cuba_stage_commit", "cuba_stage_chi2", "cuba_debug_get_hpl_structure", "cuba_debug_get_hsc_structure",
@@ -77,6 +77,8 @@ def load_library():
         "cuba_comm_unique_id": [vp],
         "cuba_engine_set_comm": [vp, i, i, vp],
         "cuba_engine_set_problem": [vp, C.POINTER(_Problem)],
+        "cuba_engine_set_structure_reuse": [vp, i],
+        "cuba_engine_get_structure_reuses": [vp, C.POINTER(C.c_longlong)],
         "cuba_engine_set_state": [vp, vp, vp, vp],
         "cuba_engine_get_sizes": [vp, C.POINTER(_Sizes)],
         "cuba_engine_reset_state": [vp],
@@ -232,6 +234,14 @@ class Engine:
         self.sizes = {n: getattr(sz, n) for n, _ in _Sizes._fields_}
         self._stats = []
         return self.sizes
+
+    def set_structure_reuse(self, enable):
+        _check(self.L.cuba_engine_set_structure_reuse(self.h, int(bool(enable))))
+
+    def structure_reuses(self):
+        n = C.c_longlong(0)
+        _check(self.L.cuba_engine_get_structure_reuses(self.h, C.byref(n)))
+        return n.value
 
     def set_state(self, q, t, Xw):
         q, t, Xw = (np.ascontiguousarray(a, dtype=np.float64) for a in (q, t, Xw))

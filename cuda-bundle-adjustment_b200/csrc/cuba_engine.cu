@@ -42,6 +42,16 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 		}                                                                                                   \
 	} while (0)
 
+// launches a 1-D kernel over n items on the engine's stream (used inside Engine<T> member functions)
+#define KLAUNCH(kernel, n, ...)                                                             \
+	do {                                                                                     \
+		if ((n) > 0) {                                                                       \
+			kernel<<<sgpu::grid_for(n), sgpu::BLK, 0, stream>>>(__VA_ARGS__);                 \
+			launches++;                                                                      \
+			CUDA_TRY(cudaGetLastError());                                                    \
+		}                                                                                    \
+	} while (0)
+
 static thread_local long long g_h2dBytes = 0, g_d2hBytes = 0;   // host<->device traffic of this thread's engines
 
 // Pinned staging arena for the many small host->device uploads of the PCG setup: a cudaMemcpyAsync from pageable
@@ -151,6 +161,8 @@ struct EngineBase {
 	int rk_type[2] = { 0, 0 };
 	double rk_delta[2] = { 0, 0 };
 	int rank = 0, world = 1;
+	bool structureReuse = true;   // cuba_engine_set_structure_reuse
+	long long structureReuses = 0;
 	int devOrdinal = 0;      // CUDA device every call of this engine runs on (set once in init)
 	void* comm = nullptr;
 	bool haveProblem = false;
@@ -377,7 +389,17 @@ struct Engine : EngineBase {
 			(p->E3 > 0 && (!p->idx3 || !p->meas3 || !p->omega3)))
 			return fail(CUBA_ERR_INVALID, "set_problem: null array with a non-zero count");
 		const auto t0 = std::chrono::steady_clock::now();
+		// Same topology as the problem this engine already holds (sizes, fixed/free split and every (iP, iL) pair identical): only the
+		// numbers changed -- the estimate after a previous optimize(), new measurements -- so every index structure, tile list,
+		// product list and PCG partition on the device stays valid.  Upload the values and re-run the three kernels that scatter them.
+		if (structureReuse && reusable && haveProblem && cfg.reserved[1] != 1 && same_topology(p)) {
+			int rc = refresh_values(p); if (rc) return rc;
+			structureReuses++;
+			prof[CUBA_PROF_BUILD_STRUCTURE] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+			return CUBA_OK;
+		}
 		haveProblem = false;
+		reusable = false;
 		hostStructureValid = false;
 		shardBoundValid = false;
 		// landmark-tile variant: 0/1 = 256 edges, 2 CTAs/SM; 2 = 256, 3 CTAs/SM; 3 = 128, 4 CTAs/SM; 4 = 128, 6 CTAs/SM
@@ -416,6 +438,47 @@ struct Engine : EngineBase {
 		const auto t1 = std::chrono::steady_clock::now();
 		prof[CUBA_PROF_BUILD_STRUCTURE] += std::chrono::duration<double>(t1 - t0).count();
 		haveProblem = true;
+		if (cfg.reserved[1] != 1 && structureReuse) {
+			lastIdx2.assign(p->idx2, p->idx2 + 2 * (size_t)p->E2); lastIdx3.assign(p->idx3, p->idx3 + 2 * (size_t)p->E3);
+			const int sz[6] = { p->Pall, p->numP, p->Lall, p->numL, p->E2, p->E3 };
+			memcpy(lastSizes, sz, sizeof(sz));
+			reusable = true;
+		}
+		return CUBA_OK;
+	}
+
+	bool same_topology(const cuba_problem* p) const
+	{
+		const int sz[6] = { p->Pall, p->numP, p->Lall, p->numL, p->E2, p->E3 };
+		if (memcmp(sz, lastSizes, sizeof(sz)) != 0) return false;
+		if (p->E2 > 0 && memcmp(p->idx2, lastIdx2.data(), sizeof(int32_t) * 2 * (size_t)p->E2) != 0) return false;
+		if (p->E3 > 0 && memcmp(p->idx3, lastIdx3.data(), sizeof(int32_t) * 2 * (size_t)p->E3) != 0) return false;
+		return true;
+	}
+
+	// set_problem on an unchanged topology: measurements, information values and the estimate go up, the edge streams are re-scattered
+	int refresh_values(const cuba_problem* p)
+	{
+		using namespace sgpu;
+		const int E2 = p->E2, E3 = p->E3, eL = S.eLocal;
+		CUDA_TRY(g_meas2.upload(p->meas2, 2 * (size_t)E2, stream)); CUDA_TRY(g_meas3.upload(p->meas3, 3 * (size_t)E3, stream));
+		CUDA_TRY(g_om2.upload(p->omega2, (size_t)E2, stream)); CUDA_TRY(g_om3.upload(p->omega3, (size_t)E3, stream));
+		int rc = upload_state(p->q, p->t, p->cam, p->Xw); if (rc) return rc;
+		KLAUNCH(k_edge_stream<T>, eL, g_keyS.p, g_valS.p, g_ff.p, g_hplG.p, savedKBeg, eL, S.hplBase, E2, g_meas2.p, g_om2.p, g_meas3.p, g_om3.p,
+			e_user.p, e_ip.p, e_il.p, e_hpl.p, e_mx.p, e_my.p, e_mz.p, e_om.p);
+		KLAUNCH(k_pose_stream<T>, eL, g_psrc.p, posePtr.p, S.numP, eL, e_ip.p, e_il.p, e_mx.p, e_my.p, e_mz.p, e_om.p, p_il.p, p_mx.p, p_my.p, p_mz.p, p_om.p);
+		if constexpr (sizeof(T) == 8) {
+			if (jhV4 && ntW > 0) {
+				const int lb = S.lmBeg, N = S.lmEnd - S.lmBeg;
+				KLAUNCH(jh4::k_emit, (long long)N * 32, w_start.p, w_pieces.p, w_base.p, N, lmPtr.p, lb, w_levels.p,
+					e_mx.p, e_my.p, e_mz.p, e_om.p, e_ip.p, e_il.p, e_hpl.p, w_tile.p, w_rec.p, w_tilePose.p, w_tilePieces.p);
+			}
+		}
+		CUDA_TRY(cudaStreamSynchronize(stream));      // the caller's buffers are free again
+		cur = 0; trialValid = false;
+		tlActive = false; coarseValid = false; coarseAge = 0; p5CoarseValid = false; p5CoarseAge = 0;
+		resolveProfile();
+		for (int i = 0; i < CUBA_PROF_NUM; i++) prof[i] = 0;
 		return CUBA_OK;
 	}
 
@@ -462,6 +525,11 @@ struct Engine : EngineBase {
 	DBuf<sgpu::Meta> g_meta;
 	sgpu::Meta* hMeta = nullptr;
 	bool hostStructureValid = false;
+	// structure reuse across set_problem calls (repeated local BA on an unchanged graph): the last problem's index lists
+	std::vector<int32_t> lastIdx2, lastIdx3;
+	int lastSizes[6] = { -1, -1, -1, -1, -1, -1 };
+	int savedKBeg = 0;
+	bool reusable = false;      // the device structures of the last problem are complete and were built on the device
 	int shardBound[9] = { 0 };    // first landmark of every rank's shard
 	bool shardBoundValid = false;
 
@@ -496,14 +564,6 @@ struct Engine : EngineBase {
 		if (hMeta->error == 3) return fail(CUBA_ERR_INVALID, "build_structure: free landmark without edges (the reference's initialize() drops such vertices)");
 		return CUBA_OK;
 	}
-#define KLAUNCH(kernel, n, ...)                                                             \
-	do {                                                                                     \
-		if ((n) > 0) {                                                                       \
-			kernel<<<sgpu::grid_for(n), sgpu::BLK, 0, stream>>>(__VA_ARGS__);                 \
-			launches++;                                                                      \
-			CUDA_TRY(cudaGetLastError());                                                    \
-		}                                                                                    \
-	} while (0)
 
 	int build_on_gpu(const cuba_problem* p)
 	{
@@ -539,6 +599,7 @@ struct Engine : EngineBase {
 		for (int r = 0; r < 9; r++) shardBound[r] = hMeta->bounds[r];
 		shardBoundValid = true;
 		const int kBeg = hMeta->kBeg, kEnd = hMeta->kEnd, eL = S.eLocal, nhpl = S.nhpl;
+		savedKBeg = kBeg;
 		CUDA_TRY(g_hplRowInd.alloc(nhpl)); CUDA_TRY(g_hplLmG.alloc(nhpl)); CUDA_TRY(g_edge2Hpl.alloc(E)); CUDA_TRY(g_hplColPtr.alloc((size_t)numL + 1));
 		KLAUNCH(k_hpl_global, E, g_keyS.p, g_valS.p, g_ff.p, g_hplG.p, E, g_hplRowInd.p, g_hplLmG.p, g_edge2Hpl.p);
 		KLAUNCH(k_hpl_colptr, numL + 1, g_lmPtrG.p, g_hplG.p, E, numL, nhpl, g_hplColPtr.p);
@@ -1310,7 +1371,8 @@ struct Engine : EngineBase {
 	Pcg5Dims p5Dims{}, p5DimsBJ{};
 	size_t p5Smem = 0;
 	int p5G = 0, p5W = 1, p5A = 0, p5Gs = 1;
-	bool p5Ok = false, p5Dist = false, p5Cluster = false;
+	bool p5Ok = false, p5Dist = false;
+	int p5Cluster = 0;                             // CTAs of the cluster that factors the coarse matrix (0: one CTA)
 	bool p5CoarseValid = false; int p5CoarseAge = 0; double p5CoarseLambda = 0;
 	size_t p5InvSmem = 0;
 	long long p5TagBound = 0;                      // conservative host-side bound on the device tag base
@@ -1379,7 +1441,7 @@ struct Engine : EngineBase {
 		const size_t budget = (size_t)smemMax > 4096 ? (size_t)smemMax - 2048 : 0;   // static arrays of k_pcg5: < 1 KB
 		// rows over world x G virtual CTAs (about eight rows each, never more than 42: one thread per (row, component) pair in the
 		// row sums), rank-aligned aggregates, halo masks: cuba_structure.cpp (CPU-tested through cuba_debug_pcg5_plan)
-		const int maxAgg = (cfg.reserved[6] > 0 && cfg.reserved[6] < PCG4_MAXAGG) ? cfg.reserved[6] : PCG4_MAXAGG;
+		const int maxAgg = (cfg.reserved[6] > 0 && cfg.reserved[6] < PCG5_MAXAGG) ? cfg.reserved[6] : PCG5_MAXAGG;
 		Pcg5Plan plan;
 		build_pcg5_plan(numP, S.nfull, S.fRowPtr, S.fColInd, W, numSMs, maxAgg, PCG5_BLOCK / 6, plan);
 		if (!plan.ok) return CUBA_OK;
@@ -1413,13 +1475,21 @@ struct Engine : EngineBase {
 		if (perSM < 1) return CUBA_OK;
 		if (getenv("CUBA_PCG_VERBOSE")) fprintf(stderr, "pcg5: world %d G %d gs %d A %d needMax %d maxRows %d blkMax %d maxNeedAgg %d zhInSmem %d sliceRows %d cap %d smem %zu\n",
 			W, G, gs, A, d.needMax, d.maxRows, PP.blkMax, d.maxNeedAgg, d.zhInSmem, d.sliceRows, d.capBlocks, p5Smem);
-		// coarse inverse: packed block triangle in the shared memory of one CTA (A <= 37) or of an 8-CTA cluster
-		p5Cluster = A > PCG4_MAXAGG1;
+		// coarse inverse: packed block triangle in the shared memory of one CTA (A <= 37), of an 8-CTA cluster (A <= 74) or of a
+		// 16-CTA cluster (A <= 148; non-portable cluster size)
+		p5Cluster = A > PCG4_MAXAGG1 ? (A > PCG4_MAXAGG ? 16 : 8) : 0;
 		const size_t nblkPz = (size_t)A * (A + 1) / 2;
-		p5InvSmem = p5Cluster ? (((nblkPz + PCG4_CL - 1) / PCG4_CL + 2 * (size_t)A) * 36 * sizeof(double) + 2 * nblkPz + 16) : ((nblkPz + 2 * (size_t)A) * 36 * sizeof(double));
+		if (p5Cluster) {
+			const size_t nloc = (nblkPz + p5Cluster - 1) / p5Cluster;
+			p5InvSmem = nloc * 36 * sizeof(double) + 2 * nloc + 16;
+		} else p5InvSmem = (nblkPz + 2 * (size_t)A) * 36 * sizeof(double);
 		if (p5InvSmem + 1024 > (size_t)smemMax) return CUBA_OK;
-		if (p5Cluster) CUDA_TRY(cudaFuncSetAttribute(k_coarse_chol_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(p5InvSmem, pcg4Cluster ? pcg4InvSmem : 0)));
+		if (p5Cluster == 16) {
+			CUDA_TRY(cudaFuncSetAttribute(k_coarse_chol_cluster2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p5InvSmem));
+			CUDA_TRY(cudaFuncSetAttribute(k_coarse_chol_cluster2<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+		} else if (p5Cluster == 8) CUDA_TRY(cudaFuncSetAttribute(k_coarse_chol_cluster2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p5InvSmem));
 		else CUDA_TRY(cudaFuncSetAttribute(k_coarse_invert<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(p5InvSmem, (!pcg4Cluster && pcg4Ok) ? pcg4InvSmem : 0)));
+		if ((size_t)A * 36 * sizeof(double) > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_coarse_trinv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)A * 36 * sizeof(double))));
 		CUDA_TRY(p5CtaRow.upload(PP.rows, stream, arena)); CUDA_TRY(p5NeedPtr.upload(PP.nptr, stream, arena)); CUDA_TRY(p5NeedCol.upload(PP.ncol, stream, arena));
 		CUDA_TRY(p5Local.upload(PP.local, stream, arena)); CUDA_TRY(p5RowPeers.upload(peers, stream, arena));
 		CUDA_TRY(p5AggRow.upload(CP.aggRow, stream, arena)); CUDA_TRY(p5NaPtr.upload(CP.naPtr, stream, arena)); CUDA_TRY(p5NaList.upload(CP.naList, stream, arena));
@@ -1457,14 +1527,21 @@ struct Engine : EngineBase {
 	}
 
 	// coarse matrix Ac = Z^T S Z of the current system and its inverse (fp32), for the aggregates behind (cbPtr, cbList)
-	int launch_coarse_setup(int A, bool cluster, size_t invSmem, const int* cbPtr, const int* cbList, double* AcP, float* AcInv, double* Lp, double* Ld, double* Wp)
+	int launch_coarse_setup(int A, int cluster, size_t invSmem, const int* cbPtr, const int* cbList, double* AcP, float* AcInv, double* Lp, double* Ld, double* Wp)
 	{
 		const int nblkP = A * (A + 1) / 2;
 		KLAUNCH(k_coarse_project<T>, 36LL * S.nfull, fVal.p, cRowOf.p, fColInd.p, S.nfull, cZx.p, cU.p);
 		KLAUNCH(k_coarse_assemble, (long long)nblkP * 36, cbPtr, cbList, cU.p, nblkP, AcP);
 		if (cluster) {
-			// Cholesky in the shared memory of an 8-CTA cluster, then the triangular inverse (one CTA per block column) and W^T W on the whole chip
-			k_coarse_chol_cluster<<<PCG4_CL, 1024, invSmem, stream>>>(AcP, A, Lp, Ld, AcInv, cInfo.p);
+			// Cholesky in the shared memory of an 8- or 16-CTA cluster, then the triangular inverse (one CTA per block column) and W^T W on the whole chip
+			cudaLaunchConfig_t lc = {};
+			lc.gridDim = dim3(cluster); lc.blockDim = dim3(1024); lc.dynamicSmemBytes = invSmem; lc.stream = stream;
+			cudaLaunchAttribute at[1];
+			at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+			lc.attrs = at; lc.numAttrs = 1;
+			int* infoP = cInfo.p;
+			if (cluster == 16) CUDA_TRY(cudaLaunchKernelEx(&lc, k_coarse_chol_cluster2<16>, (const double*)AcP, A, Lp, Ld, AcInv, infoP));
+			else CUDA_TRY(cudaLaunchKernelEx(&lc, k_coarse_chol_cluster2<8>, (const double*)AcP, A, Lp, Ld, AcInv, infoP));
 			k_coarse_trinv<<<A, 256, (size_t)A * 36 * sizeof(double), stream>>>(Lp, Ld, A, Wp, cInfo.p);
 			k_coarse_wtw<<<(nblkP * 36 + 255) / 256, 256, 0, stream>>>(Wp, A, AcInv, cInfo.p);
 			launches += 2;
@@ -1947,6 +2024,7 @@ int cuba_engine_create(const cuba_config* cfg, cuba_engine** out)
 	if (c.use_fp32) { auto* e = new Engine<float>(); e->cfg = c; impl.reset(e); rc = e->init(); }
 	else { auto* e = new Engine<double>(); e->cfg = c; impl.reset(e); rc = e->init(); }
 	if (rc) return rc;
+	if (getenv("CUBA_NO_STRUCTURE_REUSE")) impl->structureReuse = false;   // like-for-like timing against the reference, which rebuilds everything
 	*out = new cuba_engine{ std::move(impl) };
 	return CUBA_OK;
 }
@@ -1992,6 +2070,8 @@ int cuba_engine_set_comm(cuba_engine* e, int rank, int world, const void* uid)
 }
 
 int cuba_engine_set_problem(cuba_engine* e, const cuba_problem* p) { ENGINE_OR_FAIL(e); return e->impl->set_problem(p); }
+int cuba_engine_set_structure_reuse(cuba_engine* e, int enable) { ENGINE_OR_FAIL(e); e->impl->structureReuse = enable != 0; return CUBA_OK; }
+int cuba_engine_get_structure_reuses(cuba_engine* e, long long* count) { ENGINE_OR_FAIL(e); if (count) *count = e->impl->structureReuses; return CUBA_OK; }
 int cuba_engine_set_state(cuba_engine* e, const double* q, const double* t, const double* Xw)
 {
 	ENGINE_OR_FAIL(e);

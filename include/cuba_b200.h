@@ -150,6 +150,12 @@ int cuba_engine_set_comm(cuba_engine* e, int rank, int world, const void* nccl_u
 
 /* Upload the problem and build every index structure (initialize + buildStructure). */
 int cuba_engine_set_problem(cuba_engine* e, const cuba_problem* p);
+/* Structure reuse (on by default): a set_problem whose sizes, fixed/free split and (iP,iL) lists equal those of the
+ * problem the engine already holds keeps every device structure (index lists, tiles, product lists, PCG partition) and only
+ * uploads the numbers -- repeated local-BA calls on an unchanged graph, e.g. the reference protocol's second initialize()
+ * (samples/sample_ba_from_file.cpp:159-161).  The reference rebuilds everything (cpp:263-366).  Results are identical either way. */
+int cuba_engine_set_structure_reuse(cuba_engine* e, int enable);
+int cuba_engine_get_structure_reuses(cuba_engine* e, long long* count);
 /* Replace only the estimate (q,t,Xw), keeping structure -- repeated optimize() on the same graph. */
 int cuba_engine_set_state(cuba_engine* e, const double* q, const double* t, const double* Xw);
 

@@ -342,6 +342,38 @@ def test_bitwise_reproducible(pkg, problems):
         assert np.array_equal(a, b)
 
 
+def test_structure_reuse_across_initialize(pkg, oracle, problems):
+    """SURVEY.md 8 f-2: a second initialize() on an unchanged topology keeps every device structure and only uploads the numbers;
+    bitwise the same trajectory as a fresh engine, also after new measurements / a new estimate; a changed edge list rebuilds"""
+    prob = problems("small"); rk = KERNELS["huber"]
+    fresh = make_engine(pkg, prob, rk); fresh.set_structure_reuse(False)
+    a = [s["chi2"] for s in fresh.optimize(4)]
+    q, t, Xw = fresh.state()
+    p2 = prob.copy(); p2.q, p2.t, p2.Xw = q, t, Xw
+    p2.meas3 = p2.meas3 + 0.25; p2.omega2 = p2.omega2 * 0.5
+    fresh.initialize(p2)
+    b = [s["chi2"] for s in fresh.optimize(4)]
+    assert fresh.structure_reuses() == 0
+    eng = make_engine(pkg, prob, rk)
+    assert [s["chi2"] for s in eng.optimize(4)] == a
+    eng.initialize(p2)                                     # same (iP, iL) lists -> reuse
+    assert eng.structure_reuses() == 1
+    assert [s["chi2"] for s in eng.optimize(4)] == b
+    for x, y in zip(eng.state(), fresh.state()):
+        assert np.array_equal(x, y)
+    assert np.array_equal(eng.chi_squared(), fresh.chi_squared())
+    p3 = p2.copy(); p3.idx3 = p3.idx3.copy(); p3.idx3[[0, 1]] = p3.idx3[[1, 0]]; p3.meas3 = p3.meas3.copy(); p3.meas3[[0, 1]] = p3.meas3[[1, 0]]
+    p3.omega3 = p3.omega3.copy(); p3.omega3[[0, 1]] = p3.omega3[[1, 0]]
+    eng.initialize(p3)                                     # two edges swapped: a different list -> full rebuild, same optimum
+    assert eng.structure_reuses() == 1
+    c = [s["chi2"] for s in eng.optimize(4)]
+    assert np.allclose(c, b, rtol=1e-12)
+    o = oracle.Oracle(p2, *rk)
+    chi, lam, tr = o.optimize(4)
+    assert np.allclose(b, chi, rtol=TOL)
+    eng.close(); fresh.close()
+
+
 def test_reset_and_repeat(pkg, problems):
     prob = problems("small")
     eng = make_engine(pkg, prob, KERNELS["none"])

@@ -11,7 +11,7 @@ for workload in sys.argv[1:] or ["kitti07_shaped", "kitti00_shaped"]:
     path = os.path.join(ROOT, "oracle", "_ref", "fixtures", workload + ".cubagraph")
     g = pkg.graphio.read_graph(path) if workload.startswith("ba_") else pkg.synth.make_config(workload)
     prob = pkg.graphio.flatten(g)
-    for variant, magg in ((5, 0), (6, 0), (3, 0), (4, 0)):
+    for variant, magg in ((5, 0), (5, 74), (4, 0)):
         eng = pkg.Engine(device=0, pcg_variant=variant, max_aggregates=magg)
         eng.initialize(prob)
         eng.linearize()
