@@ -20,6 +20,7 @@
 #include "cuba_pcg3.cuh"
 #include "cuba_pcg4.cuh"
 #include "cuba_pcg5.cuh"
+#include "cuba_coarse_dense.cuh"
 #include "cuba_schur2.cuh"
 #include "cuba_jh4.cuh"
 #include "cuba_schur3.cuh"
@@ -1364,6 +1365,8 @@ struct Engine : EngineBase {
 	DBuf<T> p5Linv, p5R0, p5Zhat, p5RcRow, p5Rc0;
 	DBuf<float> p5AcInv;
 	DBuf<double> p5AcP, p5Lp, p5Wp, p5Ld;
+	DBuf<double> cdM, cdL, cdW, cdDinv;            // dense work matrices of k_coarse_dense
+	bool p5Dense = false;
 	DBuf<unsigned long long> p5Boards;
 	void* p5PeerBase[PCG5_MAXWORLD] = { nullptr };   // cudaIpc mappings of the peers' boards (own entry: the local allocation)
 	void* p5MappedFor = nullptr;                   // local allocation the mappings were exchanged for
@@ -1500,6 +1503,12 @@ struct Engine : EngineBase {
 		CUDA_TRY(cZx.alloc(36 * nP)); CUDA_TRY(cU.alloc(36 * (size_t)S.nfull)); CUDA_TRY(cInfo.alloc(1));
 		CUDA_TRY(fHat.alloc(36 * (size_t)S.nfull));
 		CUDA_TRY(p5AcP.alloc(nblkPz * 36)); CUDA_TRY(p5AcInv.alloc((size_t)nc * nc)); CUDA_TRY(p5Lp.alloc(nblkPz * 36)); CUDA_TRY(p5Wp.alloc(nblkPz * 36)); CUDA_TRY(p5Ld.alloc((size_t)A * 36));
+		p5Dense = A > PCG4_MAXAGG1 && !getenv("CUBA_COARSE_CLUSTER");
+		if (p5Dense) {
+			const size_t ntd = ((size_t)nc + cdense::NB - 1) / cdense::NB, npd = ntd * cdense::NB;
+			CUDA_TRY(cdM.alloc(npd * npd)); CUDA_TRY(cdL.alloc(npd * npd)); CUDA_TRY(cdW.alloc(npd * npd)); CUDA_TRY(cdDinv.alloc(ntd * cdense::NB * cdense::NB));
+			CUDA_TRY(gridBar.alloc(1));
+		}
 		// boards (16-byte words): [2 solve halves][2 pass parities] of w, of the per-CTA partials and of the rank summaries, then the control block
 		const size_t wW = 4 * 6 * nP, pW = 4 * (size_t)PCG5_REPL * G * 9, rW = 4 * (size_t)PCG5_REPL * W * NR, cW = 4 * (size_t)PCG5_REPL * nc;
 		const size_t words2 = 2 * (wW + pW + rW + cW) + (sizeof(Pcg5Ctl) + 7) / 8 + 2;
@@ -1527,11 +1536,21 @@ struct Engine : EngineBase {
 	}
 
 	// coarse matrix Ac = Z^T S Z of the current system and its inverse (fp32), for the aggregates behind (cbPtr, cbList)
-	int launch_coarse_setup(int A, int cluster, size_t invSmem, const int* cbPtr, const int* cbList, double* AcP, float* AcInv, double* Lp, double* Ld, double* Wp)
+	int launch_coarse_setup(int A, int cluster, size_t invSmem, const int* cbPtr, const int* cbList, double* AcP, float* AcInv, double* Lp, double* Ld, double* Wp, bool dense = false)
 	{
 		const int nblkP = A * (A + 1) / 2;
 		KLAUNCH(k_coarse_project<T>, 36LL * S.nfull, fVal.p, cRowOf.p, fColInd.p, S.nfull, cZx.p, cU.p);
 		KLAUNCH(k_coarse_assemble, (long long)nblkP * 36, cbPtr, cbList, cU.p, nblkP, AcP);
+		if (dense) {
+			// dense tile Cholesky + inverse on the whole chip (cuba_coarse_dense.cuh): one persistent cooperative kernel
+			CUDA_TRY(cudaMemsetAsync(cdM.p, 0, sizeof(double) * cdM.n, stream));
+			cdense::Args da;
+			da.AcP = AcP; da.A = A; da.M = cdM; da.Lm = cdL; da.Dinv = cdDinv; da.W = cdW; da.AcInv = AcInv; da.info = cInfo; da.bar = gridBar;
+			void* dargs[] = { (void*)&da };
+			CUDA_TRY(cudaLaunchCooperativeKernel((void*)cdense::k_coarse_dense, dim3(numSMs), dim3(cdense::WARPS * 32), dargs, 0, stream));
+			launches++;
+			return CUBA_OK;
+		}
 		if (cluster) {
 			// Cholesky in the shared memory of an 8- or 16-CTA cluster, then the triangular inverse (one CTA per block column) and W^T W on the whole chip
 			cudaLaunchConfig_t lc = {};
@@ -1578,7 +1597,7 @@ struct Engine : EngineBase {
 			const int refreshEvery = cfg.reserved[4] > 0 ? cfg.reserved[4] : 8;
 			const double lamRatio = (p5CoarseValid && p5CoarseLambda > 0 && curLambda > 0) ? std::max(curLambda / p5CoarseLambda, p5CoarseLambda / curLambda) : 1.0;
 			if (!p5CoarseValid || p5CoarseAge >= refreshEvery || lamRatio > 300.0) {
-				int rc = launch_coarse_setup(A, p5Cluster, p5InvSmem, p5CbPtr, p5CbList, p5AcP, p5AcInv, p5Lp, p5Ld, p5Wp); if (rc) return rc;
+				int rc = launch_coarse_setup(A, p5Cluster, p5InvSmem, p5CbPtr, p5CbList, p5AcP, p5AcInv, p5Lp, p5Ld, p5Wp, p5Dense); if (rc) return rc;
 				p5CoarseValid = true; p5CoarseAge = 0; p5CoarseLambda = curLambda;
 			}
 			p5CoarseAge++;
