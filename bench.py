@@ -145,10 +145,10 @@ def pin_problem(prob):
 class Runner:
     """one engine on this rank's GPU + the distributed plumbing of the timed loops"""
 
-    def __init__(self, pkg, local, rank, world, fp32=False):
+    def __init__(self, pkg, local, rank, world, fp32=False, mixed=False):
         import torch
         import torch.distributed as dist
-        self.pkg, self.local, self.rank, self.world, self.fp32 = pkg, local, rank, world, fp32
+        self.pkg, self.local, self.rank, self.world, self.fp32, self.mixed = pkg, local, rank, world, fp32, mixed
         self.torch, self.dist = torch, dist
         self.uid_fn = lambda: pkg.sharding.broadcast_unique_id(pkg.Engine, rank, world)
 
@@ -166,7 +166,7 @@ class Runner:
         return float(t.item())
 
     def engine(self, rk, **kw):
-        eng = self.pkg.Engine(device=self.local, use_fp32=self.fp32, **kw)
+        eng = self.pkg.Engine(device=self.local, use_fp32=("mixed" if self.mixed else self.fp32), **kw)
         for et in (0, 1):
             eng.set_robust_kernels(rk[0][et], rk[1][et], et)
         if self.world > 1:
@@ -266,6 +266,8 @@ class Runner:
                 stage_ms[label] = eng.bench_stage(st, reps=20 if E < 2000000 else 5, flush_l2=True, lam=lam)
             s = 4 if self.fp32 else 8
             b_kernel, b_stage = jh_bytes(sizes, s)          # per-rank bytes: each rank streams its shard of the edges
+            if self.mixed:
+                b_kernel -= sizes["nhpl"] * (144 - 80); b_stage -= sizes["nhpl"] * (144 - 80)   # 80-byte fp32 Hpl blocks
             b_kernel /= self.world; b_stage /= self.world
             peak, peak_src = measured_peak()
             ach = b_kernel / (stage_ms["jh_landmark_pass"] * 1e-3) / 1e9
@@ -366,9 +368,10 @@ def run_reference(args, pkg, rk, rank):
 
 
 def config_entry(name, workload, robust, fp32, m, oracle_chi2, oracle_kind):
-    e = {"config": name, "workload": workload, "robust_kernel": robust, "dtype": "f32" if fp32 else "f64", "edges": m["E"],
+    e = {"config": name, "workload": workload, "robust_kernel": robust, "dtype": "f32" if fp32 is True else ("f64 (Hpl stored in f32)" if fp32 == "mixed" else "f64"), "edges": m["E"],
          "value": m["value"], "ms_per_step": m["ms_per_step"], "e2e": m["e2e"]["value"], "e2e_ms_per_step": m["e2e"]["ms_per_step"],
-         "roofline_frac": m["roofline"]["frac"] if "roofline" in m else None,
+         "roofline_frac": m["roofline"]["frac"] if "roofline" in m else None, "jh_landmark_pass_us": 1e3 * m["stage_ms"]["jh_landmark_pass"] if "stage_ms" in m else None,
+         "schur_us": 1e3 * m["stage_ms"]["schur"] if "stage_ms" in m else None,
          "stage_frac_jh_both_kernels": m["roofline"]["stage_frac_jh_both_kernels"] if "roofline" in m else None,
          "schur_frac": m["roofline"]["schur_frac"] if "roofline" in m else None,
          "pcg_iterations_per_step": m["pcg_iterations_per_step"], "pcg_ms_per_step": m["pcg_ms_per_step"],
@@ -387,6 +390,7 @@ def main():
     ap.add_argument("--workload", default=None, help="default: ba_kitti_00 on one GPU, synth_stereo_10m on several")
     ap.add_argument("--robust", default=None, choices=list(KERNELS))
     ap.add_argument("--fp32", action="store_true")
+    ap.add_argument("--mixed", action="store_true", help="fp64 engine with the Hpl blocks stored in fp32 (SURVEY 8 f-4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the C1..C5 array (and, on several GPUs, the secondary workload)")
     ap.add_argument("--no-cpp", action="store_true")
@@ -418,7 +422,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    run = Runner(pkg, local, rank, world, fp32=args.fp32)
+    run = Runner(pkg, local, rank, world, fp32=args.fp32, mixed=args.mixed)
 
     graph = load_graph(pkg, args.workload)
     prob0 = pkg.graphio.flatten(graph)
@@ -483,12 +487,13 @@ def main():
         if world == 1:
             configs = [config_entry("C2", args.workload, args.robust, False, m, chi_oracle, oracle_kind)]
             plan = [("C1", "ba_kitti_07", "none", False, 3, 3), ("C1", "ba_kitti_07", "huber", False, 3, 3), ("C2", "ba_kitti_00", "huber", False, 3, 3),
-                    ("C5", "ba_kitti_00", "none", True, 3, 3), ("C3", "synth_mono_5m", "huber", False, 2, 1), ("C4", "synth_stereo_10m", "huber", False, 2, 1)]
+                    ("C5", "ba_kitti_00", "none", True, 3, 3), ("C5-mixed", "ba_kitti_00", "none", "mixed", 3, 3),
+                    ("C3", "synth_mono_5m", "huber", False, 2, 1), ("C4", "synth_stereo_10m", "huber", False, 2, 1)]
             for name, wl, rb, f32, st, wu in plan:
                 wl, _ = resolve_workload(wl)
                 try:
                     p = build_problem(pkg, wl)
-                    r2 = Runner(pkg, local, rank, world, fp32=f32)
+                    r2 = Runner(pkg, local, rank, world, fp32=(f32 is True), mixed=(f32 == "mixed"))
                     mm = r2.measure(p, KERNELS[rb], st, wu, protocol_warmup=wl.startswith("ba_"))
                     oc, ok_ = None, None
                     if not f32:

@@ -192,7 +192,7 @@ class Engine:
         res[4] = int(coarse_refresh)
         res[5] = int(two_level_switch)
         res[6] = int(max_aggregates)
-        cfg = _Config(device, int(use_fp32), int(pcg_max_iters), float(pcg_tol), 1, res)
+        cfg = _Config(device, 2 if use_fp32 == "mixed" else int(use_fp32), int(pcg_max_iters), float(pcg_tol), 1, res)
         h = C.c_void_p()
         _check(self.L.cuba_engine_create(C.byref(cfg), C.byref(h)))
         self.h = h

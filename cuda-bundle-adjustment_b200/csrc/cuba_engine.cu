@@ -241,6 +241,8 @@ struct Engine : EngineBase {
 	DBuf<int> e_ip, e_il, e_hpl, e_user, lmPtr, tileLm, hplLm, posePtr, p_il;
 	// system
 	DBuf<T> Hpp, bp, Hll, bl, Hpl, invHll, fVal, bsc, xp, xl;
+	DBuf<float> HplF;        // mixed precision (cfg.use_fp32 == 2, fp64 engine): the Hpl blocks in fp32, 20 floats per block
+	bool mixed = false;
 	DBuf<int> prodPtr, prodI, prodJ, prodL, blkRow, blkCol, u2f, u2fT, fRowPtr, fColInd;
 	bool useSchur3 = true;
 	// pcg
@@ -711,7 +713,10 @@ struct Engine : EngineBase {
 		// Hpp | bp | (chi2 slot) and Hsc | bsc are single allocations: one collective each in landmark-sharded runs
 		CUDA_TRY(Hpp.alloc(42 * nP + 2)); bp.alias(Hpp.p + 36 * nP, 6 * nP);
 		CUDA_TRY(Hll.alloc(9 * nL)); CUDA_TRY(bl.alloc(3 * nL));
-		CUDA_TRY(Hpl.alloc(18 * (size_t)S.nhplLocal)); CUDA_TRY(invHll.alloc(9 * nL));
+		mixed = cfg.use_fp32 == 2 && sizeof(T) == 8 && jhV4;
+		if (mixed) { CUDA_TRY(HplF.alloc(20 * (size_t)std::max(S.nhplLocal, 1))); CUDA_TRY(Hpl.alloc(1)); }
+		else CUDA_TRY(Hpl.alloc(18 * (size_t)S.nhplLocal));
+		CUDA_TRY(invHll.alloc(9 * nL));
 		CUDA_TRY(fVal.alloc(36 * (size_t)S.nfull + 6 * nP)); bsc.alias(fVal.p + 36 * (size_t)S.nfull, 6 * nP);
 		CUDA_TRY(xp.alloc(6 * nP)); CUDA_TRY(xl.alloc(3 * nL));
 		CUDA_TRY(pr.alloc(6 * nP)); CUDA_TRY(pz.alloc(6 * nP)); CUDA_TRY(pq.alloc(6 * nP)); CUDA_TRY(pp0.alloc(6 * nP)); CUDA_TRY(pp1.alloc(6 * nP));
@@ -743,7 +748,8 @@ struct Engine : EngineBase {
 		// 4 = k_schur4 (k_schur3 + cooperative cp.async block loads: slower, kept for the record), 1 = k_schur (lane per product),
 		// 2 = tile-local pair without tensor cores
 		useSchur5 = cfg.reserved[3] == 5 && cfg.reserved[1] != 1 && sizeof(T) == 8 && S.numP > 0 && S.numL > 0 && ntiles > 0 && S.eLocal > 0;
-		useSchur3 = cfg.reserved[3] == 0 || cfg.reserved[3] == 3 || cfg.reserved[3] == 4;
+		useSchur3 = cfg.reserved[3] == 0 || cfg.reserved[3] == 3 || cfg.reserved[3] == 4 || cfg.use_fp32 == 2;
+		if (cfg.use_fp32 == 2) { useSchur2 = false; useSchur5 = false; }
 		if (useSchur3 && S.nmulLocal > 0) {
 			CUDA_TRY(prodL.alloc((size_t)S.nmulLocal));
 			KLAUNCH(schur3::k_prod_landmark, S.nmulLocal, prodI.p, hplLm.p, (int)S.nmulLocal, prodL.p);
@@ -857,7 +863,7 @@ struct Engine : EngineBase {
 				jh4::Args b;
 				b.pose = pose[cur]; b.cam = cam; b.Xw = Xw[cur];
 				b.rec = w_rec; b.tile = w_tile; b.tilePose = w_tilePose; b.tilePieces = w_tilePieces; b.pieceCount = w_pieceCount; b.ntiles = ntW; b.numL = S.numL;
-				b.Hpl = Hpl; b.Hll = Hll; b.bl = bl; b.bigPartial = w_bigPartial; b.chiPartial = chiPartial; b.rk = rkParams();
+				b.Hpl = Hpl; b.HplF = mixed ? HplF.p : nullptr; b.Hll = Hll; b.bl = bl; b.bigPartial = w_bigPartial; b.chiPartial = chiPartial; b.rk = rkParams();
 				const void* fn = nullptr; size_t smem = 0;
 #define JH4_PICK(MB, NS, DB) { fn = (const void*)jh4::k_linearize_landmark4<MB, NS, DB>; smem = (size_t)NS * jh4::WARPS * sizeof(jh4::StageOf<MB, NS>); }
 				int dbg = 0;
@@ -867,6 +873,7 @@ struct Engine : EngineBase {
 					case 7: JH4_PICK(4, 3, 7) break; case 8: JH4_PICK(4, 3, 8) break; case 15: JH4_PICK(4, 3, 15) break; default: dbg = 0; } }
 				else { switch (dbg) { case 8: JH4_PICK(5, 2, 8) break; case 7: JH4_PICK(5, 2, 7) break; default: dbg = 0; } }
 #endif
+				if (mixed) { fn = (const void*)jh4::k_linearize_landmark4<4, 2, 0, true>; smem = (size_t)2 * jh4::WARPS * sizeof(jh4::StageOf<4, 2>); }
 				if (!fn) {
 					if (jh4Nst == 3) JH4_PICK(4, 3, 0)
 					else if (jh4MinB == 4) JH4_PICK(4, 2, 0)
@@ -1061,7 +1068,15 @@ struct Engine : EngineBase {
 			a.prodPtr = prodPtr; a.prodI = prodI; a.prodJ = prodJ; a.prodL = prodL;
 			a.blkRow = blkRow; a.blkCol = blkCol; a.u2f = u2f; a.u2fT = u2fT; a.nblk = S.nblk;
 			a.lambda = lambda; a.addDiag = rank == 0 ? 1 : 0; a.fVal = fVal; a.bsc = bsc;
-			if (cfg.reserved[3] != 4) schur3::k_schur3<T><<<(S.nblk + schur3::WARPS - 1) / schur3::WARPS, schur3::WARPS * 32, 0, stream>>>(a);
+			if (mixed) {
+				if constexpr (sizeof(T) == 8) {
+					schur3::Args<double, float> m;
+					m.Hpl = HplF; m.invHll = invHll; m.bl = bl; m.Hpp = Hpp; m.bp = bp; m.prodPtr = prodPtr; m.prodI = prodI; m.prodJ = prodJ; m.prodL = prodL;
+					m.blkRow = blkRow; m.blkCol = blkCol; m.u2f = u2f; m.u2fT = u2fT; m.nblk = S.nblk; m.lambda = lambda; m.addDiag = a.addDiag; m.fVal = fVal; m.bsc = bsc;
+					schur3::k_schur3<double, float><<<(S.nblk + schur3::WARPS - 1) / schur3::WARPS, schur3::WARPS * 32, 0, stream>>>(m);
+				}
+			}
+			else if (cfg.reserved[3] != 4) schur3::k_schur3<T><<<(S.nblk + schur3::WARPS - 1) / schur3::WARPS, schur3::WARPS * 32, 0, stream>>>(a);
 			else schur3::k_schur4<T><<<(S.nblk + schur3::WARPS - 1) / schur3::WARPS, schur3::WARPS * 32, 0, stream>>>(a);
 			launches++;
 			CUDA_TRY(cudaGetLastError());
@@ -1677,7 +1692,16 @@ struct Engine : EngineBase {
 			BacksubArgs<T> a;
 			a.Hpl = Hpl; a.invHll = invHll; a.bl = bl; a.xp = xp; a.ip = e_ip; a.hpl = e_hpl; a.lmPtr = tilePtr; a.tileLm = tileLm;
 			a.numL = S.numL; a.lambda = lambda; a.XwCur = Xw[cur]; a.XwTrial = Xw[cur ^ 1]; a.xl = xl; a.scalePartial = scalePartialL;
-			if (tileSize == 128) k_backsub<T, 128><<<ntiles, 128, 0, stream>>>(a);
+			if (mixed) {
+				if constexpr (sizeof(T) == 8) {
+					BacksubArgs<double, float> m;
+					m.Hpl = HplF; m.invHll = invHll; m.bl = bl; m.xp = xp; m.ip = e_ip; m.hpl = e_hpl; m.lmPtr = tilePtr; m.tileLm = tileLm;
+					m.numL = S.numL; m.lambda = lambda; m.XwCur = Xw[cur]; m.XwTrial = Xw[cur ^ 1]; m.xl = xl; m.scalePartial = scalePartialL;
+					if (tileSize == 128) k_backsub<double, 128, float><<<ntiles, 128, 0, stream>>>(m);
+					else k_backsub<double, 256, float><<<ntiles, 256, 0, stream>>>(m);
+				}
+			}
+			else if (tileSize == 128) k_backsub<T, 128><<<ntiles, 128, 0, stream>>>(a);
 			else k_backsub<T, 256><<<ntiles, 256, 0, stream>>>(a);
 			launches++;
 			CUDA_TRY(cudaGetLastError());
@@ -1933,7 +1957,13 @@ struct Engine : EngineBase {
 		if (oHpl) {
 			// local blocks land at their global positions; foreign blocks read as zero
 			memset(oHpl, 0, sizeof(double) * 18 * (size_t)S.nhpl);
-			if ((rc = download(Hpl, 18 * (size_t)S.nhplLocal, oHpl + 18 * (size_t)S.hplBase))) return rc;
+			if (mixed) {
+				std::vector<float> hf(20 * (size_t)S.nhplLocal);
+				CUDA_TRY(cudaMemcpyAsync(hf.data(), HplF.p, sizeof(float) * hf.size(), cudaMemcpyDeviceToHost, stream));
+				CUDA_TRY(cudaStreamSynchronize(stream));
+				for (size_t b = 0; b < (size_t)S.nhplLocal; b++) for (int e = 0; e < 18; e++) oHpl[18 * ((size_t)S.hplBase + b) + e] = (double)hf[20 * b + e];
+			}
+			else if ((rc = download(Hpl, 18 * (size_t)S.nhplLocal, oHpl + 18 * (size_t)S.hplBase))) return rc;
 		}
 		return CUBA_OK;
 	}
@@ -2040,7 +2070,7 @@ int cuba_engine_create(const cuba_config* cfg, cuba_engine** out)
 	if (cfg) c = *cfg;
 	std::unique_ptr<EngineBase> impl;
 	int rc;
-	if (c.use_fp32) { auto* e = new Engine<float>(); e->cfg = c; impl.reset(e); rc = e->init(); }
+	if (c.use_fp32 == 1) { auto* e = new Engine<float>(); e->cfg = c; impl.reset(e); rc = e->init(); }
 	else { auto* e = new Engine<double>(); e->cfg = c; impl.reset(e); rc = e->init(); }
 	if (rc) return rc;
 	if (getenv("CUBA_NO_STRUCTURE_REUSE")) impl->structureReuse = false;   // like-for-like timing against the reference, which rebuilds everything

@@ -67,7 +67,8 @@ struct Args {
 	const int* tilePieces;                                      // pieces of cut landmarks: (piece index << 16) | number of pieces
 	int* pieceCount;                                            // arrival counters, one per tile (zero between launches)
 	int ntiles, numL;
-	double* Hpl; double* Hll; double* bl; double* bigPartial;  // bigPartial[t*12 ..]: partial sums of the pieces
+	double* Hpl; float* HplF;        // HplF != nullptr (kernel template HF): Hpl blocks in fp32, 20 floats (80 B) per block
+	double* Hll; double* bl; double* bigPartial;  // bigPartial[t*12 ..]: partial sums of the pieces
 	double* chiPartial;
 	RobustParams rk;
 };
@@ -136,7 +137,7 @@ __device__ __forceinline__ void issue_loads(const Args& a, int t, const Desc& d,
 
 // DBG (diagnosis builds only, tools/jh4_dbg.sh): bit 0 skips the arithmetic, bit 1 the Hpl staging + bulk store,
 // bit 2 the per-landmark reduction and the Hll/bl stores, bit 3 adds clock64 phase counters.  DBG == 0 is the product.
-template <int MINB, int NST, int DBG = 0>
+template <int MINB, int NST, int DBG = 0, bool HF = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB) k_linearize_landmark4(const Args a)
 {
 	typedef double T;
@@ -258,15 +259,18 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_linearize_landmark4(const 
 				v[8] = JL[0][2] * wr[0] + JL[1][2] * wr[1] + JL[2][2] * wr[2];
 				if (!(DBG & 2) && hl >= 0) {
 					T* dst = reinterpret_cast<T*>(&st) + 18 * hl;
+					float* dstF = reinterpret_cast<float*>(&st) + 20 * hl;      // mixed precision: 80-byte fp32 blocks
 #pragma unroll
 					for (int n = 0; n < 3; n++) {
 #pragma unroll
 						for (int l = 0; l < 6; l += 2) {
 							const T h0 = JP[0][l] * wJL[0][n] + JP[1][l] * wJL[1][n] + JP[2][l] * wJL[2][n];
 							const T h1 = JP[0][l + 1] * wJL[0][n] + JP[1][l + 1] * wJL[1][n] + JP[2][l + 1] * wJL[2][n];
-							st2(dst + n * 6 + l, h0, h1);
+							if constexpr (HF) *reinterpret_cast<float2*>(dstF + n * 6 + l) = make_float2((float)h0, (float)h1);
+							else st2(dst + n * 6 + l, h0, h1);
 						}
 					}
+					if constexpr (HF) *reinterpret_cast<float2*>(dstF + 18) = make_float2(0.f, 0.f);
 				}
 			}
 		}
@@ -276,9 +280,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_linearize_landmark4(const 
 		__syncwarp();
 		const int nh = cur.nh;
 		if (!(DBG & 2) && lane == 0 && nh > 0) {
-			T* gdst = a.Hpl + 18 * (size_t)cur.h0;
-			asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-				:: "l"(gdst), "r"(smem_u32(&st)), "r"((unsigned int)(nh * 18 * sizeof(T))) : "memory");
+			if constexpr (HF) {
+				float* gdst = a.HplF + 20 * (size_t)cur.h0;
+				asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+					:: "l"(gdst), "r"(smem_u32(&st)), "r"((unsigned int)(nh * 20 * sizeof(float))) : "memory");
+			} else {
+				T* gdst = a.Hpl + 18 * (size_t)cur.h0;
+				asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+					:: "l"(gdst), "r"(smem_u32(&st)), "r"((unsigned int)(nh * 18 * sizeof(T))) : "memory");
+			}
 		}
 		if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 		JH4_TICK(4);

@@ -991,9 +991,22 @@ __global__ void __launch_bounds__(PCG_BLOCK) k_pcg(const PcgArgs<T> a)
 //   xl = invHll (bl - sum_i Hpl_i^T xp[row_i]) ; Xw_trial = Xw + xl ; scale += xl.(lambda xl + bl)
 // (reference cu:1029-1043, 1057-1068, 1070-1091)
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+// Mixed precision: an fp64 engine may keep the Hpl blocks -- the dominant 144 B/edge stream, written once by the
+// J+H pass and read by the Schur and back-substitution kernels -- in fp32, 18 values padded to 20 (80-byte blocks: a multiple
+// of the 16-byte granule of the bulk store).  Everything is still computed and accumulated in fp64.
+template <typename T, typename TH> struct HplStride { static constexpr int value = sizeof(TH) < sizeof(T) ? 20 : 18; };
+template <typename T, typename TH>
+__device__ __forceinline__ void ldh2(const TH* __restrict__ p, T& a, T& b)
+{
+	if constexpr (sizeof(TH) == sizeof(T)) ld2(p, a, b);
+	else { const float2 v = __ldg(reinterpret_cast<const float2*>(p)); a = (T)v.x; b = (T)v.y; }
+}
+template <typename T, typename TH>
+__device__ __forceinline__ T ldh(const TH* __restrict__ p) { return (T)__ldg(p); }
+
+template <typename T, typename TH = T>
 struct BacksubArgs {
-	const T* Hpl; const T* invHll; const T* bl; const T* xp;
+	const TH* Hpl; const T* invHll; const T* bl; const T* xp;
 	const int* ip; const int* hpl; const int* lmPtr; const int* tileLm;
 	int numL;
 	T lambda;
@@ -1001,8 +1014,8 @@ struct BacksubArgs {
 	double* scalePartial;
 };
 
-template <typename T, int TL>
-__global__ void __launch_bounds__(TL) k_backsub(const BacksubArgs<T> a)
+template <typename T, int TL, typename TH = T>
+__global__ void __launch_bounds__(TL) k_backsub(const BacksubArgs<T, TH> a)
 {
 	__shared__ T s_val[3][TL + 1];
 	__shared__ T s_acc[TL * 3];
@@ -1024,13 +1037,13 @@ __global__ void __launch_bounds__(TL) k_backsub(const BacksubArgs<T> a)
 				const int hp = a.hpl[e];
 				if (hp >= 0) {
 					const int ip = a.ip[e] & 0x7fffffff;
-					const T* A = a.Hpl + 18 * (size_t)hp;
+					const TH* A = a.Hpl + HplStride<T, TH>::value * (size_t)hp;
 					const T* x = a.xp + 6 * (size_t)ip;
 					T xr[6];
 					ld2(x, xr[0], xr[1]); ld2(x + 2, xr[2], xr[3]); ld2(x + 4, xr[4], xr[5]);
 					T A0[6], A1[6], A2[6];
 #pragma unroll
-					for (int r = 0; r < 6; r += 2) { ld2(A + r, A0[r], A0[r + 1]); ld2(A + 6 + r, A1[r], A1[r + 1]); ld2(A + 12 + r, A2[r], A2[r + 1]); }
+					for (int r = 0; r < 6; r += 2) { ldh2<T, TH>(A + r, A0[r], A0[r + 1]); ldh2<T, TH>(A + 6 + r, A1[r], A1[r + 1]); ldh2<T, TH>(A + 12 + r, A2[r], A2[r + 1]); }
 #pragma unroll
 					for (int r = 0; r < 6; r++) { v0 += A0[r] * xr[r]; v1 += A1[r] * xr[r]; v2 += A2[r] * xr[r]; }
 				}

@@ -27,9 +27,9 @@ __global__ void k_prod_landmark(const int* __restrict__ prodI, const int* __rest
 	prodL[k] = i >= 0 ? hplLm[i] : -1;
 }
 
-template <typename T>
+template <typename T, typename TH = T>
 struct Args {
-	const T* Hpl; const T* invHll; const T* bl; const T* Hpp; const T* bp;
+	const TH* Hpl; const T* invHll; const T* bl; const T* Hpp; const T* bp;
 	const int* prodPtr; const int* prodI; const int* prodJ; const int* prodL;
 	const int* blkRow; const int* blkCol; const int* u2f; const int* u2fT;
 	int nblk;
@@ -38,8 +38,8 @@ struct Args {
 	T* fVal; T* bsc;
 };
 
-template <typename T>
-__global__ void __launch_bounds__(WARPS * 32, 3) k_schur3(const Args<T> a)
+template <typename T, typename TH = T>
+__global__ void __launch_bounds__(WARPS * 32, 3) k_schur3(const Args<T, TH> a)
 {
 	__shared__ T s_red[WARPS][SLOTS][6][8];     // [slot][row][6 entries of the row + bsc + pad]
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -65,14 +65,14 @@ __global__ void __launch_bounds__(WARPS * 32, 3) k_schur3(const Args<T> a)
 		pi = -1; pj = -1; pl = -1;
 		if (worker && nn < n1) { pi = a.prodI[nn]; pj = a.prodJ[nn]; pl = a.prodL[nn]; }
 		if (have) {
-			const T* Ai = a.Hpl + 18 * (size_t)ci;
-			const T* Aj = a.Hpl + 18 * (size_t)cj;
+			const TH* Ai = a.Hpl + HplStride<T, TH>::value * (size_t)ci;
+			const TH* Aj = a.Hpl + HplStride<T, TH>::value * (size_t)cj;
 			const T* iv = a.invHll + 9 * (size_t)cl;
-			const T a0 = __ldg(Ai + r), a1 = __ldg(Ai + 6 + r), a2 = __ldg(Ai + 12 + r);
+			const T a0 = ldh<T, TH>(Ai + r), a1 = ldh<T, TH>(Ai + 6 + r), a2 = ldh<T, TH>(Ai + 12 + r);
 			const T i0 = __ldg(iv), i1 = __ldg(iv + 3), i2 = __ldg(iv + 6), i3 = __ldg(iv + 4), i4 = __ldg(iv + 7), i5 = __ldg(iv + 8);
 			T B[18];
 #pragma unroll
-			for (int x = 0; x < 18; x += 2) ld2(Aj + x, B[x], B[x + 1]);
+			for (int x = 0; x < 18; x += 2) ldh2<T, TH>(Aj + x, B[x], B[x + 1]);
 			const T w0 = a0 * i0 + a1 * i1 + a2 * i2;
 			const T w1 = a0 * i1 + a1 * i3 + a2 * i4;
 			const T w2 = a0 * i2 + a1 * i4 + a2 * i5;

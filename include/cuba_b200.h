@@ -69,7 +69,9 @@ extern "C" {
 
 typedef struct cuba_config {
 	int device;            /* CUDA device ordinal, -1 = current device                            */
-	int use_fp32;          /* 0 = fp64 (default); 1 = reference's USE_FLOAT32 behaviour           */
+	int use_fp32;          /* 0 = fp64 (default); 1 = reference's USE_FLOAT32 behaviour; 2 = mixed precision: fp64 engine whose Hpl
+	                          blocks -- the dominant 144 B/edge stream -- are STORED in fp32 (80-byte blocks), everything computed
+	                          and accumulated in fp64, PCG in fp64                                        */
 	int pcg_max_iters;     /* <=0: default                                         */
 	double pcg_tol;        /* stop when sqrt(r'z / r0'z0) <= pcg_tol; <=0: default 1e-11 (fp64)    */
 	int deterministic;     /* kept for layout compatibility; every kernel sums in a fixed order: results are bit-reproducible run to run */

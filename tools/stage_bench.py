@@ -24,7 +24,7 @@ for workload in args or ["kitti00_shaped"]:
         g = pkg.synth.make_config(workload)
     prob = pkg.graphio.flatten(g)
     for sv in schur:
-        eng = pkg.Engine(device=0, schur_variant=sv)
+        eng = pkg.Engine(device=0, schur_variant=sv, use_fp32=("mixed" if os.environ.get("MIXED") else False))
         eng.initialize(prob)
         eng.linearize()
         lam = 1e-5 * eng.max_diagonal()
