@@ -1389,7 +1389,7 @@ struct Engine : EngineBase {
 	Pcg5Dims p5Dims{}, p5DimsBJ{};
 	size_t p5Smem = 0;
 	int p5G = 0, p5W = 1, p5A = 0, p5Gs = 1;
-	bool p5Ok = false, p5Dist = false;
+	bool p5Ok = false, p5Dist = false, p5Big = false;
 	int p5Cluster = 0;                             // CTAs of the cluster that factors the coarse matrix (0: one CTA)
 	bool p5CoarseValid = false; int p5CoarseAge = 0; double p5CoarseLambda = 0;
 	size_t p5InvSmem = 0;
@@ -1461,7 +1461,7 @@ struct Engine : EngineBase {
 		// row sums), rank-aligned aggregates, halo masks: cuba_structure.cpp (CPU-tested through cuba_debug_pcg5_plan)
 		const int maxAgg = (cfg.reserved[6] > 0 && cfg.reserved[6] < PCG5_MAXAGG) ? cfg.reserved[6] : PCG5_MAXAGG;
 		Pcg5Plan plan;
-		build_pcg5_plan(numP, S.nfull, S.fRowPtr, S.fColInd, W, numSMs, maxAgg, PCG5_BLOCK / 6, plan);
+		build_pcg5_plan(numP, S.nfull, S.fRowPtr, S.fColInd, W, numSMs, maxAgg, 2 * PCG5_BLOCK / 6, plan);
 		if (!plan.ok) return CUBA_OK;
 		const int G = plan.G, gs = plan.gs, A = plan.A;
 		const PcgPartition& PP = plan.P; const CoarsePartition& CP = plan.C;
@@ -1472,7 +1472,8 @@ struct Engine : EngineBase {
 		d.npv = std::max(std::max(G * 9, W * NR), 6 * CP.maxNeedAgg); d.nls = NR;
 		d.sliceRows = (nc + G - 1) / G;
 		const size_t per = 36 * sizeof(T) + 4;
-		const size_t wantCache = PP.blkMax > PCG5_REGBLK ? (size_t)(PP.blkMax - PCG5_REGBLK) : 0;
+		size_t wantCache = PP.blkMax > PCG5_REGBLK ? (size_t)(PP.blkMax - PCG5_REGBLK) : 0;
+		bool big = PP.maxRows * 6 > PCG5_BLOCK;
 		{
 			d.capBlocks = 0; d.zhInSmem = 0;
 			const size_t base = Pcg5Layout<T>(d).total + 64;
@@ -1482,14 +1483,21 @@ struct Engine : EngineBase {
 			if (used + zhBytes <= budget) { d.zhInSmem = 1; used += zhBytes; }
 			const size_t fixed = used - wantCache * per;
 			d.capBlocks = (int)std::min(wantCache, (budget - fixed) / per);
+			// blocks would have to be streamed from the global copy every pass: the variant without register-resident blocks streams
+			// with eighteen 16-byte loads in flight per thread (the register variant can afford six 8-byte loads)
+			if ((size_t)d.capBlocks < wantCache) big = true;
+			if (big) d.capBlocks = (int)std::min((size_t)PP.blkMax, (budget - fixed) / per);
 		}
 		p5Dims = d;
 		p5DimsBJ = d; p5DimsBJ.nc = 0; p5DimsBJ.maxNeedAgg = 0; p5DimsBJ.zhInSmem = 0; p5DimsBJ.sliceRows = 0; p5DimsBJ.nls = 3; p5DimsBJ.npv = std::max(G * 3, W * 3);
 		p5Smem = std::max(Pcg5Layout<T>(p5Dims).total, Pcg5Layout<T>(p5DimsBJ).total);
 		if (p5Smem > (size_t)smemMax - 1024) return CUBA_OK;
-		CUDA_TRY(cudaFuncSetAttribute(k_pcg5<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p5Smem));
+		p5Big = big;
+		const void* p5Fn = p5Big ? (const void*)k_pcg5<T, true> : (const void*)k_pcg5<T, false>;
+		CUDA_TRY(cudaFuncSetAttribute(p5Fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p5Smem));
 		int perSM = 0;
-		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_pcg5<T>, PCG5_BLOCK, p5Smem));
+		if (p5Big) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_pcg5<T, true>, PCG5_BLOCK, p5Smem));
+		else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_pcg5<T, false>, PCG5_BLOCK, p5Smem));
 		if (perSM < 1) return CUBA_OK;
 		if (getenv("CUBA_PCG_VERBOSE")) fprintf(stderr, "pcg5: world %d G %d gs %d A %d needMax %d maxRows %d blkMax %d maxNeedAgg %d zhInSmem %d sliceRows %d cap %d smem %zu\n",
 			W, G, gs, A, d.needMax, d.maxRows, PP.blkMax, d.maxNeedAgg, d.zhInSmem, d.sliceRows, d.capBlocks, p5Smem);
@@ -1645,7 +1653,7 @@ struct Engine : EngineBase {
 #endif
 		if (p5Dist) CUDA_TRY(cudaMemsetAsync(xp.p, 0, sizeof(T) * 6 * (size_t)numP, stream));     // rows of the other ranks: summed in below
 		void* args[] = { (void*)&a };
-		CUDA_TRY(cudaLaunchCooperativeKernel((void*)k_pcg5<T>, dim3(p5G), dim3(PCG5_BLOCK), args, p5Smem, stream));
+		CUDA_TRY(cudaLaunchCooperativeKernel(p5Big ? (void*)k_pcg5<T, true> : (void*)k_pcg5<T, false>, dim3(p5G), dim3(PCG5_BLOCK), args, p5Smem, stream));
 		k_pcg5_commit<<<1, 1, 0, stream>>>(p5Ctl(p5Boards.p));
 		launches += 2;
 		CUDA_TRY(cudaGetLastError());
@@ -2228,7 +2236,7 @@ int cuba_debug_pcg5_plan(const cuba_problem* p, int world, int numSMs, int maxAg
 	const char* err = "";
 	if (!build_structure(p->Pall, p->numP, p->Lall, p->numL, p->E2, p->idx2, p->E3, p->idx3, 0, 1, TILE, S, &err)) return fail(CUBA_ERR_INVALID, err);
 	Pcg5Plan plan;
-	build_pcg5_plan(S.numP, S.nfull, S.fRowPtr, S.fColInd, world, numSMs, maxAgg, PCG5_BLOCK / 6, plan);
+	build_pcg5_plan(S.numP, S.nfull, S.fRowPtr, S.fColInd, world, numSMs, maxAgg, 2 * PCG5_BLOCK / 6, plan);
 	if (info) for (int i = 0; i < 8; i++) info[i] = 0;
 	if (!plan.ok) return CUBA_OK;
 	const char* bad = check_pcg5_plan(S.numP, S.nfull, S.fRowPtr, S.fColInd, plan);

@@ -208,7 +208,8 @@ __device__ __forceinline__ bool ll_poll_many(int n, SlotOf slotOf, double* dst, 
 	return true;
 }
 
-template <typename T>
+// BIG: the CTA may own more than 42 rows (up to 85): every thread then serves two (row, component) pairs in the row sums
+template <typename T, bool BIG = false>
 __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -246,8 +247,12 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 	const int row0 = a.ctaRow[cta], row1 = a.ctaRow[cta + 1], nrows = row1 - row0;
 	const int need0 = a.needPtr[cta], nneed = a.needPtr[cta + 1] - need0;
 	const int blk0 = a.fRowPtr[row0], nblkCta = a.fRowPtr[row1] - blk0;
-	const int ncached = nblkCta > PCG5_REGBLK ? (nblkCta - PCG5_REGBLK < capBlocks ? nblkCta - PCG5_REGBLK : capBlocks) : 0;
+	// BIG: no register-resident blocks -- the registers go to the loads in flight of the streamed part (see the product loop)
+	constexpr int REGBLK = BIG ? 0 : PCG5_REGBLK;
+	const int ncached = nblkCta > REGBLK ? (nblkCta - REGBLK < capBlocks ? nblkCta - REGBLK : capBlocks) : 0;
 	const size_t n6 = 6 * (size_t)a.numP;
+	const int nover = nblkCta - REGBLK - ncached > 0 ? nblkCta - REGBLK - ncached : 0;   // blocks read from the global copy every pass
+	const size_t overBase = 36 * (size_t)(blk0 + REGBLK + ncached);
 	int nagg = 0;
 	// tags and the solve half of the boards
 	const unsigned int tagBase = a.ctl->tagBase, half = a.ctl->solve & 1u;
@@ -317,7 +322,7 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 #pragma unroll
 		for (int u = 0; u < PCG5_BPT; u++) {
 			const int n = u * PCG5_BLOCK + tid;
-			if (n < nblkCta) {
+			if (!BIG && n < nblkCta) {
 				T out[36];
 				transform(n, out);
 #pragma unroll
@@ -325,15 +330,18 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 				myLoc[u] = a.fLocal[blk0 + n];
 			}
 		}
-		for (int n = PCG5_REGBLK + tid; n < nblkCta; n += PCG5_BLOCK) {
+		for (int n = REGBLK + tid; n < nblkCta; n += PCG5_BLOCK) {
 			T out[36];
 			transform(n, out);
-			const int m = n - PCG5_REGBLK;
+			const int m = n - REGBLK;
 			if (m < ncached) {
 				for (int e = 0; e < 36; e++) s_blk[(size_t)e * capBlocks + m] = out[e];
 				s_loc[m] = a.fLocal[blk0 + n];
 			} else {
-				for (int e = 0; e < 36; e++) a.fHat[36 * (size_t)(blk0 + n) + e] = out[e];
+				// past the shared-memory cache: the global copy.  BIG: block-major (a thread streams its 288 contiguous bytes with
+				// eighteen 16-byte loads in flight); else element-major inside this CTA's slice (coalesced 8-byte loads)
+				if (BIG) { for (int e = 0; e < 36; e++) a.fHat[36 * (size_t)(blk0 + n) + e] = out[e]; }
+				else { for (int e = 0; e < 36; e++) a.fHat[overBase + (size_t)e * nover + (m - ncached)] = out[e]; }
 			}
 		}
 	}
@@ -515,14 +523,31 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 			// ---- w_{k+1} = A^ u_{k+1} for the own rows: block products from registers, then per-row sums ----
 			const unsigned int otag = tagBase + (unsigned int)(k + 2);
 			const int opar = (k + 2) & 1;
-			T wacc = T(0);
+			// (row, component) pairs of this thread: pair tid / tpp, and -- only when the CTA owns more than 42 rows (tpp == 1) -- pair tid + BLOCK
+			constexpr int NPU = BIG ? 2 : 1;
+			T wacc[NPU];
+#pragma unroll
+			for (int pu = 0; pu < NPU; pu++) wacc[pu] = T(0);
+			const int npairs = nrows * 6;
 			for (int cs = 0; cs < nblkCta; cs += PCG5_CHUNK) {
 				if (cs > 0) __syncthreads();
+#pragma unroll
+								for (int c = 0; c < 6; c++) {
+									const T rc = rj[c];
+#pragma unroll
+									for (int r = 0; r < 6; r++) y[r] += bv[u][c * 6 + r] * rc;
+								}
+							}
+						}
+#pragma unroll
+						for (int r = 0; r < 6; r++) s_cc[r * PCG5_CHUNK + u * PCG5_BLOCK + tid] = y[r];
+					}
+				} else {
 #pragma unroll
 				for (int u = 0; u < PCG5_BPT; u++) {
 					const int n = cs + u * PCG5_BLOCK + tid;
 					T y[6] = { T(0), T(0), T(0), T(0), T(0), T(0) };
-					if (cs == 0) {
+					if (!BIG && cs == 0) {
 						if (myLoc[u] >= 0) {
 							const T* rj = s_v + 6 * (size_t)myLoc[u];
 #pragma unroll
@@ -533,7 +558,7 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 							}
 						}
 					} else if (n < nblkCta) {
-						const int m = n - PCG5_REGBLK;
+						const int m = n - REGBLK;
 						const bool cached = m < ncached;
 						const int loc = cached ? s_loc[m] : a.fLocal[blk0 + n];
 						if (loc >= 0) {
@@ -547,13 +572,29 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 #pragma unroll
 									for (int r = 0; r < 6; r++) y[r] += B[(c * 6 + r) * st] * rc;
 								}
-							} else {
+							} else if (BIG) {
+								// streamed block: all 288 bytes requested before the first use (measured: requesting the blocks of both
+								// chunk slots at once, 144 registers of loads in flight, is slower -- spills and L1 thrash: 123 vs 92 us)
 								const T* B = a.fHat + 36 * (size_t)(blk0 + n);
+								T bv[36];
+#pragma unroll
+								for (int x = 0; x < 36; x += 2) {      // plain (coherent) vector loads: this CTA wrote the block earlier in this launch
+									const typename V2<T>::type v2 = *reinterpret_cast<const typename V2<T>::type*>(B + x);
+									bv[x] = v2.x; bv[x + 1] = v2.y;
+								}
 #pragma unroll
 								for (int c = 0; c < 6; c++) {
 									const T rc = rj[c];
 #pragma unroll
-									for (int r = 0; r < 6; r++) y[r] += B[c * 6 + r] * rc;
+									for (int r = 0; r < 6; r++) y[r] += bv[c * 6 + r] * rc;
+								}
+							} else {
+								const T* B = a.fHat + overBase + (m - ncached);
+#pragma unroll 1
+								for (int c = 0; c < 6; c++) {
+									const T rc = rj[c];
+#pragma unroll
+									for (int r = 0; r < 6; r++) { y[r] += __ldcg(B) * rc; B += nover; }
 								}
 							}
 						}
@@ -562,34 +603,39 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 					for (int r = 0; r < 6; r++) s_cc[r * PCG5_CHUNK + u * PCG5_BLOCK + tid] = y[r];
 				}
 				__syncthreads();
-				if (tid < nrows * 6 * tpp) {                     // nrows*6 <= PCG5_BLOCK (checked on the host)
-					const int pair = tid / tpp, sub = tid - pair * tpp;
-					const int li = pair / 6, comp = pair - 6 * li;
-					int n0 = s_rowPtr[li], n1 = s_rowPtr[li + 1];
-					n0 = (n0 > cs ? n0 : cs) - cs;
-					n1 = (n1 < cs + PCG5_CHUNK ? n1 : cs + PCG5_CHUNK) - cs;
-					T s0 = T(0), s1 = T(0);
-					const T* col = s_cc + comp * PCG5_CHUNK;
-					int q = n0 + sub;
-					for (; q + tpp < n1; q += 2 * tpp) { s0 += col[q]; s1 += col[q + tpp]; }
-					if (q < n1) s0 += col[q];
-					wacc += s0 + s1;
+#pragma unroll
+				for (int pu = 0; pu < NPU; pu++) {
+					const int pair = tid / tpp + pu * PCG5_BLOCK, sub = tid % tpp;
+					if (pair < npairs && (pu == 0 || tpp == 1)) {       // nrows * 6 <= 2 * PCG5_BLOCK (checked on the host)
+						const int li = pair / 6, comp = pair - 6 * li;
+						int n0 = s_rowPtr[li], n1 = s_rowPtr[li + 1];
+						n0 = (n0 > cs ? n0 : cs) - cs;
+						n1 = (n1 < cs + PCG5_CHUNK ? n1 : cs + PCG5_CHUNK) - cs;
+						T s0 = T(0), s1 = T(0);
+						const T* col = s_cc + comp * PCG5_CHUNK;
+						int q = n0 + sub;
+						for (; q + tpp < n1; q += 2 * tpp) { s0 += col[q]; s1 += col[q + tpp]; }
+						if (q < n1) s0 += col[q];
+						wacc[pu] += s0 + s1;
+					}
 				}
 			}
-			for (int o = 1; o < tpp; o <<= 1) wacc += __shfl_xor_sync(0xffffffffu, wacc, o);
+			for (int o = 1; o < tpp; o <<= 1) wacc[0] += __shfl_xor_sync(0xffffffffu, wacc[0], o);
 			PCG_T(t6);
 			// ---- publish w (own board + the boards of the ranks that need the row), partial inner products, Z^^T w ----
 			// The nine quantities of the (row, component) threads go to shared memory; afterwards warp w adds quantity w (warp 0
 			// also the ninth) in a fixed order and its first REPL lanes publish the replicas.
 			const int nact = nrows * 6;                           // active threads: tid = pair * tpp
 			double* s_q = reinterpret_cast<double*>(smem_raw + lay.sq);   // [9][nact]; read below, rewritten only after the next pass's barriers
-			if (tid < nrows * 6 * tpp && (tid % tpp) == 0) {
-				const int pair = tid / tpp;
+#pragma unroll
+			for (int pu = 0; pu < NPU; pu++) {
+				const int pair = tid / tpp + pu * PCG5_BLOCK;
+				if (!(pair < npairs && (tid % tpp) == 0 && (pu == 0 || tpp == 1))) continue;
 				const int li = pair / 6, comp = pair - 6 * li;
 				const int dl = s_diag[li];
 				const T ri = s_r[6 * (size_t)dl + comp];
 				const T ui = s_v[6 * (size_t)dl + comp];
-				const T wv1 = wacc + ui;                                   // A^_ii = I
+				const T wv1 = wacc[pu] + ui;                                   // A^_ii = I
 				const size_t slot = wHalf + (size_t)opar * wStride + 6 * (size_t)(row0 + li) + comp;
 				ll_store(a.wBoard + 2 * slot, (double)wv1, otag);
 				if (world > 1) {
