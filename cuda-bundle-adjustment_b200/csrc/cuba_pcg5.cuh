@@ -532,18 +532,6 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 			for (int cs = 0; cs < nblkCta; cs += PCG5_CHUNK) {
 				if (cs > 0) __syncthreads();
 #pragma unroll
-								for (int c = 0; c < 6; c++) {
-									const T rc = rj[c];
-#pragma unroll
-									for (int r = 0; r < 6; r++) y[r] += bv[u][c * 6 + r] * rc;
-								}
-							}
-						}
-#pragma unroll
-						for (int r = 0; r < 6; r++) s_cc[r * PCG5_CHUNK + u * PCG5_BLOCK + tid] = y[r];
-					}
-				} else {
-#pragma unroll
 				for (int u = 0; u < PCG5_BPT; u++) {
 					const int n = cs + u * PCG5_BLOCK + tid;
 					T y[6] = { T(0), T(0), T(0), T(0), T(0), T(0) };
