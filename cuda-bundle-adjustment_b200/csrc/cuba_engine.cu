@@ -241,8 +241,10 @@ struct Engine : EngineBase {
 	DBuf<int> e_ip, e_il, e_hpl, e_user, lmPtr, tileLm, hplLm, posePtr, p_il;
 	// system
 	DBuf<T> Hpp, bp, Hll, bl, Hpl, invHll, fVal, bsc, xp, xl;
+	DBuf<T> uVal;            // landmark-sharded runs: upper Hsc blocks | bsc, the buffer of the per-trial all-reduce
 	DBuf<float> HplF;        // mixed precision (cfg.use_fp32 == 2, fp64 engine): the Hpl blocks in fp32, 20 floats per block
 	bool mixed = false;
+	bool upperReduce = false;   // k_schur3 writes the upper blocks into uVal; one all-reduce of uVal | bsc, then k_expand_upper
 	DBuf<int> prodPtr, prodI, prodJ, prodL, blkRow, blkCol, u2f, u2fT, fRowPtr, fColInd;
 	bool useSchur3 = true;
 	// pcg
@@ -718,6 +720,8 @@ struct Engine : EngineBase {
 		else CUDA_TRY(Hpl.alloc(18 * (size_t)S.nhplLocal));
 		CUDA_TRY(invHll.alloc(9 * nL));
 		CUDA_TRY(fVal.alloc(36 * (size_t)S.nfull + 6 * nP)); bsc.alias(fVal.p + 36 * (size_t)S.nfull, 6 * nP);
+		upperReduce = world > 1 && (cfg.reserved[3] == 0 || cfg.reserved[3] == 3 || cfg.use_fp32 == 2) && S.numP > 0 && S.numL > 0;
+		if (upperReduce) { CUDA_TRY(uVal.alloc(36 * (size_t)S.nblk + 6 * nP)); bsc.alias(uVal.p + 36 * (size_t)S.nblk, 6 * nP); }
 		CUDA_TRY(xp.alloc(6 * nP)); CUDA_TRY(xl.alloc(3 * nL));
 		CUDA_TRY(pr.alloc(6 * nP)); CUDA_TRY(pz.alloc(6 * nP)); CUDA_TRY(pq.alloc(6 * nP)); CUDA_TRY(pp0.alloc(6 * nP)); CUDA_TRY(pp1.alloc(6 * nP));
 		CUDA_TRY(Minv.alloc(36 * nP));
@@ -1067,12 +1071,12 @@ struct Engine : EngineBase {
 			a.Hpl = Hpl; a.invHll = invHll; a.bl = bl; a.Hpp = Hpp; a.bp = bp;
 			a.prodPtr = prodPtr; a.prodI = prodI; a.prodJ = prodJ; a.prodL = prodL;
 			a.blkRow = blkRow; a.blkCol = blkCol; a.u2f = u2f; a.u2fT = u2fT; a.nblk = S.nblk;
-			a.lambda = lambda; a.addDiag = rank == 0 ? 1 : 0; a.fVal = fVal; a.bsc = bsc;
+			a.lambda = lambda; a.addDiag = rank == 0 ? 1 : 0; a.fVal = fVal; a.bsc = bsc; a.uVal = upperReduce ? uVal.p : nullptr;
 			if (mixed) {
 				if constexpr (sizeof(T) == 8) {
 					schur3::Args<double, float> m;
 					m.Hpl = HplF; m.invHll = invHll; m.bl = bl; m.Hpp = Hpp; m.bp = bp; m.prodPtr = prodPtr; m.prodI = prodI; m.prodJ = prodJ; m.prodL = prodL;
-					m.blkRow = blkRow; m.blkCol = blkCol; m.u2f = u2f; m.u2fT = u2fT; m.nblk = S.nblk; m.lambda = lambda; m.addDiag = a.addDiag; m.fVal = fVal; m.bsc = bsc;
+					m.blkRow = blkRow; m.blkCol = blkCol; m.u2f = u2f; m.u2fT = u2fT; m.nblk = S.nblk; m.lambda = lambda; m.addDiag = a.addDiag; m.fVal = fVal; m.bsc = bsc; m.uVal = a.uVal;
 					schur3::k_schur3<double, float><<<(S.nblk + schur3::WARPS - 1) / schur3::WARPS, schur3::WARPS * 32, 0, stream>>>(m);
 				}
 			}
@@ -1080,7 +1084,12 @@ struct Engine : EngineBase {
 			else schur3::k_schur4<T><<<(S.nblk + schur3::WARPS - 1) / schur3::WARPS, schur3::WARPS * 32, 0, stream>>>(a);
 			launches++;
 			CUDA_TRY(cudaGetLastError());
-			if (world > 1) {
+			if (upperReduce) {
+				// upper blocks | bsc: one collective of half the bytes, then both triangles are filled locally
+				int rc = allreduce(uVal.p, 36 * (size_t)S.nblk + 6 * (size_t)S.numP, true); if (rc) return rc;
+				KLAUNCH(schur3::k_expand_upper<T>, 36LL * S.nblk, uVal.p, u2f.p, u2fT.p, blkRow.p, blkCol.p, S.nblk, fVal.p);
+			}
+			else if (world > 1) {
 				int rc = allreduce(fVal.p, 36 * (size_t)S.nfull + 6 * (size_t)S.numP, true); if (rc) return rc;   // Hsc | bsc: one buffer
 			}
 		}

@@ -36,6 +36,7 @@ struct Args {
 	T lambda;
 	int addDiag;
 	T* fVal; T* bsc;
+	T* uVal;     // landmark-sharded runs: the UPPER blocks only, [nblk][36] in block order (half the all-reduce; k_expand_upper mirrors them)
 };
 
 template <typename T, typename TH = T>
@@ -101,12 +102,28 @@ __global__ void __launch_bounds__(WARPS * 32, 3) k_schur3(const Args<T, TH> a)
 		if (e < 36) {
 			T val = -s;
 			if (diag && a.addDiag) val += a.Hpp[36 * (size_t)ra + e] + (rr == c ? a.lambda : T(0));
-			a.fVal[36 * (size_t)a.u2f[k] + e] = val;
-			if (!diag) a.fVal[36 * (size_t)a.u2fT[k] + rr * 6 + c] = val;
+			if (a.uVal) a.uVal[36 * (size_t)k + e] = val;
+			else {
+				a.fVal[36 * (size_t)a.u2f[k] + e] = val;
+				if (!diag) a.fVal[36 * (size_t)a.u2fT[k] + rr * 6 + c] = val;
+			}
 		} else if (diag) {
 			a.bsc[6 * (size_t)ra + rr] = (a.addDiag ? a.bp[6 * (size_t)ra + rr] : T(0)) - s;
 		}
 	}
+}
+
+// upper blocks (summed over the ranks) -> both triangles of the symmetric-full BSR
+template <typename T>
+__global__ void k_expand_upper(const T* __restrict__ uVal, const int* __restrict__ u2f, const int* __restrict__ u2fT, const int* __restrict__ blkRow,
+	const int* __restrict__ blkCol, int nblk, T* fVal)
+{
+	const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= 36LL * nblk) return;
+	const int k = (int)(w / 36), e = (int)(w - 36LL * k), c = e / 6, r = e - 6 * c;
+	const T v = uVal[w];
+	fVal[36 * (size_t)u2f[k] + e] = v;
+	if (blkRow[k] != blkCol[k]) fVal[36 * (size_t)u2fT[k] + r * 6 + c] = v;
 }
 
 }  // namespace schur3
