@@ -21,6 +21,7 @@
 #include "cuba_pcg4.cuh"
 #include "cuba_pcg5.cuh"
 #include "cuba_coarse_dense.cuh"
+#include "cuba_peer_reduce.cuh"
 #include "cuba_schur2.cuh"
 #include "cuba_jh4.cuh"
 #include "cuba_schur3.cuh"
@@ -285,7 +286,7 @@ struct Engine : EngineBase {
 	{
 		DevGuard guard(devOrdinal);
 		if (stream) cudaStreamSynchronize(stream);
-		p5CloseMappings();
+		p5CloseMappings(); uCloseMappings();
 		for (auto& pe : profEvents) { cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second); }
 		for (auto ev : eventPool) cudaEventDestroy(ev);
 		if (hScal) cudaFreeHost(hScal);
@@ -721,7 +722,29 @@ struct Engine : EngineBase {
 		CUDA_TRY(invHll.alloc(9 * nL));
 		CUDA_TRY(fVal.alloc(36 * (size_t)S.nfull + 6 * nP)); bsc.alias(fVal.p + 36 * (size_t)S.nfull, 6 * nP);
 		upperReduce = world > 1 && (cfg.reserved[3] == 0 || cfg.reserved[3] == 3 || cfg.use_fp32 == 2) && S.numP > 0 && S.numL > 0;
-		if (upperReduce) { CUDA_TRY(uVal.alloc(36 * (size_t)S.nblk + 6 * nP)); bsc.alias(uVal.p + 36 * (size_t)S.nblk, 6 * nP); }
+		if (upperReduce) {
+			uCount = 36 * (size_t)S.nblk + 6 * nP;
+			const size_t need = ((uCount + 1) & ~(size_t)1) + 64;          // + the signal block of the peer all-reduce
+			if (!uVal.p || need > uVal.cap) {
+				if (uMappedFor) { CUDA_TRY(cudaStreamSynchronize(stream)); uCloseMappings(); }
+				CUDA_TRY(uVal.alloc(std::max(need, (size_t)1 << 18)));
+				CUDA_TRY(cudaMemsetAsync(uVal.p, 0, sizeof(T) * uVal.cap, stream));
+				uEpoch = 0;
+			}
+			bsc.alias(uVal.p + 36 * (size_t)S.nblk, 6 * nP);
+			// map the peers' buffers; the signal block must sit at the same offset everywhere (it does: uCount is global)
+			uPeerOk = false;
+			if (!getenv("CUBA_NCCL_HSC")) {
+				// signals of an earlier problem may sit at another offset: start from a clean block (all ranks do, in lockstep)
+				CUDA_TRY(cudaMemsetAsync(uVal.p + ((uCount + 1) & ~(size_t)1), 0, sizeof(T) * 64, stream));
+				uEpoch = 0;
+				int rcx = allreduce(&dScal.p->v[7], 1, false); if (rcx) return rcx;          // nobody signals into a block that is being cleared
+				bool ok = false;
+				rcx = ipcExchange((void*)uVal.p, uPeerBase, uMappedFor, ok); if (rcx) return rcx;
+				uPeerOk = ok;
+				CUDA_TRY(gridBar.alloc(1));
+			}
+		}
 		CUDA_TRY(xp.alloc(6 * nP)); CUDA_TRY(xl.alloc(3 * nL));
 		CUDA_TRY(pr.alloc(6 * nP)); CUDA_TRY(pz.alloc(6 * nP)); CUDA_TRY(pq.alloc(6 * nP)); CUDA_TRY(pp0.alloc(6 * nP)); CUDA_TRY(pp1.alloc(6 * nP));
 		CUDA_TRY(Minv.alloc(36 * nP));
@@ -1086,7 +1109,7 @@ struct Engine : EngineBase {
 			CUDA_TRY(cudaGetLastError());
 			if (upperReduce) {
 				// upper blocks | bsc: one collective of half the bytes, then both triangles are filled locally
-				int rc = allreduce(uVal.p, 36 * (size_t)S.nblk + 6 * (size_t)S.numP, true); if (rc) return rc;
+				int rc = uPeerOk ? launch_peer_allreduce() : allreduce(uVal.p, 36 * (size_t)S.nblk + 6 * (size_t)S.numP, true); if (rc) return rc;
 				KLAUNCH(schur3::k_expand_upper<T>, 36LL * S.nblk, uVal.p, u2f.p, u2fT.p, blkRow.p, blkCol.p, S.nblk, fVal.p);
 			}
 			else if (world > 1) {
@@ -1415,28 +1438,29 @@ struct Engine : EngineBase {
 		p5MappedFor = nullptr;
 	}
 
-	// Maps the boards of every peer into this process (cudaIpc over NVLink peer access); the 64-byte handles travel by
-	// ncclAllGather.  All ranks agree on the outcome (sum of per-rank success flags), so either everybody runs the distributed
-	// solve or everybody keeps the replicated one.
-	int p5Exchange(bool& ok)
+	// Maps one device allocation of every peer into this process (cudaIpc over NVLink peer access); the 64-byte handles travel by
+	// ncclAllGather.  All ranks agree on the outcome (sum of per-rank success flags), so either everybody uses the peer path or
+	// everybody keeps the NCCL one.
+	int ipcExchange(void* localBase, void** peerBase, void*& mappedFor, bool& ok)
 	{
 		ok = false;
-		if (p5MappedFor == (void*)p5Boards.p) { ok = true; return CUBA_OK; }
-		p5CloseMappings();
+		if (mappedFor == localBase) { ok = true; return CUBA_OK; }
+		for (int r = 0; r < PCG5_MAXWORLD; r++) { if (peerBase[r] && r != rank) cudaIpcCloseMemHandle(peerBase[r]); peerBase[r] = nullptr; }
+		mappedFor = nullptr;
 		cudaIpcMemHandle_t mine;
-		int good = cudaIpcGetMemHandle(&mine, p5Boards.p) == cudaSuccess ? 1 : 0;
+		int good = cudaIpcGetMemHandle(&mine, localBase) == cudaSuccess ? 1 : 0;
 		if (!good) cudaGetLastError();
 		DBuf<char> dh;
 		CUDA_TRY(dh.alloc(sizeof(cudaIpcMemHandle_t) * (size_t)world));
 		CUDA_TRY(cudaMemcpyAsync(dh.p + sizeof(cudaIpcMemHandle_t) * (size_t)rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, stream));
 		int rc = g_nccl.AllGather(dh.p + sizeof(cudaIpcMemHandle_t) * (size_t)rank, dh.p, sizeof(cudaIpcMemHandle_t), NCCL_INT8, comm, stream);
-		if (rc != 0) return fail(CUBA_ERR_COMM, "ncclAllGather (board handles) failed");
+		if (rc != 0) return fail(CUBA_ERR_COMM, "ncclAllGather (memory handles) failed");
 		std::vector<cudaIpcMemHandle_t> all(world);
 		CUDA_TRY(cudaMemcpyAsync(all.data(), dh.p, sizeof(cudaIpcMemHandle_t) * (size_t)world, cudaMemcpyDeviceToHost, stream));
 		CUDA_TRY(cudaStreamSynchronize(stream));
 		for (int r = 0; r < world && good; r++) {
-			if (r == rank) { p5PeerBase[r] = (void*)p5Boards.p; continue; }
-			if (cudaIpcOpenMemHandle(&p5PeerBase[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); p5PeerBase[r] = nullptr; good = 0; }
+			if (r == rank) { peerBase[r] = localBase; continue; }
+			if (cudaIpcOpenMemHandle(&peerBase[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); peerBase[r] = nullptr; good = 0; }
 		}
 		// agreement
 		DBuf<double> flag;
@@ -1447,9 +1471,38 @@ struct Engine : EngineBase {
 		double tot = 0;
 		CUDA_TRY(cudaMemcpyAsync(&tot, flag.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
 		CUDA_TRY(cudaStreamSynchronize(stream));
-		if ((int)(tot + 0.5) != world) { p5CloseMappings(); return CUBA_OK; }
-		p5MappedFor = (void*)p5Boards.p;
+		if ((int)(tot + 0.5) != world) {
+			for (int r = 0; r < PCG5_MAXWORLD; r++) { if (peerBase[r] && r != rank) cudaIpcCloseMemHandle(peerBase[r]); peerBase[r] = nullptr; }
+			return CUBA_OK;
+		}
+		mappedFor = localBase;
 		ok = true;
+		return CUBA_OK;
+	}
+	int p5Exchange(bool& ok) { return ipcExchange((void*)p5Boards.p, p5PeerBase, p5MappedFor, ok); }
+
+	// ---- the per-trial Hsc | bsc all-reduce over peer memory (cuba_peer_reduce.cuh) ----
+	void* uPeerBase[PCG5_MAXWORLD] = { nullptr };
+	void* uMappedFor = nullptr;
+	bool uPeerOk = false;
+	unsigned int uEpoch = 0;
+	size_t uCount = 0;             // elements of the all-reduced part of uVal
+	void uCloseMappings()
+	{
+		for (int r = 0; r < PCG5_MAXWORLD; r++) { if (uPeerBase[r] && r != rank) cudaIpcCloseMemHandle(uPeerBase[r]); uPeerBase[r] = nullptr; }
+		uMappedFor = nullptr; uPeerOk = false;
+	}
+	int launch_peer_allreduce()
+	{
+		peer::Args<T> pa;
+		pa.local = uVal.p; pa.n = uCount; pa.rank = rank; pa.world = world; pa.epoch = ++uEpoch; pa.bar = gridBar;
+		const size_t sigOff = (uCount + 1) & ~(size_t)1;       // the signal block sits behind the data (element units)
+		for (int r = 0; r < peer::MAXW; r++) { pa.peers[r] = nullptr; pa.sigPeer[r] = nullptr; }
+		for (int r = 0; r < world; r++) { pa.peers[r] = (T*)uPeerBase[r]; pa.sigPeer[r] = (unsigned int*)((T*)uPeerBase[r] + sigOff); }
+		pa.sigLocal = (unsigned int*)(uVal.p + sigOff);
+		void* args[] = { (void*)&pa };
+		CUDA_TRY(cudaLaunchCooperativeKernel((void*)peer::k_peer_allreduce<T>, dim3(numSMs), dim3(peer::BLOCK), args, 0, stream));
+		launches++;
 		return CUBA_OK;
 	}
 
