@@ -349,7 +349,7 @@ struct Engine : EngineBase {
 	// ---- collectives (landmark-sharded runs) ----------------------------------------------------------
 	int allreduce(void* buf, size_t count, bool isT)
 	{
-		if (world <= 1) return CUBA_OK;
+		if (world <= 1 || !comm) return CUBA_OK;      // (!comm: CUBA_DRY_SHARD diagnosis, one shard of a sharded run timed on one GPU)
 		const int dt = isT ? (sizeof(T) == 8 ? NCCL_FLOAT64 : NCCL_FLOAT32) : NCCL_FLOAT64;
 		const int rc = g_nccl.AllReduce(buf, buf, count, dt, NCCL_SUM, comm, stream);
 		if (rc != 0) return fail(CUBA_ERR_COMM, std::string("ncclAllReduce failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
@@ -658,7 +658,7 @@ struct Engine : EngineBase {
 		KLAUNCH(k_prod_emit, nhpl, g_hplLmG.p, g_hplColPtr.p, g_hplRowInd.p, g_off.p, nhpl, S.lmBeg, S.lmEnd, S.hplBase, g_pkey.p, g_pkeyVal.p, g_pi.p, g_pj.p);
 		KLAUNCH(k_prod_diag, numP, numP, nmul, g_pkey.p, g_pkeyVal.p, g_pi.p, g_pj.p);
 		rc = sortPairs(g_pkey.p, g_pkeyS.p, g_pkeyVal.p, g_pvalS.p, (int)N, 32 + bits_for((unsigned long long)std::max(numP, 1))); if (rc) return rc;
-		CUDA_TRY(g_head.alloc((size_t)N)); CUDA_TRY(g_blkId.alloc((size_t)N));
+		CUDA_TRY(g_head.alloc((size_t)N + 1)); CUDA_TRY(g_blkId.alloc((size_t)N + 1));
 		KLAUNCH(k_heads, N, g_pkeyS.p, (int)N, g_head.p);
 		rc = exclusiveSum(g_head.p, g_blkId.p, (int)N); if (rc) return rc;
 		k_nblk<<<1, 32, 0, stream>>>(g_head.p, g_blkId.p, (int)N, g_meta.p);
@@ -673,6 +673,20 @@ struct Engine : EngineBase {
 		KLAUNCH(k_blocks, N + 1, g_pkeyS.p, g_pvalS.p, g_head.p, g_blkId.p, g_pi.p, g_pj.p, (int)N, blkRow.p, blkCol.p, prodPtr.p, prodI.p, prodJ.p);
 		CUDA_TRY(g_hscRowPtr.alloc((size_t)numP + 1));
 		KLAUNCH(k_rowptr_from_rows, numP + 1, blkRow.p, nblk, numP, g_hscRowPtr.p);
+		int* dLocalCount = nullptr;
+		if (world > 1) {
+			// the sorted list holds every rank's products (the block numbering must be global); a destination's warp would walk all of
+			// them and skip the foreign ones -- the Schur kernel then does not speed up with the rank count (measured: 1.34 ms for a
+			// 1/8 shard of the 10 M-edge graph against 3.7 ms for the whole).  Keep the local products and the diagonal placeholders only.
+			CUDA_TRY(g_head.alloc((size_t)N + 1)); CUDA_TRY(g_blkId.alloc((size_t)N + 1));
+			KLAUNCH(k_local_flag, N + 1, prodI.p, prodJ.p, (int)N, g_head.p);
+			rc = exclusiveSum(g_head.p, g_blkId.p, (int)N + 1); if (rc) return rc;
+			KLAUNCH(k_compact_products, N, prodI.p, prodJ.p, g_head.p, g_blkId.p, (int)N, g_pi.p, g_pj.p);
+			KLAUNCH(k_remap_ptr, nblk + 1, g_blkId.p, nblk, prodPtr.p);
+			CUDA_TRY(cudaMemcpyAsync(prodI.p, g_pi.p, sizeof(int) * (size_t)N, cudaMemcpyDeviceToDevice, stream));
+			CUDA_TRY(cudaMemcpyAsync(prodJ.p, g_pj.p, sizeof(int) * (size_t)N, cudaMemcpyDeviceToDevice, stream));
+			dLocalCount = g_blkId.p + N;
+		}
 		// 6. symmetric-full BSR for the PCG
 		const int nfull = 2 * nblk - numP;
 		S.nfull = nfull;
@@ -687,9 +701,12 @@ struct Engine : EngineBase {
 		g_d2hBytes += (long long)(sizeof(int) * ((size_t)numP + 1 + nfull));
 		CUDA_TRY(cudaMemcpyAsync(S.fRowPtr.data(), fRowPtr.p, sizeof(int) * ((size_t)numP + 1), cudaMemcpyDeviceToHost, stream));
 		if (nfull > 0) CUDA_TRY(cudaMemcpyAsync(S.fColInd.data(), fColInd.p, sizeof(int) * (size_t)nfull, cudaMemcpyDeviceToHost, stream));
+		int localCount = (int)N;
+		if (dLocalCount) CUDA_TRY(cudaMemcpyAsync(&localCount, dLocalCount, sizeof(int), cudaMemcpyDeviceToHost, stream));
 		tmark("queued to sync 4");
 		CUDA_TRY(cudaStreamSynchronize(stream));                                  // sync point 4
 		tmark("sync 4");
+		S.nmulLocal = localCount;
 		return CUBA_OK;
 	}
 
@@ -734,7 +751,7 @@ struct Engine : EngineBase {
 			bsc.alias(uVal.p + 36 * (size_t)S.nblk, 6 * nP);
 			// map the peers' buffers; the signal block must sit at the same offset everywhere (it does: uCount is global)
 			uPeerOk = false;
-			if (!getenv("CUBA_NCCL_HSC")) {
+			if (!getenv("CUBA_NCCL_HSC") && comm) {
 				// signals of an earlier problem may sit at another offset: start from a clean block (all ranks do, in lockstep)
 				CUDA_TRY(cudaMemsetAsync(uVal.p + ((uCount + 1) & ~(size_t)1), 0, sizeof(T) * 64, stream));
 				uEpoch = 0;
@@ -1043,7 +1060,7 @@ struct Engine : EngineBase {
 			CUDA_TRY(cudaGetLastError());
 		}
 		if (world > 1) {
-			const int rcn = g_nccl.AllReduce(&dScal.p->maxdiag, &dScal.p->maxdiag, 1, NCCL_FLOAT64, NCCL_MAX, comm, stream);
+			const int rcn = comm ? g_nccl.AllReduce(&dScal.p->maxdiag, &dScal.p->maxdiag, 1, NCCL_FLOAT64, NCCL_MAX, comm, stream) : 0;
 			if (rcn != 0) return fail(CUBA_ERR_COMM, "ncclAllReduce(max) failed");
 		}
 		int rc = fetchScalars(); if (rc) return rc;
@@ -1084,10 +1101,14 @@ struct Engine : EngineBase {
 			}
 			return CUBA_OK;
 		}
-		if (S.numL > 0) {
-			k_inv_hll<T><<<(S.numL + 255) / 256, 256, 0, stream>>>(Hll, S.numL, lambda, invHll);
-			launches++;
-			CUDA_TRY(cudaGetLastError());
+		{
+			// the inverses of this rank's landmarks only (nobody reads the others here)
+			const int l0 = std::min(S.lmBeg, S.numL), l1 = std::min(S.lmEnd, S.numL);
+			if (l1 > l0) {
+				k_inv_hll<T><<<(l1 - l0 + 255) / 256, 256, 0, stream>>>(Hll.p + 9 * (size_t)l0, l1 - l0, lambda, invHll.p + 9 * (size_t)l0);
+				launches++;
+				CUDA_TRY(cudaGetLastError());
+			}
 		}
 		if (useSchur3 && S.numP > 0 && S.numL > 0) {
 			schur3::Args<T> a;
@@ -1109,8 +1130,19 @@ struct Engine : EngineBase {
 			CUDA_TRY(cudaGetLastError());
 			if (upperReduce) {
 				// upper blocks | bsc: one collective of half the bytes, then both triangles are filled locally
+				static const bool timing = getenv("CUBA_SCHUR_TIMING") != nullptr;      // diagnosis: split of the stage, printed by rank 0
+				cudaEvent_t ev[3];
+				if (timing) { for (auto& e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], stream); }
 				int rc = uPeerOk ? launch_peer_allreduce() : allreduce(uVal.p, 36 * (size_t)S.nblk + 6 * (size_t)S.numP, true); if (rc) return rc;
+				if (timing) cudaEventRecord(ev[1], stream);
 				KLAUNCH(schur3::k_expand_upper<T>, 36LL * S.nblk, uVal.p, u2f.p, u2fT.p, blkRow.p, blkCol.p, S.nblk, fVal.p);
+				if (timing) {
+					cudaEventRecord(ev[2], stream); cudaEventSynchronize(ev[2]);
+					float a1 = 0, a2 = 0; cudaEventElapsedTime(&a1, ev[0], ev[1]); cudaEventElapsedTime(&a2, ev[1], ev[2]);
+					static int count = 0;
+					if (rank == 0 && (count++ % 16) == 8) fprintf(stderr, "schur split: all-reduce (%s) %.3f ms, expand %.3f ms, %zu elements\n", uPeerOk ? "peer" : "nccl", a1, a2, uCount);
+					for (auto& e : ev) cudaEventDestroy(e);
+				}
 			}
 			else if (world > 1) {
 				int rc = allreduce(fVal.p, 36 * (size_t)S.nfull + 6 * (size_t)S.numP, true); if (rc) return rc;   // Hsc | bsc: one buffer
@@ -1514,7 +1546,7 @@ struct Engine : EngineBase {
 		if (numP < 1) return CUBA_OK;
 		const int mode = cfg.reserved[0];
 		if (mode == 1 || mode == 2 || mode == 3 || mode == 4) return CUBA_OK;          // an older kernel was asked for explicitly
-		const bool wantDist = world > 1 && mode != 7 && (mode == 8 || numP >= 2048);
+		const bool wantDist = world > 1 && comm && mode != 7 && (mode == 8 || numP >= 2048);
 		const int W = wantDist ? world : 1;
 		int smemMax = 0;
 		CUDA_TRY(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, devOrdinal));
@@ -2178,6 +2210,7 @@ int cuba_engine_set_comm(cuba_engine* e, int rank, int world, const void* uid)
 	if (e->impl->haveProblem) return fail(CUBA_ERR_STATE, "set_comm must precede set_problem");
 	e->impl->rank = rank; e->impl->world = world;
 	if (world == 1) return CUBA_OK;
+	if (getenv("CUBA_DRY_SHARD")) return CUBA_OK;      // diagnosis: keep the shard, skip every collective (results are then partial sums)
 	if (!uid) return fail(CUBA_ERR_INVALID, "set_comm: null unique id");
 	std::string why;
 	if (!g_nccl.load(why)) return fail(CUBA_ERR_COMM, why);

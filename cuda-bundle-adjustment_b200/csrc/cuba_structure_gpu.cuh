@@ -259,6 +259,27 @@ __global__ void k_blocks(const unsigned long long* __restrict__ keys, const int*
 	prodI[i] = pi[s]; prodJ[i] = pj[s];
 }
 
+// ---- landmark-sharded runs: keep only this rank's products (and the diagonal placeholders) in the destination-sorted list ----
+__global__ void k_local_flag(const int* __restrict__ prodI, const int* __restrict__ prodJ, int n, int* flag)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i > n) return;
+	flag[i] = (i < n && (prodI[i] >= 0 || prodJ[i] < 0)) ? 1 : 0;      // local product, or the placeholder of a diagonal block
+}
+__global__ void k_compact_products(const int* __restrict__ prodI, const int* __restrict__ prodJ, const int* __restrict__ flag, const int* __restrict__ pos,
+	int n, int* outI, int* outJ)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n || !flag[i]) return;
+	outI[pos[i]] = prodI[i]; outJ[pos[i]] = prodJ[i];
+}
+__global__ void k_remap_ptr(const int* __restrict__ pos, int nblk, int* prodPtr)
+{
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k > nblk) return;
+	prodPtr[k] = pos[prodPtr[k]];
+}
+
 // rowPtr[a] = first block k with blkRow[k] >= a
 __global__ void k_rowptr_from_rows(const int* __restrict__ rows, int n, int numP, int* rowPtr)
 {

@@ -25,6 +25,9 @@ for workload in args or ["kitti00_shaped"]:
     prob = pkg.graphio.flatten(g)
     for sv in schur:
         eng = pkg.Engine(device=0, schur_variant=sv, use_fp32=("mixed" if os.environ.get("MIXED") else False))
+        if os.environ.get("CUBA_DRY_SHARD"):
+            r, w = os.environ["CUBA_DRY_SHARD"].split("/")
+            eng.set_comm(int(r), int(w), b"\0" * 128)
         eng.initialize(prob)
         eng.linearize()
         lam = 1e-5 * eng.max_diagonal()
