@@ -72,6 +72,19 @@ private:
 	T* p_ = nullptr; size_t n_ = 0, cap_ = 0; bool pinned_ = false;
 };
 
+// splits [0, n) over a few host threads (the loops over vertex / edge objects are pointer chasing: memory-latency bound)
+template <class F>
+static void parallel_for(size_t n, F fn)
+{
+	unsigned nthreads = static_cast<unsigned>(std::min<size_t>(8, n / 32768 + 1));
+	nthreads = std::max(1u, std::min(nthreads, std::max(1u, std::thread::hardware_concurrency())));
+	if (nthreads == 1) { fn(size_t(0), n); return; }
+	std::vector<std::thread> pool;
+	for (unsigned t = 1; t < nthreads; t++) pool.emplace_back(fn, n * t / nthreads, n * (t + 1) / nthreads);
+	fn(size_t(0), n / nthreads);
+	for (auto& th : pool) th.join();
+}
+
 class Impl : public CudaBundleAdjustment
 {
 public:
@@ -170,7 +183,7 @@ public:
 			cam_[5 * i] = v->camera.fx; cam_[5 * i + 1] = v->camera.fy; cam_[5 * i + 2] = v->camera.cx;
 			cam_[5 * i + 3] = v->camera.cy; cam_[5 * i + 4] = v->camera.bf;
 		}
-		for (size_t i = 0; i < vL_.size(); i++) for (int k = 0; k < 3; k++) Xw_[3 * i + k] = vL_[i]->Xw.data()[k];
+		parallel_for(vL_.size(), [this](size_t b, size_t e) { for (size_t i = b; i < e; i++) for (int k = 0; k < 3; k++) Xw_[3 * i + k] = vL_[i]->Xw.data()[k]; });
 
 		// edges: every list entry is written at its own position by a few threads; only if an edge with both ends fixed
 		// turned up (they are dropped, cpp:210-211) the arrays are closed up afterwards
@@ -270,7 +283,7 @@ public:
 			for (int k = 0; k < 4; k++) vP_[i]->q.coeffs().data()[k] = q_[4 * i + k];
 			for (int k = 0; k < 3; k++) vP_[i]->t.data()[k] = t_[3 * i + k];
 		}
-		for (size_t i = 0; i < vL_.size(); i++) for (int k = 0; k < 3; k++) vL_[i]->Xw.data()[k] = Xw_[3 * i + k];
+		parallel_for(vL_.size(), [this](size_t b, size_t e) { for (size_t i = b; i < e; i++) for (int k = 0; k < 3; k++) vL_[i]->Xw.data()[k] = Xw_[3 * i + k]; });
 
 		// getChiSqs(): the values now, the pointer -> value map when somebody asks (chiSquared)
 		chi_.resize(om2_.size() + om3_.size());

@@ -1,6 +1,8 @@
 /*
- * cuda_bundle_adjustment.h -- the cuba::CudaBundleAdjustment interface, re-authored for the B200-native
- * engine.  Method-for-method the same abstract class as the reference's
+ * cuda_bundle_adjustment.h -- the cuba::CudaBundleAdjustment interface for the B200-native engine.
+ * INTERFACE DERIVED FROM fixstars/cuda-bundle-adjustment (Copyright 2020 Fixstars Corporation, Apache License 2.0,
+ * http://www.apache.org/licenses/LICENSE-2.0): the virtual-method order fixes the vtable a drop-in must share.
+ * Method-for-method the same abstract class as the reference's
  * include/cuda_bundle_adjustment.h:34-125 (@4390e13); create() returns the implementation in
  * libcuba_b200.so (csrc/cuba_api.cpp), which flattens the graph like the reference's
  * CudaBlockSolver::initialize (src/cuda_bundle_adjustment.cpp:115-261) and drives the C ABI of

@@ -1,8 +1,11 @@
 /*
- * cuda_bundle_adjustment_types.h -- graph types of the cuba:: API, re-authored for the B200-native
- * engine (no text taken from the reference).  Same names, members and semantics as the reference's
- * include/cuda_bundle_adjustment_types.h (@4390e13) so that user code written against
- * fixstars/cuda-bundle-adjustment compiles unchanged:
+ * cuda_bundle_adjustment_types.h -- graph types of the cuba:: API for the B200-native engine.
+ *
+ * INTERFACE DECLARATIONS DERIVED FROM fixstars/cuda-bundle-adjustment (include/cuda_bundle_adjustment_types.h @4390e13,
+ * Copyright 2020 Fixstars Corporation, Apache License 2.0, http://www.apache.org/licenses/LICENSE-2.0): a source-compatible
+ * drop-in must reproduce the type names, the member order and the constructor signatures of Edge<DIM>, PoseVertex and
+ * LandmarkVertex, so the declarations below necessarily match the reference's; comments and everything behind the interface
+ * are this repository's own.  User code written against the reference compiles unchanged:
  *
  *   Array<T,N>, Set<T>, UniquePtr<T>          reference types.h:36-43
  *   CameraParams {fx,fy,cx,cy,bf}             :51-62

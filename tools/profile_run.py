@@ -11,7 +11,8 @@ workload = sys.argv[1] if len(sys.argv) > 1 else "kitti00_shaped"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 robust = sys.argv[3] if len(sys.argv) > 3 else "none"
 KERNELS = {"none": ((0, 0), (0.0, 0.0)), "huber": ((1, 1), (5.991 ** 0.5, 7.815 ** 0.5))}
-prob = pkg.graphio.flatten(pkg.synth.make_config(workload))
+path = os.path.join(ROOT, "oracle", "_ref", "fixtures", workload + ".cubagraph")
+prob = pkg.graphio.flatten(pkg.graphio.read_graph(path) if workload.startswith("ba_") else pkg.synth.make_config(workload))
 eng = pkg.Engine(device=0)
 for et in (0, 1):
     eng.set_robust_kernels(KERNELS[robust][0][et], KERNELS[robust][1][et], et)
