@@ -439,6 +439,7 @@ struct Engine : EngineBase {
 			fprintf(stderr, "setup total %8.3f ms\n", 1e3 * std::chrono::duration<double>(marks.back().second - marks.front().second).count());
 		}
 		cur = 0; trialValid = false;
+		tlActive = false; coarseValid = false; coarseAge = 0; p5CoarseValid = false; p5CoarseAge = 0;
 		resolveProfile();   // drop the events of earlier problems
 		for (int i = 0; i < CUBA_PROF_NUM; i++) prof[i] = 0;
 		const auto t1 = std::chrono::steady_clock::now();
@@ -1287,8 +1288,11 @@ struct Engine : EngineBase {
 		CUDA_TRY(gridBar.alloc(1));
 		CUDA_TRY(cudaMemsetAsync(gridBar.p, 0, sizeof(GridBar), stream));
 		tmark("  pcg2 partition + uploads");
-		// ---- two-level PCG: aggregates = groups of gs consecutive CTAs (at most PCG4_MAXAGG of them) ----
-		{
+		// ---- two-level PCG of round 1 (k_pcg4): aggregates = groups of gs consecutive CTAs (at most PCG4_MAXAGG of them).
+		//      Only prepared when it can be asked for: explicitly (reserved[0] == 3), by the fp32 engine, or as the fallback for systems
+		//      beyond k_pcg5's 85 rows per CTA; otherwise its host lists and uploads are skipped (k_pcg5 has its own plan) ----
+		pcg4Ok = false;
+		if (cfg.reserved[0] == 3 || sizeof(T) != 8 || numP > 80 * numSMs * (world > 1 && numP >= 2048 ? world : 1)) {
 			// up to 74 aggregates (coarse inverse in the shared memory of an 8-CTA cluster), 37 with cfg.reserved[6] == 37 (one CTA)
 			const int maxAgg = (cfg.reserved[6] > 0 && cfg.reserved[6] < PCG4_MAXAGG) ? cfg.reserved[6] : PCG4_MAXAGG;
 			CoarsePartition CP;
