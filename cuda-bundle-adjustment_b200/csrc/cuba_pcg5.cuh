@@ -117,6 +117,48 @@ struct Pcg5Args {
 	long long* timing;               // [G][8] per-phase clock64 sums (only with -DCUBA_PCG_TIMING)
 };
 
+// chol6_factor_and_inverse of cuba_pcg4.cuh with every loop unrolled: L and Li live in registers instead of local memory
+// (k_pcg5_prep_rows ran 53 us for 1 321 rows with the rolled version, profiles/r02_launches_k00_bench.csv).  Same operations
+// in the same order.
+template <typename T>
+__device__ __forceinline__ bool chol6_factor_and_inverse_u(const T* A, T* L, T* Li)
+{
+#pragma unroll
+	for (int i = 0; i < 36; i++) { L[i] = T(0); Li[i] = T(0); }
+	bool ok = true;
+#pragma unroll
+	for (int j = 0; j < 6; j++) {
+		T d = A[j * 6 + j];
+#pragma unroll
+		for (int k = 0; k < 6; k++) if (k < j) d -= L[k * 6 + j] * L[k * 6 + j];
+		if (!(d > T(0))) ok = false;
+		d = t_sqrt(ok ? d : T(1));
+		L[j * 6 + j] = d;
+		const T id = 1 / d;
+#pragma unroll
+		for (int i = 0; i < 6; i++) {
+			if (i <= j) continue;
+			T s = A[j * 6 + i];
+#pragma unroll
+			for (int k = 0; k < 6; k++) if (k < j) s -= L[k * 6 + i] * L[k * 6 + j];
+			L[j * 6 + i] = s * id;
+		}
+	}
+#pragma unroll
+	for (int j = 0; j < 6; j++) {
+		Li[j * 6 + j] = 1 / L[j * 6 + j];
+#pragma unroll
+		for (int i = 0; i < 6; i++) {
+			if (i <= j) continue;
+			T s = T(0);
+#pragma unroll
+			for (int k = 0; k < 6; k++) if (k >= j && k < i) s -= L[k * 6 + i] * Li[j * 6 + k];
+			Li[j * 6 + i] = s / L[i * 6 + i];
+		}
+	}
+	return ok;
+}
+
 // ---- preparation: factor every diagonal block, b^ = L^-1 b, Z^ = L^T Z, per-row share of rc0 = Z^^T b^ ----------------
 template <typename T>
 struct Pcg5PrepArgs {
@@ -133,23 +175,41 @@ __global__ void k_pcg5_prep_rows(const Pcg5PrepArgs<T> a)
 	int d = -1;
 	for (int n = a.fRowPtr[i]; n < a.fRowPtr[i + 1]; n++) if (a.fColInd[n] == i) { d = n; break; }
 	T L[36], Li[36];
-	const bool ok = d >= 0 && chol6_factor_and_inverse(a.fVal + 36 * (size_t)d, L, Li);
-	if (!ok) { atomicAdd(&a.ctl->nbad, 1); for (int e = 0; e < 36; e++) { Li[e] = (e % 7) == 0 ? T(1) : T(0); L[e] = Li[e]; } }
+	T Ad[36];
+#pragma unroll
+	for (int e = 0; e < 36; e++) Ad[e] = d >= 0 ? a.fVal[36 * (size_t)d + e] : T(0);
+	const bool ok = d >= 0 && chol6_factor_and_inverse_u(Ad, L, Li);
+	if (!ok) {
+		atomicAdd(&a.ctl->nbad, 1);
+#pragma unroll
+		for (int e = 0; e < 36; e++) { Li[e] = (e % 7) == 0 ? T(1) : T(0); L[e] = Li[e]; }
+	}
+#pragma unroll
 	for (int e = 0; e < 36; e++) a.Linv[36 * (size_t)i + e] = Li[e];
-	T bh[6];
+	T bh[6], bi[6];
+#pragma unroll
+	for (int c = 0; c < 6; c++) bi[c] = a.b[6 * (size_t)i + c];
+#pragma unroll
 	for (int r = 0; r < 6; r++) {
 		T s = T(0);
-		for (int c = 0; c <= r; c++) s += Li[c * 6 + r] * a.b[6 * (size_t)i + c];
+#pragma unroll
+		for (int c = 0; c < 6; c++) if (c <= r) s += Li[c * 6 + r] * bi[c];
 		bh[r] = s;
 		a.R0[6 * (size_t)i + r] = s;
 	}
 	if (a.A > 0) {
 		const T* Z = a.Zx + 36 * (size_t)i;
+#pragma unroll
 		for (int q = 0; q < 6; q++) {
+			T zq[6];
+#pragma unroll
+			for (int k = 0; k < 6; k++) zq[k] = Z[q * 6 + k];
 			T rcq = T(0);
+#pragma unroll
 			for (int r = 0; r < 6; r++) {
 				T s = T(0);
-				for (int k = r; k < 6; k++) s += L[r * 6 + k] * Z[q * 6 + k];       // Z^(r,q) = sum_{k>=r} L(k,r) Z(k,q)
+#pragma unroll
+				for (int k = 0; k < 6; k++) if (k >= r) s += L[r * 6 + k] * zq[k];       // Z^(r,q) = sum_{k>=r} L(k,r) Z(k,q)
 				a.Zhat[36 * (size_t)i + q * 6 + r] = s;
 				rcq += s * bh[r];
 			}
