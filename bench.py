@@ -537,6 +537,11 @@ def main():
                 except Exception as ex:
                     configs.append({"config": name, "workload": wl, "robust_kernel": rb, "error": str(ex)[-200:]})
             line["configs"] = configs
+            # the N > 1 headline workload measured on ONE GPU in this same run: the base of the strong-scaling curve
+            c4 = [c for c in configs if c.get("config") == "C4" and "value" in c]
+            if c4:
+                line["scaling_base"] = {"workload": c4[0]["workload"], "n_gpus": 1, "value": c4[0]["value"], "ms_per_step": c4[0]["ms_per_step"],
+                                        "note": "bench.py --gpus N>1 runs this workload; divide its value by N x this value for the scaling efficiency"}
         else:
             try:
                 p = build_problem(pkg, "kitti00_shaped")
