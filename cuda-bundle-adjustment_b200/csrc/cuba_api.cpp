@@ -72,17 +72,28 @@ private:
 	T* p_ = nullptr; size_t n_ = 0, cap_ = 0; bool pinned_ = false;
 };
 
-// splits [0, n) over a few host threads (the loops over vertex / edge objects are pointer chasing: memory-latency bound)
+// Host loops over vertex / edge objects are pointer chasing (memory-latency bound): a few threads, each prefetching ahead.
+static unsigned host_threads(size_t n, size_t grain)
+{
+	const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+	return static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(std::min<size_t>(16, hw), n / grain + 1)));
+}
+
+// runs fn(t, begin, end) for the t-th of nthreads equal slices of [0, n)
+template <class F>
+static void parallel_slices(size_t n, unsigned nthreads, F fn)
+{
+	if (nthreads <= 1) { fn(0u, size_t(0), n); return; }
+	std::vector<std::thread> pool;
+	for (unsigned t = 1; t < nthreads; t++) pool.emplace_back(fn, t, n * t / nthreads, n * (t + 1) / nthreads);
+	fn(0u, size_t(0), n / nthreads);
+	for (auto& th : pool) th.join();
+}
+
 template <class F>
 static void parallel_for(size_t n, F fn)
 {
-	unsigned nthreads = static_cast<unsigned>(std::min<size_t>(8, n / 32768 + 1));
-	nthreads = std::max(1u, std::min(nthreads, std::max(1u, std::thread::hardware_concurrency())));
-	if (nthreads == 1) { fn(size_t(0), n); return; }
-	std::vector<std::thread> pool;
-	for (unsigned t = 1; t < nthreads; t++) pool.emplace_back(fn, n * t / nthreads, n * (t + 1) / nthreads);
-	fn(size_t(0), n / nthreads);
-	for (auto& th : pool) th.join();
+	parallel_slices(n, host_threads(n, 32768), [&fn](unsigned, size_t b, size_t e) { fn(b, e); });
 }
 
 class Impl : public CudaBundleAdjustment
@@ -165,17 +176,48 @@ public:
 			orderDirty_ = false;
 		}
 		// index assignment: ascending id, free vertices first, fixed ones appended, vertices without edges skipped
-		vP_.clear(); vL_.clear();
-		vP_.reserve(orderP_.size()); vL_.reserve(orderL_.size());
+		vP_.clear();
+		vP_.reserve(orderP_.size());
 		size_t nFixedP = 0, nFixedL = 0;
 		for (PoseVertex* v : orderP_) { if (v->edges.empty()) continue; if (v->fixed) nFixedP++; else { v->iP = static_cast<int>(vP_.size()); vP_.push_back(v); } }
 		numP_ = static_cast<int>(vP_.size());
 		if (nFixedP) for (PoseVertex* v : orderP_) if (v->fixed && !v->edges.empty()) { v->iP = static_cast<int>(vP_.size()); vP_.push_back(v); }
-		for (LandmarkVertex* v : orderL_) { if (v->edges.empty()) continue; if (v->fixed) nFixedL++; else { v->iL = static_cast<int>(vL_.size()); vL_.push_back(v); } }
-		numL_ = static_cast<int>(vL_.size());
-		if (nFixedL) for (LandmarkVertex* v : orderL_) if (v->fixed && !v->edges.empty()) { v->iL = static_cast<int>(vL_.size()); vL_.push_back(v); }
+		// landmarks (many): pass 1 classifies every vertex (0 = no edges, 1 = free, 2 = fixed) and counts per slice, pass 2 writes
+		// index, list entry and coordinates at the slice's offsets -- same numbering as a serial walk in ascending id
+		{
+			const size_t nl = orderL_.size();
+			const unsigned nt = host_threads(nl, 16384);
+			cls_.resize(nl);
+			std::vector<size_t> cntFree(nt + 1, 0), cntFixed(nt + 1, 0);
+			parallel_slices(nl, nt, [&](unsigned tix, size_t b, size_t e) {
+				size_t nf = 0, nx = 0;
+				for (size_t i = b; i < e; i++) {
+					if (i + 8 < e) __builtin_prefetch(orderL_[i + 8]);
+					const LandmarkVertex* v = orderL_[i];
+					const unsigned char c = v->edges.empty() ? 0 : (v->fixed ? 2 : 1);
+					cls_[i] = c; nf += c == 1; nx += c == 2;
+				}
+				cntFree[tix + 1] = nf; cntFixed[tix + 1] = nx;
+			});
+			for (unsigned t = 0; t < nt; t++) { cntFree[t + 1] += cntFree[t]; cntFixed[t + 1] += cntFixed[t]; }
+			numL_ = static_cast<int>(cntFree[nt]);
+			nFixedL = cntFixed[nt];
+			vL_.resize(cntFree[nt] + cntFixed[nt]);
+			Xw_.resize(3 * vL_.size());
+			parallel_slices(nl, nt, [&](unsigned tix, size_t b, size_t e) {
+				size_t wf = cntFree[tix], wx = cntFree[nt] + cntFixed[tix];
+				for (size_t i = b; i < e; i++) {
+					if (i + 8 < e) __builtin_prefetch(orderL_[i + 8], 1);
+					if (!cls_[i]) continue;
+					LandmarkVertex* v = orderL_[i];
+					const size_t w = cls_[i] == 1 ? wf++ : wx++;
+					v->iL = static_cast<int>(w); vL_[w] = v;
+					for (int k = 0; k < 3; k++) Xw_[3 * w + k] = v->Xw.data()[k];
+				}
+			});
+		}
 
-		q_.resize(4 * vP_.size()); t_.resize(3 * vP_.size()); cam_.resize(5 * vP_.size()); Xw_.resize(3 * vL_.size());
+		q_.resize(4 * vP_.size()); t_.resize(3 * vP_.size()); cam_.resize(5 * vP_.size());
 		for (size_t i = 0; i < vP_.size(); i++) {
 			const PoseVertex* v = vP_[i];
 			for (int k = 0; k < 4; k++) q_[4 * i + k] = v->q.coeffs().data()[k];
@@ -183,22 +225,23 @@ public:
 			cam_[5 * i] = v->camera.fx; cam_[5 * i + 1] = v->camera.fy; cam_[5 * i + 2] = v->camera.cx;
 			cam_[5 * i + 3] = v->camera.cy; cam_[5 * i + 4] = v->camera.bf;
 		}
-		parallel_for(vL_.size(), [this](size_t b, size_t e) { for (size_t i = b; i < e; i++) for (int k = 0; k < 3; k++) Xw_[3 * i + k] = vL_[i]->Xw.data()[k]; });
 
 		// edges: every list entry is written at its own position by a few threads; only if an edge with both ends fixed
 		// turned up (they are dropped, cpp:210-211) the arrays are closed up afterwards
 		idx2_.resize(2 * mono_.size()); meas2_.resize(2 * mono_.size()); om2_.resize(mono_.size());
 		idx3_.resize(2 * stereo_.size()); meas3_.resize(3 * stereo_.size()); om3_.resize(stereo_.size());
-		auto am = std::make_shared<std::vector<const BaseEdge*>>(mono_.size());
-		auto as = std::make_shared<std::vector<const BaseEdge*>>(stereo_.size());
+		auto am = takeList(mono_.size());
+		auto as = takeList(stereo_.size());
 		const size_t n2 = mono_.size(), n3 = stereo_.size(), total = n2 + n3;
-		unsigned nthreads = static_cast<unsigned>(std::min<size_t>(8, total / 65536 + 1));
-		nthreads = std::max(1u, std::min(nthreads, std::max(1u, std::thread::hardware_concurrency())));
+		const unsigned nthreads = host_threads(total, 65536);
 		std::vector<size_t> dropped(nthreads, 0);
-		auto work = [&](unsigned tix) {
-			const size_t b = total * tix / nthreads, e = total * (tix + 1) / nthreads;
+		parallel_slices(total, nthreads, [&](unsigned tix, size_t b, size_t e) {
+			// two prefetch distances: the edge object 16 ahead, its landmark (read through the edge) 8 ahead
+			auto edgeAt = [&](size_t k) -> const BaseEdge* { return k < n2 ? static_cast<const BaseEdge*>(mono_[k]) : static_cast<const BaseEdge*>(stereo_[k - n2]); };
 			size_t drop = 0;
 			for (size_t k = b; k < e; k++) {
+				if (k + 16 < e) __builtin_prefetch(edgeAt(k + 16));
+				if (k + 8 < e) __builtin_prefetch(k + 8 < n2 ? static_cast<const void*>(mono_[k + 8]->vertexL) : static_cast<const void*>(stereo_[k + 8 - n2]->vertexL));
 				if (k < n2) {
 					const MonoEdge* ed = mono_[k];
 					const PoseVertex* vp = ed->vertexP; const LandmarkVertex* vl = ed->vertexL;
@@ -219,14 +262,7 @@ public:
 				}
 			}
 			dropped[tix] = drop;
-		};
-		if (nthreads == 1) work(0);
-		else {
-			std::vector<std::thread> pool;
-			for (unsigned tix = 1; tix < nthreads; tix++) pool.emplace_back(work, tix);
-			work(0);
-			for (auto& th : pool) th.join();
-		}
+		});
 		size_t ndrop = 0;
 		for (size_t d : dropped) ndrop += d;
 		if (ndrop) {
@@ -344,6 +380,16 @@ private:
 		deadMono_ = deadStereo_ = 0;
 	}
 
+	// a position -> edge list for chiSquared(): the previous optimize()'s lists stay alive in chiMono_/chiStereo_, so the
+	// lists rotate through a small pool instead of being allocated (and page-faulted in) on every initialize()
+	std::shared_ptr<std::vector<const BaseEdge*>> takeList(size_t n)
+	{
+		for (auto& l : listPool_)
+			if (l.use_count() == 1) { l->resize(n); return l; }
+		listPool_.push_back(std::make_shared<std::vector<const BaseEdge*>>(n));
+		return listPool_.back();
+	}
+
 	void ensureEngine()
 	{
 		if (engine_) return;
@@ -375,6 +421,8 @@ private:
 	std::vector<PoseVertex*> vP_;
 	std::vector<LandmarkVertex*> vL_;
 	std::shared_ptr<const std::vector<const BaseEdge*>> activeMono_, activeStereo_, chiMono_, chiStereo_;
+	std::vector<std::shared_ptr<std::vector<const BaseEdge*>>> listPool_;
+	std::vector<unsigned char> cls_;
 	int numP_ = 0, numL_ = 0;
 	HostBuf<double> q_, t_, cam_, Xw_, meas2_, om2_, meas3_, om3_, chi_;
 	HostBuf<int32_t> idx2_, idx3_;
