@@ -1569,6 +1569,9 @@ struct Engine : EngineBase {
 		d.needMax = PP.needMax; d.maxRows = PP.maxRows; d.nc = nc; d.maxNeedAgg = CP.maxNeedAgg;
 		d.npv = std::max(std::max(G * 9, W * NR), 6 * CP.maxNeedAgg); d.nls = NR;
 		d.sliceRows = (nc + G - 1) / G;
+		// staging of the block products: one round when a CTA's blocks fit a chunk (then only as many slots as needed; the polled w
+		// entries of the needed columns share the storage)
+		d.ccCap = PP.blkMax >= PCG5_CHUNK ? PCG5_CHUNK : std::max((std::max(PP.blkMax, PP.needMax) + 31) / 32 * 32, 32);
 		const size_t per = 36 * sizeof(T) + 4;
 		size_t wantCache = PP.blkMax > PCG5_REGBLK ? (size_t)(PP.blkMax - PCG5_REGBLK) : 0;
 		bool big = PP.maxRows * 6 > PCG5_BLOCK;

@@ -32,13 +32,27 @@
 
 namespace cuba_b200 {
 
-constexpr int PCG5_BLOCK = 256;
-constexpr int PCG5_BPT = 2;                        // register-resident A^ blocks per thread
+// launch shape (overridable at build time for experiments: -DCUBA_P5_BLOCK=512 -DCUBA_P5_BPT=1 -DCUBA_P5_CPT=2 -DCUBA_P5_PCH=5)
+#ifndef CUBA_P5_BLOCK
+#define CUBA_P5_BLOCK 256
+#endif
+#ifndef CUBA_P5_BPT
+#define CUBA_P5_BPT 2
+#endif
+#ifndef CUBA_P5_CPT
+#define CUBA_P5_CPT 3
+#endif
+#ifndef CUBA_P5_PCH
+#define CUBA_P5_PCH 8
+#endif
+constexpr int PCG5_BLOCK = CUBA_P5_BLOCK;
+constexpr int PCG5_BPT = CUBA_P5_BPT;                // register-resident A^ blocks per thread
 constexpr int PCG5_REGBLK = PCG5_BLOCK * PCG5_BPT;
-constexpr int PCG5_CHUNK = PCG5_REGBLK;
+constexpr int PCG5_CPT = CUBA_P5_CPT;                // blocks per thread and product round: the register slots, then cached / streamed blocks
+constexpr int PCG5_CHUNK = PCG5_BLOCK * PCG5_CPT;
 constexpr int PCG5_REPL = 8;                       // replicas of the partial / summary boards
 constexpr int PCG5_MAXWORLD = 8;
-constexpr int PCG5_PCH = 8;                        // polled words in flight per thread
+constexpr int PCG5_PCH = CUBA_P5_PCH;                        // polled words in flight per thread
 constexpr int PCG5_TPR = 16;                       // threads per row of the coarse slice product
 
 // device-resident solve bookkeeping: read by every CTA at its start, changed only BETWEEN solves by k_pcg5_commit
@@ -49,6 +63,7 @@ struct Pcg5Dims {
 	int sliceRows; // rows of the inverse coarse matrix this CTA multiplies: ceil(nc / G)
 	int npv;      // max(G * NP, world * NR): polled partial / summary words
 	int nls;      // NR: words of a rank summary
+	int ccCap;    // slots per component of the block-product staging: PCG5_CHUNK, or less when a CTA never owns that many blocks
 };
 
 // shared-memory carve-up, one definition for the host (size) and the device (pointers)
@@ -65,14 +80,14 @@ struct Pcg5Layout {
 		u = take((size_t)d.needMax * 6 * sizeof(T), 8);
 		p = take((size_t)d.maxRows * 6 * sizeof(T), 8);
 		y = take((size_t)d.maxRows * 6 * sizeof(T), 8);
-		cc = take((size_t)PCG5_CHUNK * 6 * sizeof(double), 8);      // block-product staging; polled w entries (double) between passes
+		cc = take((size_t)d.ccCap * 6 * sizeof(double), 8);      // block-product staging; polled w entries (double) between passes
 		rc = take((size_t)d.nc * sizeof(T), 8);
 		sc = take((size_t)d.nc * sizeof(T), 8);
 		c = take((size_t)d.maxNeedAgg * 6 * sizeof(T), 8);
 		zh = take(d.zhInSmem ? (size_t)d.needMax * 36 * sizeof(T) : 0, 8);
 		pv = take((size_t)d.npv * sizeof(double), 8);
 		ls = take((size_t)d.nls * sizeof(double), 8);
-		sq = take((size_t)9 * d.maxRows * 6 * sizeof(double), 8);   // partial inner products of the (row, component) threads
+		sq = take((size_t)9 * (PCG5_BLOCK / 32) * sizeof(double), 8);   // per-warp sums of the nine partial inner products
 		ai = take((size_t)d.sliceRows * d.nc * sizeof(float), 16);
 		loc = take((size_t)d.capBlocks * sizeof(int), 4);
 		rowPtr = take(((size_t)d.maxRows + 1) * sizeof(int), 4);
@@ -245,10 +260,10 @@ __device__ __forceinline__ bool ll_decode(unsigned long long lo, unsigned long l
 	return true;
 }
 
-// Polls `n` LL words (slot of item i given by slotOf(i)) into dst[i]; PCG5_PCH loads of a thread are in flight together.
-// Returns false when the solve was aborted (a peer vanished: spin limit).
-template <typename SlotOf>
-__device__ __forceinline__ bool ll_poll_many(int n, SlotOf slotOf, double* dst, unsigned int tag, Pcg5Ctl* ctl)
+// Polls `n` LL words (slot of item i given by slotOf(i)) and hands every value to put(i, v); PCG5_PCH loads of a thread are in
+// flight together.  Returns false when the solve was aborted (a peer vanished: spin limit).
+template <typename SlotOf, typename Put>
+__device__ __forceinline__ bool ll_poll_each(int n, SlotOf slotOf, Put put, unsigned int tag, Pcg5Ctl* ctl)
 {
 	const int tid = threadIdx.x;
 	for (int base = 0; base < n; base += PCG5_BLOCK * PCG5_PCH) {
@@ -262,7 +277,7 @@ __device__ __forceinline__ bool ll_poll_many(int n, SlotOf slotOf, double* dst, 
 #pragma unroll
 			for (int u = 0; u < PCG5_PCH; u++) if ((pend >> u) & 1u) {
 				double v;
-				if (ll_decode(lo[u], hi[u], tag, v)) { dst[base + u * PCG5_BLOCK + tid] = v; pend &= ~(1u << u); }
+				if (ll_decode(lo[u], hi[u], tag, v)) { put(base + u * PCG5_BLOCK + tid, v); pend &= ~(1u << u); }
 			}
 			if ((spin & 1023u) == 1023u) {
 				if (*(volatile int*)&ctl->abort) return false;
@@ -272,6 +287,11 @@ __device__ __forceinline__ bool ll_poll_many(int n, SlotOf slotOf, double* dst, 
 	}
 	return true;
 }
+template <typename SlotOf>
+__device__ __forceinline__ bool ll_poll_many(int n, SlotOf slotOf, double* dst, unsigned int tag, Pcg5Ctl* ctl)
+{
+	return ll_poll_each(n, slotOf, [dst](int i, double v) { dst[i] = v; }, tag, ctl);
+}
 
 // BIG: the CTA may own more than 42 rows (up to 85): every thread then serves two (row, component) pairs in the row sums
 template <typename T, bool BIG = false>
@@ -279,14 +299,14 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const Pcg5Layout<T> lay(a.dims);
-	const int capBlocks = a.dims.capBlocks, nc = a.dims.nc;
+	const int capBlocks = a.dims.capBlocks, nc = a.dims.nc, ccCap = a.dims.ccCap;
 	T* s_blk = reinterpret_cast<T*>(smem_raw + lay.blk);            // [36][capBlocks] blocks past the registers, element-major
 	T* s_r = reinterpret_cast<T*>(smem_raw + lay.r);                // [needMax][6] residual of the needed columns
 	T* s_s = reinterpret_cast<T*>(smem_raw + lay.s);                // [needMax][6] s = w + beta s
 	T* s_u = reinterpret_cast<T*>(smem_raw + lay.u);                // [needMax][6] u = M^-1 r
 	T* s_p = reinterpret_cast<T*>(smem_raw + lay.p);                // [maxRows][6]
 	T* s_y = reinterpret_cast<T*>(smem_raw + lay.y);                // [maxRows][6]
-	T* s_cc = reinterpret_cast<T*>(smem_raw + lay.cc);              // [6][PCG5_CHUNK] block products, component-major
+	T* s_cc = reinterpret_cast<T*>(smem_raw + lay.cc);              // [6][ccCap] block products, component-major
 	double* s_w = reinterpret_cast<double*>(smem_raw + lay.cc);     // polled w entries of the needed columns (same storage, other phase)
 	T* s_rc = reinterpret_cast<T*>(smem_raw + lay.rc);              // [nc] coarse residual Z^^T r
 	T* s_sc = reinterpret_cast<T*>(smem_raw + lay.sc);              // [nc]
@@ -424,6 +444,22 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 #endif
 	int tpp = 1;                                         // threads per (row, component) pair of the row sums, a power of two
 	while (tpp < 8 && nrows * 6 * tpp * 2 <= PCG5_BLOCK) tpp *= 2;
+	// s, r of the needed columns, p, y of the own rows (u_k is still in s_u); alpha, beta of the current pass
+	auto advance_vectors = [&]() {
+		for (int wi = tid; wi < nneed * 6; wi += PCG5_BLOCK) {
+			const T snew = (T)s_w[wi] + (T)beta * s_s[wi];
+			const T rold = s_r[wi];
+			s_s[wi] = snew;
+			s_r[wi] = rold - (T)alpha * snew;
+			const int own = s_own[wi / 6];
+			if (own >= 0) {
+				const int o = own * 6 + (wi % 6);
+				const T p = (coarse ? s_u[wi] : rold) + (T)beta * s_p[o];
+				s_p[o] = p;
+				s_y[o] += (T)alpha * p;
+			}
+		}
+	};
 	if (nbad > 0) status = 2;
 	else {
 		// pass k = -1: u0 = M^-1 r0, w0 = A^ u0, first partials; pass k >= 0: CG iteration k.
@@ -439,9 +475,10 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 					const int nW = nneed * 6, nPl = G * NP;
 					const unsigned long long* wB = a.wBoard + 2 * (wHalf + (size_t)par * wStride);
 					const unsigned long long* pB = a.pBoard + 2 * (pHalf + (size_t)par * pStride + (size_t)rep * nPl);
-					// one destination array: s_w directly followed (logically) by s_pv -> two calls keep the indexing simple
-					bool ok = ll_poll_many(nW, [&](int i) { return wB + 2 * (size_t)s_woff[i]; }, s_w, tag, a.ctl);
-					ok = ok && ll_poll_many(nPl, [&](int i) { return pB + 2 * (size_t)i; }, s_pv, tag, a.ctl);
+					// ONE list (w entries, then the partials): the loads of both boards are in flight together
+					const bool ok = ll_poll_each(nW + nPl,
+						[&](int i) { return i < nW ? wB + 2 * (size_t)s_woff[i] : pB + 2 * (size_t)(i - nW); },
+						[&](int i, double v) { if (i < nW) s_w[i] = v; else s_pv[i - nW] = v; }, tag, a.ctl);
 					if (!ok) s_abort = 1;
 				}
 				__syncthreads();
@@ -507,20 +544,8 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 					gamma = gnew;
 				}
 				if (k >= a.maxIters) { status = 1; break; }
-				// ---- advance s, r (needed columns), p, y (own rows; u_k is still in s_u) and the coarse residual ----
-				for (int wi = tid; wi < nneed * 6; wi += PCG5_BLOCK) {
-					const T snew = (T)s_w[wi] + (T)beta * s_s[wi];
-					const T rold = s_r[wi];
-					s_s[wi] = snew;
-					s_r[wi] = rold - (T)alpha * snew;
-					const int own = s_own[wi / 6];
-					if (own >= 0) {
-						const int o = own * 6 + (wi % 6);
-						const T p = (coarse ? s_u[wi] : rold) + (T)beta * s_p[o];
-						s_p[o] = p;
-						s_y[o] += (T)alpha * p;
-					}
-				}
+				// ---- the coarse residual first: its product with Ac^-1 is published before r, s, p, y are advanced, so that the
+				//      words cross the L2 while this CTA still has work to do ----
 				if (coarse)
 					for (int q = tid; q < nc; q += PCG5_BLOCK) {
 						// global aggregate q/6 = rank r, local aggregate al
@@ -535,6 +560,7 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 						s_sc[q] = sc;
 						s_rc[q] -= (T)alpha * sc;
 					}
+				else advance_vectors();
 				__syncthreads();
 				PCG_T(t3);
 				PCG_ACC(0, t0, t1); PCG_ACC(1, t1, t2); PCG_ACC(2, t2, t3);
@@ -553,6 +579,7 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 					sacc = warp_sum(sacc);
 					if (lane < PCG5_REPL) ll_store(cB + 2 * ((size_t)lane * nc + rowi), (double)sacc, ctag);
 				}
+				if (k >= 0) advance_vectors();
 				{
 					const unsigned long long* cR = cB + 2 * ((size_t)rep * nc);
 					double* cdst = sizeof(T) == 8 ? reinterpret_cast<double*>(s_c) : s_pv;
@@ -597,17 +624,18 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 			for (int cs = 0; cs < nblkCta; cs += PCG5_CHUNK) {
 				if (cs > 0) __syncthreads();
 #pragma unroll
-				for (int u = 0; u < PCG5_BPT; u++) {
+				for (int u = 0; u < PCG5_CPT; u++) {
 					const int n = cs + u * PCG5_BLOCK + tid;
 					T y[6] = { T(0), T(0), T(0), T(0), T(0), T(0) };
-					if (!BIG && cs == 0) {
-						if (myLoc[u] >= 0) {
-							const T* rj = s_v + 6 * (size_t)myLoc[u];
+					if (!BIG && u < PCG5_BPT && cs == 0) {
+						const int ur = u < PCG5_BPT ? u : 0;
+						if (myLoc[ur] >= 0) {
+							const T* rj = s_v + 6 * (size_t)myLoc[ur];
 #pragma unroll
 							for (int c = 0; c < 6; c++) {
 								const T rc = rj[c];
 #pragma unroll
-								for (int r = 0; r < 6; r++) y[r] += breg[u][c * 6 + r] * rc;
+								for (int r = 0; r < 6; r++) y[r] += breg[ur][c * 6 + r] * rc;
 							}
 						}
 					} else if (n < nblkCta) {
@@ -652,8 +680,10 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 							}
 						}
 					}
+					if (u * PCG5_BLOCK + tid < ccCap) {
 #pragma unroll
-					for (int r = 0; r < 6; r++) s_cc[r * PCG5_CHUNK + u * PCG5_BLOCK + tid] = y[r];
+						for (int r = 0; r < 6; r++) s_cc[r * ccCap + u * PCG5_BLOCK + tid] = y[r];
+					}
 				}
 				__syncthreads();
 #pragma unroll
@@ -665,7 +695,7 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 						n0 = (n0 > cs ? n0 : cs) - cs;
 						n1 = (n1 < cs + PCG5_CHUNK ? n1 : cs + PCG5_CHUNK) - cs;
 						T s0 = T(0), s1 = T(0);
-						const T* col = s_cc + comp * PCG5_CHUNK;
+						const T* col = s_cc + comp * ccCap;
 						int q = n0 + sub;
 						for (; q + tpp < n1; q += 2 * tpp) { s0 += col[q]; s1 += col[q + tpp]; }
 						if (q < n1) s0 += col[q];
@@ -676,10 +706,12 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 			for (int o = 1; o < tpp; o <<= 1) wacc[0] += __shfl_xor_sync(0xffffffffu, wacc[0], o);
 			PCG_T(t6);
 			// ---- publish w (own board + the boards of the ranks that need the row), partial inner products, Z^^T w ----
-			// The nine quantities of the (row, component) threads go to shared memory; afterwards warp w adds quantity w (warp 0
-			// also the ninth) in a fixed order and its first REPL lanes publish the replicas.
-			const int nact = nrows * 6;                           // active threads: tid = pair * tpp
-			double* s_q = reinterpret_cast<double*>(smem_raw + lay.sq);   // [9][nact]; read below, rewritten only after the next pass's barriers
+			// Every (row, component) thread keeps its nine products in registers; a butterfly adds them over the warp, lane 0 leaves the
+			// warp's sums in shared memory and 9 x REPL threads add the eight warps in a fixed order and publish the replicas.
+			double* s_q = reinterpret_cast<double*>(smem_raw + lay.sq);   // [warps][9]; rewritten only after the next pass's barriers
+			double q9[9];
+#pragma unroll
+			for (int w = 0; w < 9; w++) q9[w] = 0.0;
 #pragma unroll
 			for (int pu = 0; pu < NPU; pu++) {
 				const int pair = tid / tpp + pu * PCG5_BLOCK;
@@ -699,22 +731,29 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 						ll_store(a.peerW[pr] + 2 * slot, (double)wv1, otag);
 					}
 				}
-				s_q[pair] = (double)ri * (double)ui;
-				s_q[nact + pair] = (double)wv1 * (double)ui;
-				s_q[2 * nact + pair] = (double)ri * (double)ri;
+				q9[0] += (double)ri * (double)ui;
+				q9[1] += (double)wv1 * (double)ui;
+				q9[2] += (double)ri * (double)ri;
 				if (coarse) {
 					const T* Zh = a.dims.zhInSmem ? s_zh + 36 * (size_t)dl + comp : a.Zhat + 36 * (size_t)(row0 + li) + comp;
 #pragma unroll
-					for (int q = 0; q < 6; q++) s_q[(3 + q) * nact + pair] = (double)(Zh[6 * q] * wv1);   // (Z^^T w)(q) = sum_comp Z^(comp,q) w(comp)
+					for (int q = 0; q < 6; q++) q9[3 + q] += (double)(Zh[6 * q] * wv1);   // (Z^^T w)(q) = sum_comp Z^(comp,q) w(comp)
 				}
+			}
+#pragma unroll
+			for (int w = 0; w < 9; w++) if (w < NP) q9[w] = warp_sum(q9[w]);
+			if (lane == 0) {
+#pragma unroll
+				for (int w = 0; w < 9; w++) if (w < NP) s_q[wid * 9 + w] = q9[w];
 			}
 			__syncthreads();
 			PCG_T(t7);
-			for (int word = wid; word < NP; word += PCG5_BLOCK / 32) {
+			if (tid < NP * PCG5_REPL) {
+				const int word = tid / PCG5_REPL, rp = tid - word * PCG5_REPL;
 				double v = 0;
-				for (int i = lane; i < nact; i += 32) v += s_q[word * nact + i];
-				v = warp_sum(v);
-				if (lane < PCG5_REPL) ll_store(a.pBoard + 2 * (pHalf + (size_t)opar * pStride + ((size_t)lane * G + lc) * NP + word), v, otag);
+#pragma unroll
+				for (int w8 = 0; w8 < PCG5_BLOCK / 32; w8++) v += s_q[w8 * 9 + word];
+				ll_store(a.pBoard + 2 * (pHalf + (size_t)opar * pStride + ((size_t)rp * G + lc) * NP + word), v, otag);
 			}
 			PCG_T(t8);
 			PCG_ACC(3, t4, t5); PCG_ACC(4, t5, t6); PCG_ACC(5, t6, t7); PCG_ACC(6, t7, t8);
