@@ -20,6 +20,9 @@
 #include "cuba_pcg3.cuh"
 #include "cuba_pcg4.cuh"
 #include "cuba_pcg5.cuh"
+#ifndef P5_TUNED
+#define P5_TUNED 2          // partial products of the tuned k_pcg5 shape: 1 = warp butterflies, 2 = shared-memory staging (cuba_pcg5.cuh)
+#endif
 #include "cuba_coarse_dense.cuh"
 #include "cuba_peer_reduce.cuh"
 #include "cuba_schur2.cuh"
@@ -1457,7 +1460,9 @@ struct Engine : EngineBase {
 	Pcg5Dims p5Dims{}, p5DimsBJ{};
 	size_t p5Smem = 0;
 	int p5G = 0, p5W = 1, p5A = 0, p5Gs = 1;
-	bool p5Ok = false, p5Dist = false, p5Big = false;
+	bool p5Ok = false, p5Dist = false, p5Big = false, p5Tuned = false;
+	const void* p5Fn = nullptr;
+	int p5Block = PCG5_BLOCK;
 	int p5Cluster = 0;                             // CTAs of the cluster that factors the coarse matrix (0: one CTA)
 	bool p5CoarseValid = false; int p5CoarseAge = 0; double p5CoarseLambda = 0;
 	size_t p5InvSmem = 0;
@@ -1571,11 +1576,15 @@ struct Engine : EngineBase {
 		d.sliceRows = (nc + G - 1) / G;
 		// staging of the block products: one round when a CTA's blocks fit a chunk (then only as many slots as needed; the polled w
 		// entries of the needed columns share the storage)
-		d.ccCap = PP.blkMax >= PCG5_CHUNK ? PCG5_CHUNK : std::max((std::max(PP.blkMax, PP.needMax) + 31) / 32 * 32, 32);
+		// shape (cuba_pcg5.cuh): the tuned one for a solve on one GPU whose blocks fit registers + shared memory, else the legacy one
+		bool tuned = W == 1 && !getenv("CUBA_PCG5_LEGACY");
+		d.sqWords = std::max(9 * PP.maxRows * 6, 9 * 16);
 		const size_t per = 36 * sizeof(T) + 4;
 		size_t wantCache = PP.blkMax > PCG5_REGBLK ? (size_t)(PP.blkMax - PCG5_REGBLK) : 0;
-		bool big = PP.maxRows * 6 > PCG5_BLOCK;
-		{
+		bool big = !tuned && PP.maxRows * 6 > PCG5_BLOCK;
+		for (int attempt = 0; attempt < 2; attempt++) {
+			const int chunk = tuned ? Pcg5Shape<false, P5_TUNED>::CHUNK : Pcg5Shape<false, 0>::CHUNK;
+			d.ccCap = PP.blkMax >= chunk ? chunk : std::max((std::max(PP.blkMax, PP.needMax) + 31) / 32 * 32, 32);
 			d.capBlocks = 0; d.zhInSmem = 0;
 			const size_t base = Pcg5Layout<T>(d).total + 64;
 			if (base > budget) return CUBA_OK;
@@ -1586,22 +1595,27 @@ struct Engine : EngineBase {
 			d.capBlocks = (int)std::min(wantCache, (budget - fixed) / per);
 			// blocks would have to be streamed from the global copy every pass: the variant without register-resident blocks streams
 			// with eighteen 16-byte loads in flight per thread (the register variant can afford six 8-byte loads)
-			if ((size_t)d.capBlocks < wantCache) big = true;
+			if ((size_t)d.capBlocks < wantCache) {
+				if (tuned) { tuned = false; big = PP.maxRows * 6 > PCG5_BLOCK; continue; }   // size the legacy shape instead
+				big = true;
+			}
 			if (big) d.capBlocks = (int)std::min((size_t)PP.blkMax, (budget - fixed) / per);
+			break;
 		}
 		p5Dims = d;
 		p5DimsBJ = d; p5DimsBJ.nc = 0; p5DimsBJ.maxNeedAgg = 0; p5DimsBJ.zhInSmem = 0; p5DimsBJ.sliceRows = 0; p5DimsBJ.nls = 3; p5DimsBJ.npv = std::max(G * 3, W * 3);
 		p5Smem = std::max(Pcg5Layout<T>(p5Dims).total, Pcg5Layout<T>(p5DimsBJ).total);
 		if (p5Smem > (size_t)smemMax - 1024) return CUBA_OK;
-		p5Big = big;
-		const void* p5Fn = p5Big ? (const void*)k_pcg5<T, true> : (const void*)k_pcg5<T, false>;
+		p5Big = big; p5Tuned = tuned && !big;
+		p5Fn = p5Big ? (const void*)k_pcg5<T, true, 0> : p5Tuned ? (const void*)k_pcg5<T, false, P5_TUNED> : (const void*)k_pcg5<T, false, 0>;
+		p5Block = p5Tuned ? Pcg5Shape<false, P5_TUNED>::BLOCK : PCG5_BLOCK;
 		CUDA_TRY(cudaFuncSetAttribute(p5Fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p5Smem));
 		int perSM = 0;
-		if (p5Big) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_pcg5<T, true>, PCG5_BLOCK, p5Smem));
-		else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_pcg5<T, false>, PCG5_BLOCK, p5Smem));
+		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, p5Fn, p5Block, p5Smem));
 		if (perSM < 1) return CUBA_OK;
 		if (getenv("CUBA_PCG_VERBOSE")) fprintf(stderr, "pcg5: world %d G %d gs %d A %d needMax %d maxRows %d blkMax %d maxNeedAgg %d zhInSmem %d sliceRows %d cap %d smem %zu\n",
 			W, G, gs, A, d.needMax, d.maxRows, PP.blkMax, d.maxNeedAgg, d.zhInSmem, d.sliceRows, d.capBlocks, p5Smem);
+		if (getenv("CUBA_PCG_VERBOSE")) fprintf(stderr, "pcg5: shape %s, %d threads\n", p5Big ? "big" : p5Tuned ? "tuned" : "legacy", p5Block);
 		// coarse inverse: packed block triangle in the shared memory of one CTA (A <= 37), of an 8-CTA cluster (A <= 74) or of a
 		// 16-CTA cluster (A <= 148; non-portable cluster size)
 		p5Cluster = A > PCG4_MAXAGG1 ? (A > PCG4_MAXAGG ? 16 : 8) : 0;
@@ -1754,7 +1768,7 @@ struct Engine : EngineBase {
 #endif
 		if (p5Dist) CUDA_TRY(cudaMemsetAsync(xp.p, 0, sizeof(T) * 6 * (size_t)numP, stream));     // rows of the other ranks: summed in below
 		void* args[] = { (void*)&a };
-		CUDA_TRY(cudaLaunchCooperativeKernel(p5Big ? (void*)k_pcg5<T, true> : (void*)k_pcg5<T, false>, dim3(p5G), dim3(PCG5_BLOCK), args, p5Smem, stream));
+		CUDA_TRY(cudaLaunchCooperativeKernel(p5Fn, dim3(p5G), dim3(p5Block), args, p5Smem, stream));
 		k_pcg5_commit<<<1, 1, 0, stream>>>(p5Ctl(p5Boards.p));
 		launches += 2;
 		CUDA_TRY(cudaGetLastError());

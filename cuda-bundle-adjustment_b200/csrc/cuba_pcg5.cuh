@@ -32,27 +32,24 @@
 
 namespace cuba_b200 {
 
-// launch shape (overridable at build time for experiments: -DCUBA_P5_BLOCK=512 -DCUBA_P5_BPT=1 -DCUBA_P5_CPT=2 -DCUBA_P5_PCH=5)
-#ifndef CUBA_P5_BLOCK
-#define CUBA_P5_BLOCK 256
-#endif
-#ifndef CUBA_P5_BPT
-#define CUBA_P5_BPT 2
-#endif
-#ifndef CUBA_P5_CPT
-#define CUBA_P5_CPT 3
-#endif
-#ifndef CUBA_P5_PCH
-#define CUBA_P5_PCH 8
-#endif
-constexpr int PCG5_BLOCK = CUBA_P5_BLOCK;
-constexpr int PCG5_BPT = CUBA_P5_BPT;                // register-resident A^ blocks per thread
-constexpr int PCG5_REGBLK = PCG5_BLOCK * PCG5_BPT;
-constexpr int PCG5_CPT = CUBA_P5_CPT;                // blocks per thread and product round: the register slots, then cached / streamed blocks
-constexpr int PCG5_CHUNK = PCG5_BLOCK * PCG5_CPT;
+// Launch shapes.  LEGACY (TUNED = 0): 256 threads, two register-resident blocks per thread -- the shape every multi-GPU and every
+// large-graph (BIG) measurement was made with; kept unchanged for the row-distributed and the BIG solves.  TUNED (one GPU, the
+// whole system in registers + shared memory): 512 threads with one register block each -- twice the warps to hide the shared-memory
+// and L2 latencies of the short phases -- the coarse product published before r, s, p, y are advanced, the three scalars summed by
+// three warps instead of by all of them (ba_kitti_00: 14.1 -> 11.7 us per iteration, profiles/r02_pcg5_shape_ab.log).
+constexpr int PCG5_BLOCK = 256;                    // LEGACY block; bounds the rows per CTA of every plan (2 * 256 / 6)
+template <bool BIG, int TUNED>
+struct Pcg5Shape {
+	static constexpr int BLOCK = TUNED ? 512 : PCG5_BLOCK;
+	static constexpr int BPT = TUNED ? 1 : 2;          // register-resident A^ blocks per thread (none with BIG)
+	static constexpr int REGBLK = BIG ? 0 : BLOCK * BPT;
+	static constexpr int CPT = 2;                      // blocks per thread and product round
+	static constexpr int CHUNK = BLOCK * CPT;
+	static constexpr int PCH = TUNED ? 3 : 8;          // polled words in flight per thread
+};
+constexpr int PCG5_REGBLK = 512;                   // both shapes keep 512 blocks in registers
 constexpr int PCG5_REPL = 8;                       // replicas of the partial / summary boards
 constexpr int PCG5_MAXWORLD = 8;
-constexpr int PCG5_PCH = CUBA_P5_PCH;                        // polled words in flight per thread
 constexpr int PCG5_TPR = 16;                       // threads per row of the coarse slice product
 
 // device-resident solve bookkeeping: read by every CTA at its start, changed only BETWEEN solves by k_pcg5_commit
@@ -63,7 +60,8 @@ struct Pcg5Dims {
 	int sliceRows; // rows of the inverse coarse matrix this CTA multiplies: ceil(nc / G)
 	int npv;      // max(G * NP, world * NR): polled partial / summary words
 	int nls;      // NR: words of a rank summary
-	int ccCap;    // slots per component of the block-product staging: PCG5_CHUNK, or less when a CTA never owns that many blocks
+	int ccCap;    // slots per component of the block-product staging: the shape's CHUNK, or less when a CTA never owns that many blocks
+	int sqWords;  // doubles of the partial-product staging: 9 * maxRows * 6
 };
 
 // shared-memory carve-up, one definition for the host (size) and the device (pointers)
@@ -87,7 +85,7 @@ struct Pcg5Layout {
 		zh = take(d.zhInSmem ? (size_t)d.needMax * 36 * sizeof(T) : 0, 8);
 		pv = take((size_t)d.npv * sizeof(double), 8);
 		ls = take((size_t)d.nls * sizeof(double), 8);
-		sq = take((size_t)9 * (PCG5_BLOCK / 32) * sizeof(double), 8);   // per-warp sums of the nine partial inner products
+		sq = take((size_t)d.sqWords * sizeof(double), 8);           // nine products of every (row, component) thread
 		ai = take((size_t)d.sliceRows * d.nc * sizeof(float), 16);
 		loc = take((size_t)d.capBlocks * sizeof(int), 4);
 		rowPtr = take(((size_t)d.maxRows + 1) * sizeof(int), 4);
@@ -262,9 +260,10 @@ __device__ __forceinline__ bool ll_decode(unsigned long long lo, unsigned long l
 
 // Polls `n` LL words (slot of item i given by slotOf(i)) and hands every value to put(i, v); PCG5_PCH loads of a thread are in
 // flight together.  Returns false when the solve was aborted (a peer vanished: spin limit).
-template <typename SlotOf, typename Put>
+template <int KB, int PCG5_PCH, typename SlotOf, typename Put>
 __device__ __forceinline__ bool ll_poll_each(int n, SlotOf slotOf, Put put, unsigned int tag, Pcg5Ctl* ctl)
 {
+	constexpr int PCG5_BLOCK = KB;                      // (shadows the legacy constant inside this function)
 	const int tid = threadIdx.x;
 	for (int base = 0; base < n; base += PCG5_BLOCK * PCG5_PCH) {
 		unsigned int pend = 0;
@@ -287,16 +286,20 @@ __device__ __forceinline__ bool ll_poll_each(int n, SlotOf slotOf, Put put, unsi
 	}
 	return true;
 }
-template <typename SlotOf>
+template <int KB, int KPCH, typename SlotOf>
 __device__ __forceinline__ bool ll_poll_many(int n, SlotOf slotOf, double* dst, unsigned int tag, Pcg5Ctl* ctl)
 {
-	return ll_poll_each(n, slotOf, [dst](int i, double v) { dst[i] = v; }, tag, ctl);
+	return ll_poll_each<KB, KPCH>(n, slotOf, [dst](int i, double v) { dst[i] = v; }, tag, ctl);
 }
 
 // BIG: the CTA may own more than 42 rows (up to 85): every thread then serves two (row, component) pairs in the row sums
-template <typename T, bool BIG = false>
-__global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
+template <typename T, bool BIG = false, int TUNED = 0>
+__global__ void __launch_bounds__((Pcg5Shape<BIG, TUNED>::BLOCK), 1) k_pcg5(const Pcg5Args<T> a)
 {
+	static_assert(!(BIG && TUNED), "the tuned shape keeps the whole system on chip");
+	using Shape = Pcg5Shape<BIG, TUNED>;
+	// the names of the legacy constants, bound to this instantiation's shape
+	constexpr int PCG5_BLOCK = Shape::BLOCK, PCG5_BPT = Shape::BPT, PCG5_CPT = Shape::CPT, PCG5_CHUNK = Shape::CHUNK, PCG5_PCH = Shape::PCH;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const Pcg5Layout<T> lay(a.dims);
 	const int capBlocks = a.dims.capBlocks, nc = a.dims.nc, ccCap = a.dims.ccCap;
@@ -333,7 +336,7 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 	const int need0 = a.needPtr[cta], nneed = a.needPtr[cta + 1] - need0;
 	const int blk0 = a.fRowPtr[row0], nblkCta = a.fRowPtr[row1] - blk0;
 	// BIG: no register-resident blocks -- the registers go to the loads in flight of the streamed part (see the product loop)
-	constexpr int REGBLK = BIG ? 0 : PCG5_REGBLK;
+	constexpr int REGBLK = Shape::REGBLK;
 	const int ncached = nblkCta > REGBLK ? (nblkCta - REGBLK < capBlocks ? nblkCta - REGBLK : capBlocks) : 0;
 	const size_t n6 = 6 * (size_t)a.numP;
 	const int nover = nblkCta - REGBLK - ncached > 0 ? nblkCta - REGBLK - ncached : 0;   // blocks read from the global copy every pass
@@ -475,17 +478,28 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 					const int nW = nneed * 6, nPl = G * NP;
 					const unsigned long long* wB = a.wBoard + 2 * (wHalf + (size_t)par * wStride);
 					const unsigned long long* pB = a.pBoard + 2 * (pHalf + (size_t)par * pStride + (size_t)rep * nPl);
-					// ONE list (w entries, then the partials): the loads of both boards are in flight together
-					const bool ok = ll_poll_each(nW + nPl,
-						[&](int i) { return i < nW ? wB + 2 * (size_t)s_woff[i] : pB + 2 * (size_t)(i - nW); },
-						[&](int i, double v) { if (i < nW) s_w[i] = v; else s_pv[i - nW] = v; }, tag, a.ctl);
+					// two lists, one after the other (one mixed list, the loads of both boards in flight together, was slower: +0.6 us per
+					// iteration on ba_kitti_00 with 256 threads, +0.5 us with 512)
+					bool ok = ll_poll_many<PCG5_BLOCK, PCG5_PCH>(nW, [&](int i) { return wB + 2 * (size_t)s_woff[i]; }, s_w, tag, a.ctl);
+					ok = ok && ll_poll_many<PCG5_BLOCK, PCG5_PCH>(nPl, [&](int i) { return pB + 2 * (size_t)i; }, s_pv, tag, a.ctl);
 					if (!ok) s_abort = 1;
 				}
 				__syncthreads();
 				PCG_T(t1);
 				if (s_abort) { status = 3; break; }
 				double gnew, delta, rnew;
-				if (world == 1) {
+				if (world == 1 && TUNED) {
+					// ---- one GPU, 16 warps: three of them add one scalar each over the CTAs (every warp adding all three, as below, keeps
+					//      the shared-memory and shuffle pipes busy for ~2 000 cycles); the others meet them at the barrier ----
+					if (wid < 3) {
+						double v = 0;
+						for (int c = lane; c < G; c += 32) v += s_pv[c * NP + wid];
+						v = warp_sum(v);
+						if (lane == 0) s_ls[wid] = v;
+					}
+					__syncthreads();
+					gnew = s_ls[0]; delta = s_ls[1]; rnew = s_ls[2];
+				} else if (world == 1) {
 					// ---- one GPU: every warp adds the three scalars over the CTAs itself (same order everywhere), no barrier;
 					//      the restricted Z^^T w of an aggregate is summed by the thread that advances that coarse entry ----
 					double v0 = 0, v1 = 0, v2 = 0;
@@ -516,7 +530,7 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 						for (int q = tid; q < NR; q += PCG5_BLOCK) ll_store(dst + 2 * (size_t)q, s_ls[q], tag);
 					}
 					const unsigned long long* rB = a.rBoard + 2 * (rOff + (size_t)rep * world * NR);
-					const bool ok = ll_poll_many(world * NR, [&](int i) { return rB + 2 * (size_t)i; }, s_pv, tag, a.ctl);
+					const bool ok = ll_poll_many<PCG5_BLOCK, PCG5_PCH>(world * NR, [&](int i) { return rB + 2 * (size_t)i; }, s_pv, tag, a.ctl);
 					if (!ok) s_abort = 1;
 					__syncthreads();
 					if (s_abort) { status = 3; break; }
@@ -544,8 +558,10 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 					gamma = gnew;
 				}
 				if (k >= a.maxIters) { status = 1; break; }
-				// ---- the coarse residual first: its product with Ac^-1 is published before r, s, p, y are advanced, so that the
-				//      words cross the L2 while this CTA still has work to do ----
+				// ---- advance s, r (needed columns), p, y (own rows; u_k is still in s_u) and the coarse residual.  TUNED: the coarse
+				//      residual first -- its product with Ac^-1 is published before r, s, p, y are advanced, so that the words
+				//      cross the L2 while this CTA still has work to do ----
+				if (!(TUNED && coarse)) advance_vectors();
 				if (coarse)
 					for (int q = tid; q < nc; q += PCG5_BLOCK) {
 						// global aggregate q/6 = rank r, local aggregate al
@@ -560,7 +576,6 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 						s_sc[q] = sc;
 						s_rc[q] -= (T)alpha * sc;
 					}
-				else advance_vectors();
 				__syncthreads();
 				PCG_T(t3);
 				PCG_ACC(0, t0, t1); PCG_ACC(1, t1, t2); PCG_ACC(2, t2, t3);
@@ -579,11 +594,11 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 					sacc = warp_sum(sacc);
 					if (lane < PCG5_REPL) ll_store(cB + 2 * ((size_t)lane * nc + rowi), (double)sacc, ctag);
 				}
-				if (k >= 0) advance_vectors();
+				if (TUNED && k >= 0) advance_vectors();
 				{
 					const unsigned long long* cR = cB + 2 * ((size_t)rep * nc);
 					double* cdst = sizeof(T) == 8 ? reinterpret_cast<double*>(s_c) : s_pv;
-					const bool ok = ll_poll_many(nagg * 6, [&](int i) { return cR + 2 * (size_t)(s_alist[i / 6] * 6 + (i % 6)); }, cdst, ctag, a.ctl);
+					const bool ok = ll_poll_many<PCG5_BLOCK, PCG5_PCH>(nagg * 6, [&](int i) { return cR + 2 * (size_t)(s_alist[i / 6] * 6 + (i % 6)); }, cdst, ctag, a.ctl);
 					if (!ok) s_abort = 1;
 				}
 				__syncthreads();
@@ -706,54 +721,97 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 			for (int o = 1; o < tpp; o <<= 1) wacc[0] += __shfl_xor_sync(0xffffffffu, wacc[0], o);
 			PCG_T(t6);
 			// ---- publish w (own board + the boards of the ranks that need the row), partial inner products, Z^^T w ----
-			// Every (row, component) thread keeps its nine products in registers; a butterfly adds them over the warp, lane 0 leaves the
-			// warp's sums in shared memory and 9 x REPL threads add the eight warps in a fixed order and publish the replicas.
-			double* s_q = reinterpret_cast<double*>(smem_raw + lay.sq);   // [warps][9]; rewritten only after the next pass's barriers
-			double q9[9];
+			if constexpr (TUNED == 1) {
+				// Every (row, component) thread keeps its nine products in registers; a butterfly adds them over the warp, lane 0 leaves the
+				// warp's sums in shared memory and 9 x REPL threads add the eight warps in a fixed order and publish the replicas.
+				double* s_q = reinterpret_cast<double*>(smem_raw + lay.sq);   // [warps][9]; rewritten only after the next pass's barriers
+				double q9[9];
 #pragma unroll
-			for (int w = 0; w < 9; w++) q9[w] = 0.0;
+				for (int w = 0; w < 9; w++) q9[w] = 0.0;
 #pragma unroll
-			for (int pu = 0; pu < NPU; pu++) {
-				const int pair = tid / tpp + pu * PCG5_BLOCK;
-				if (!(pair < npairs && (tid % tpp) == 0 && (pu == 0 || tpp == 1))) continue;
-				const int li = pair / 6, comp = pair - 6 * li;
-				const int dl = s_diag[li];
-				const T ri = s_r[6 * (size_t)dl + comp];
-				const T ui = s_v[6 * (size_t)dl + comp];
-				const T wv1 = wacc[pu] + ui;                                   // A^_ii = I
-				const size_t slot = wHalf + (size_t)opar * wStride + 6 * (size_t)(row0 + li) + comp;
-				ll_store(a.wBoard + 2 * slot, (double)wv1, otag);
-				if (world > 1) {
-					unsigned int peers = a.rowPeers[row0 + li];
-					while (peers) {
-						const int pr = __ffs(peers) - 1;
-						peers &= peers - 1;
-						ll_store(a.peerW[pr] + 2 * slot, (double)wv1, otag);
+				for (int pu = 0; pu < NPU; pu++) {
+					const int pair = tid / tpp + pu * PCG5_BLOCK;
+					if (!(pair < npairs && (tid % tpp) == 0 && (pu == 0 || tpp == 1))) continue;
+					const int li = pair / 6, comp = pair - 6 * li;
+					const int dl = s_diag[li];
+					const T ri = s_r[6 * (size_t)dl + comp];
+					const T ui = s_v[6 * (size_t)dl + comp];
+					const T wv1 = wacc[pu] + ui;                                   // A^_ii = I
+					const size_t slot = wHalf + (size_t)opar * wStride + 6 * (size_t)(row0 + li) + comp;
+					ll_store(a.wBoard + 2 * slot, (double)wv1, otag);
+					if (world > 1) {
+						unsigned int peers = a.rowPeers[row0 + li];
+						while (peers) {
+							const int pr = __ffs(peers) - 1;
+							peers &= peers - 1;
+							ll_store(a.peerW[pr] + 2 * slot, (double)wv1, otag);
+						}
+					}
+					q9[0] += (double)ri * (double)ui;
+					q9[1] += (double)wv1 * (double)ui;
+					q9[2] += (double)ri * (double)ri;
+					if (coarse) {
+						const T* Zh = a.dims.zhInSmem ? s_zh + 36 * (size_t)dl + comp : a.Zhat + 36 * (size_t)(row0 + li) + comp;
+#pragma unroll
+						for (int q = 0; q < 6; q++) q9[3 + q] += (double)(Zh[6 * q] * wv1);   // (Z^^T w)(q) = sum_comp Z^(comp,q) w(comp)
 					}
 				}
-				q9[0] += (double)ri * (double)ui;
-				q9[1] += (double)wv1 * (double)ui;
-				q9[2] += (double)ri * (double)ri;
-				if (coarse) {
-					const T* Zh = a.dims.zhInSmem ? s_zh + 36 * (size_t)dl + comp : a.Zhat + 36 * (size_t)(row0 + li) + comp;
 #pragma unroll
-					for (int q = 0; q < 6; q++) q9[3 + q] += (double)(Zh[6 * q] * wv1);   // (Z^^T w)(q) = sum_comp Z^(comp,q) w(comp)
+				for (int w = 0; w < 9; w++) if (w < NP) q9[w] = warp_sum(q9[w]);
+				if (lane == 0) {
+#pragma unroll
+					for (int w = 0; w < 9; w++) if (w < NP) s_q[wid * 9 + w] = q9[w];
 				}
-			}
+				__syncthreads();
+				PCG_T(t7);
+				if (tid < NP * PCG5_REPL) {
+					const int word = tid / PCG5_REPL, rp = tid - word * PCG5_REPL;
+					double v = 0;
 #pragma unroll
-			for (int w = 0; w < 9; w++) if (w < NP) q9[w] = warp_sum(q9[w]);
-			if (lane == 0) {
+					for (int w8 = 0; w8 < PCG5_BLOCK / 32; w8++) v += s_q[w8 * 9 + word];
+					ll_store(a.pBoard + 2 * (pHalf + (size_t)opar * pStride + ((size_t)rp * G + lc) * NP + word), v, otag);
+				}
+			} else {
+				// The nine quantities of the (row, component) threads go to shared memory; afterwards warp w adds quantity w (with eight
+				// warps warp 0 also the ninth) in a fixed order and its first REPL lanes publish the replicas.
+				const int nact = nrows * 6;                           // active threads: tid = pair * tpp
+				double* s_q = reinterpret_cast<double*>(smem_raw + lay.sq);   // [9][nact]; read below, rewritten only after the next pass's barriers
 #pragma unroll
-				for (int w = 0; w < 9; w++) if (w < NP) s_q[wid * 9 + w] = q9[w];
-			}
-			__syncthreads();
-			PCG_T(t7);
-			if (tid < NP * PCG5_REPL) {
-				const int word = tid / PCG5_REPL, rp = tid - word * PCG5_REPL;
-				double v = 0;
+				for (int pu = 0; pu < NPU; pu++) {
+					const int pair = tid / tpp + pu * PCG5_BLOCK;
+					if (!(pair < npairs && (tid % tpp) == 0 && (pu == 0 || tpp == 1))) continue;
+					const int li = pair / 6, comp = pair - 6 * li;
+					const int dl = s_diag[li];
+					const T ri = s_r[6 * (size_t)dl + comp];
+					const T ui = s_v[6 * (size_t)dl + comp];
+					const T wv1 = wacc[pu] + ui;                                   // A^_ii = I
+					const size_t slot = wHalf + (size_t)opar * wStride + 6 * (size_t)(row0 + li) + comp;
+					ll_store(a.wBoard + 2 * slot, (double)wv1, otag);
+					if (world > 1) {
+						unsigned int peers = a.rowPeers[row0 + li];
+						while (peers) {
+							const int pr = __ffs(peers) - 1;
+							peers &= peers - 1;
+							ll_store(a.peerW[pr] + 2 * slot, (double)wv1, otag);
+						}
+					}
+					s_q[pair] = (double)ri * (double)ui;
+					s_q[nact + pair] = (double)wv1 * (double)ui;
+					s_q[2 * nact + pair] = (double)ri * (double)ri;
+					if (coarse) {
+						const T* Zh = a.dims.zhInSmem ? s_zh + 36 * (size_t)dl + comp : a.Zhat + 36 * (size_t)(row0 + li) + comp;
 #pragma unroll
-				for (int w8 = 0; w8 < PCG5_BLOCK / 32; w8++) v += s_q[w8 * 9 + word];
-				ll_store(a.pBoard + 2 * (pHalf + (size_t)opar * pStride + ((size_t)rp * G + lc) * NP + word), v, otag);
+						for (int q = 0; q < 6; q++) s_q[(3 + q) * nact + pair] = (double)(Zh[6 * q] * wv1);   // (Z^^T w)(q) = sum_comp Z^(comp,q) w(comp)
+					}
+				}
+				__syncthreads();
+				PCG_T(t7);
+				for (int word = wid; word < NP; word += PCG5_BLOCK / 32) {
+					double v = 0;
+					for (int i = lane; i < nact; i += 32) v += s_q[word * nact + i];
+					v = warp_sum(v);
+					if (lane < PCG5_REPL) ll_store(a.pBoard + 2 * (pHalf + (size_t)opar * pStride + ((size_t)lane * G + lc) * NP + word), v, otag);
+				}
 			}
 			PCG_T(t8);
 			PCG_ACC(3, t4, t5); PCG_ACC(4, t5, t6); PCG_ACC(5, t6, t7); PCG_ACC(6, t7, t8);

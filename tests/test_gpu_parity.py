@@ -251,6 +251,36 @@ def test_all_pcg_kernels_solve_the_same_system(pkg, oracle, problems, variant):
     eng.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", [5, 6])
+def test_pcg5_legacy_and_tuned_shapes_agree(pkg, oracle, problems, variant, monkeypatch):
+    """k_pcg5 has two launch shapes: the tuned one (512 threads; a solve on one GPU whose blocks fit on chip) and the legacy one
+    (256 threads; row-distributed and large solves).  CUBA_PCG5_LEGACY forces the legacy shape on one GPU: both against the
+    direct solve of the oracle, and against each other."""
+    prob = problems("kitti07_shaped"); rk = KERNELS["huber"]
+    o = oracle.Oracle(prob, *rk)
+    o.compute_errors(); o.build_system()
+    out = {}
+    for shape in ("tuned", "legacy"):
+        if shape == "legacy":
+            monkeypatch.setenv("CUBA_PCG5_LEGACY", "1")
+        eng = make_engine(pkg, prob, rk, pcg_variant=variant)
+        eng.linearize()
+        res = []
+        for lam, tol in ((1e3, TOL), (10.0, 1e-9), (0.1, 1e-7)):
+            iters, ok = eng.solve(lam); assert ok and iters > 0
+            assert o.solve(lam)
+            for nme, a, b in zip(("xp", "xl"), eng.delta(), o.delta()):
+                assert relerr(a, b) < tol, (shape, nme, lam, iters, relerr(a, b))
+            res.append((iters, [x.copy() for x in eng.delta()]))
+        out[shape] = res
+        eng.close()
+    for (it_t, d_t), (it_l, d_l) in zip(out["tuned"], out["legacy"]):
+        assert abs(it_t - it_l) <= 2, (it_t, it_l)
+        for a, b in zip(d_t, d_l):
+            assert relerr(a, b) < 1e-7
+
+
 def _variant(pkg, base, **kw):
     from test_structure import _variant as v
     return v(pkg, base, **kw)

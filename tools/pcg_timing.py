@@ -22,7 +22,7 @@ VARIANT = int(os.environ.get("PCG_VARIANT", "0"))
 names = ["poll", "sync_after_poll", "scalars", "update+sync", "spmv", "reduce+sync", "publish"] if VARIANT not in (3, 5, 6) else \
     ["loads+scalars", "rc+owners+gather", "coarse slices", "u", "spmv+restrict", "reduce+publish", "grid barrier"]
 if VARIANT in (5, 6):   # k_pcg5
-    names = ["poll w + partials", "local sums (+rank hop) + scalars", "advance r,s,p,y,rc", "coarse slices + u", "spmv + row sums", "publish w + warp sums", "publish partials"]
+    names = ["poll w + partials", "local sums (+rank hop) + scalars", "advance rc (BJ: r,s,p,y)", "coarse rows, advance r,s,p,y, poll c, u", "spmv + row sums", "publish w + butterfly sums", "publish partials"]
 for workload in sys.argv[1:] or ["kitti00_shaped"]:
     path = os.path.join(ROOT, "oracle", "_ref", "fixtures", workload + ".cubagraph")
     g = pkg.graphio.read_graph(path) if workload.startswith("ba_") else pkg.synth.make_config(workload)
@@ -40,6 +40,6 @@ for workload in sys.argv[1:] or ["kitti00_shaped"]:
     print("%s: %d iters, %.2f us/iter, %d CTAs; cycles per iteration (thread 0 of each CTA): mean / min / max over CTAs" % (workload, it, 1e3 * ms / it, n))
     for i, nm in enumerate(names):
         c = t[:, i] / iters
-        print("   %-16s %8.0f %8.0f %8.0f" % (nm, c.mean(), c.min(), c.max()))
+        print("   %-42s %8.0f %8.0f %8.0f" % (nm, c.mean(), c.min(), c.max()))
     print("   total            %8.0f" % (t[:, :7].sum(1) / iters).mean())
     eng.close()
