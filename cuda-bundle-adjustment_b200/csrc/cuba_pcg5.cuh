@@ -721,6 +721,9 @@ __global__ void __launch_bounds__((Pcg5Shape<BIG, TUNED>::BLOCK), 1) k_pcg5(cons
 			for (int o = 1; o < tpp; o <<= 1) wacc[0] += __shfl_xor_sync(0xffffffffu, wacc[0], o);
 			PCG_T(t6);
 			// ---- publish w (own board + the boards of the ranks that need the row), partial inner products, Z^^T w ----
+#ifdef CUBA_PCG_TIMING
+			long long t7 = 0;
+#endif
 			if constexpr (TUNED == 1) {
 				// Every (row, component) thread keeps its nine products in registers; a butterfly adds them over the warp, lane 0 leaves the
 				// warp's sums in shared memory and 9 x REPL threads add the eight warps in a fixed order and publish the replicas.
@@ -763,7 +766,9 @@ __global__ void __launch_bounds__((Pcg5Shape<BIG, TUNED>::BLOCK), 1) k_pcg5(cons
 					for (int w = 0; w < 9; w++) if (w < NP) s_q[wid * 9 + w] = q9[w];
 				}
 				__syncthreads();
-				PCG_T(t7);
+#ifdef CUBA_PCG_TIMING
+				t7 = clock64();
+#endif
 				if (tid < NP * PCG5_REPL) {
 					const int word = tid / PCG5_REPL, rp = tid - word * PCG5_REPL;
 					double v = 0;
@@ -805,7 +810,9 @@ __global__ void __launch_bounds__((Pcg5Shape<BIG, TUNED>::BLOCK), 1) k_pcg5(cons
 					}
 				}
 				__syncthreads();
-				PCG_T(t7);
+#ifdef CUBA_PCG_TIMING
+				t7 = clock64();
+#endif
 				for (int word = wid; word < NP; word += PCG5_BLOCK / 32) {
 					double v = 0;
 					for (int i = lane; i < nact; i += 32) v += s_q[word * nact + i];
