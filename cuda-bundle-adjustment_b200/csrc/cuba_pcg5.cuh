@@ -36,7 +36,8 @@ namespace cuba_b200 {
 // large-graph (BIG) measurement was made with; kept unchanged for the row-distributed and the BIG solves.  TUNED (one GPU, the
 // whole system in registers + shared memory): 512 threads with one register block each -- twice the warps to hide the shared-memory
 // and L2 latencies of the short phases -- the coarse product published before r, s, p, y are advanced, the three scalars summed by
-// three warps instead of by all of them (ba_kitti_00: 14.1 -> 11.7 us per iteration, profiles/r02_pcg5_shape_ab.log).
+// three warps instead of by all of them, the nine partial products added by warp butterflies (ba_kitti_00: 14.1 -> 11.2 us per
+// iteration, profiles/r02_pcg5_shape_ab.log).
 constexpr int PCG5_BLOCK = 256;                    // LEGACY block; bounds the rows per CTA of every plan (2 * 256 / 6)
 template <bool BIG, int TUNED>
 struct Pcg5Shape {
