@@ -20,9 +20,7 @@
 #include "cuba_pcg3.cuh"
 #include "cuba_pcg4.cuh"
 #include "cuba_pcg5.cuh"
-#ifndef P5_TUNED
-#define P5_TUNED 1          // the tuned k_pcg5 shape (cuba_pcg5.cuh); 2 = the same with the legacy shared-memory staging of the partial products (11.6 vs 11.2 us per iteration)
-#endif
+#include "cuba_pcg5t.cuh"
 #include "cuba_coarse_dense.cuh"
 #include "cuba_peer_reduce.cuh"
 #include "cuba_schur2.cuh"
@@ -1461,6 +1459,7 @@ struct Engine : EngineBase {
 	size_t p5Smem = 0;
 	int p5G = 0, p5W = 1, p5A = 0, p5Gs = 1;
 	bool p5Ok = false, p5Dist = false, p5Big = false, p5Tuned = false;
+	p5t::Pcg5Dims p5tDims{}, p5tDimsBJ{};            // the tuned one-GPU shape (cuba_pcg5t.cuh), when p5Tuned
 	const void* p5Fn = nullptr;
 	int p5Block = PCG5_BLOCK;
 	int p5Cluster = 0;                             // CTAs of the cluster that factors the coarse matrix (0: one CTA)
@@ -1574,17 +1573,40 @@ struct Engine : EngineBase {
 		d.needMax = PP.needMax; d.maxRows = PP.maxRows; d.nc = nc; d.maxNeedAgg = CP.maxNeedAgg;
 		d.npv = std::max(std::max(G * 9, W * NR), 6 * CP.maxNeedAgg); d.nls = NR;
 		d.sliceRows = (nc + G - 1) / G;
-		// staging of the block products: one round when a CTA's blocks fit a chunk (then only as many slots as needed; the polled w
-		// entries of the needed columns share the storage)
-		// shape (cuba_pcg5.cuh): the tuned one for a solve on one GPU whose blocks fit registers + shared memory, else the legacy one
-		bool tuned = W == 1 && !getenv("CUBA_PCG5_LEGACY");
-		d.sqWords = std::max(9 * PP.maxRows * 6, 9 * 16);
 		const size_t per = 36 * sizeof(T) + 4;
 		size_t wantCache = PP.blkMax > PCG5_REGBLK ? (size_t)(PP.blkMax - PCG5_REGBLK) : 0;
-		bool big = !tuned && PP.maxRows * 6 > PCG5_BLOCK;
-		for (int attempt = 0; attempt < 2; attempt++) {
-			const int chunk = tuned ? Pcg5Shape<false, P5_TUNED>::CHUNK : Pcg5Shape<false, 0>::CHUNK;
-			d.ccCap = PP.blkMax >= chunk ? chunk : std::max((std::max(PP.blkMax, PP.needMax) + 31) / 32 * 32, 32);
+		// the tuned shape (cuba_pcg5t.cuh): a solve on one GPU whose blocks fit registers + shared memory
+		p5Tuned = false;
+		if (W == 1 && !getenv("CUBA_PCG5_LEGACY")) {
+			using TS = p5t::Pcg5Shape<false, 1>;
+			p5t::Pcg5Dims t{};
+			t.needMax = PP.needMax; t.maxRows = PP.maxRows; t.nc = nc; t.maxNeedAgg = CP.maxNeedAgg;
+			t.npv = d.npv; t.nls = NR; t.sliceRows = d.sliceRows;
+			t.ccCap = PP.blkMax >= TS::CHUNK ? TS::CHUNK : std::max((std::max(PP.blkMax, PP.needMax) + 31) / 32 * 32, 32);
+			t.sqWords = std::max(9 * PP.maxRows * 6, 9 * (TS::BLOCK / 32));
+			t.capBlocks = 0; t.zhInSmem = 0;
+			const size_t base = p5t::Pcg5Layout<T>(t).total + 64;
+			const size_t zhBytes = (size_t)t.needMax * 36 * sizeof(T);
+			size_t used = base + wantCache * per;
+			if (used + zhBytes <= budget) { t.zhInSmem = 1; used += zhBytes; }
+			if (PP.maxRows * 6 <= TS::BLOCK && used <= budget) {
+				t.capBlocks = (int)wantCache;
+				p5tDims = t;
+				p5tDimsBJ = t; p5tDimsBJ.nc = 0; p5tDimsBJ.maxNeedAgg = 0; p5tDimsBJ.zhInSmem = 0; p5tDimsBJ.sliceRows = 0; p5tDimsBJ.nls = 3; p5tDimsBJ.npv = std::max(G * 3, W * 3);
+				const size_t smemT = std::max(p5t::Pcg5Layout<T>(p5tDims).total, p5t::Pcg5Layout<T>(p5tDimsBJ).total);
+				const void* fn = (const void*)p5t::k_pcg5<T, false, 1>;
+				int perSM = 0;
+				if (smemT <= (size_t)smemMax - 1024 && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemT) == cudaSuccess &&
+					cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, fn, TS::BLOCK, smemT) == cudaSuccess && perSM >= 1) {
+					p5Tuned = true; p5Big = false; p5Fn = fn; p5Block = TS::BLOCK; p5Smem = smemT;
+					p5Dims = Pcg5Dims{}; p5Dims.capBlocks = t.capBlocks;
+					d.capBlocks = t.capBlocks; d.zhInSmem = t.zhInSmem;
+				} else cudaGetLastError();
+			}
+		}
+		if (!p5Tuned) {
+		bool big = PP.maxRows * 6 > PCG5_BLOCK;
+		{
 			d.capBlocks = 0; d.zhInSmem = 0;
 			const size_t base = Pcg5Layout<T>(d).total + 64;
 			if (base > budget) return CUBA_OK;
@@ -1595,24 +1617,22 @@ struct Engine : EngineBase {
 			d.capBlocks = (int)std::min(wantCache, (budget - fixed) / per);
 			// blocks would have to be streamed from the global copy every pass: the variant without register-resident blocks streams
 			// with eighteen 16-byte loads in flight per thread (the register variant can afford six 8-byte loads)
-			if ((size_t)d.capBlocks < wantCache) {
-				if (tuned) { tuned = false; big = PP.maxRows * 6 > PCG5_BLOCK; continue; }   // size the legacy shape instead
-				big = true;
-			}
+			if ((size_t)d.capBlocks < wantCache) big = true;
 			if (big) d.capBlocks = (int)std::min((size_t)PP.blkMax, (budget - fixed) / per);
-			break;
 		}
 		p5Dims = d;
 		p5DimsBJ = d; p5DimsBJ.nc = 0; p5DimsBJ.maxNeedAgg = 0; p5DimsBJ.zhInSmem = 0; p5DimsBJ.sliceRows = 0; p5DimsBJ.nls = 3; p5DimsBJ.npv = std::max(G * 3, W * 3);
 		p5Smem = std::max(Pcg5Layout<T>(p5Dims).total, Pcg5Layout<T>(p5DimsBJ).total);
 		if (p5Smem > (size_t)smemMax - 1024) return CUBA_OK;
-		p5Big = big; p5Tuned = tuned && !big;
-		p5Fn = p5Big ? (const void*)k_pcg5<T, true, 0> : p5Tuned ? (const void*)k_pcg5<T, false, P5_TUNED> : (const void*)k_pcg5<T, false, 0>;
-		p5Block = p5Tuned ? Pcg5Shape<false, P5_TUNED>::BLOCK : PCG5_BLOCK;
+		p5Big = big;
+		p5Fn = p5Big ? (const void*)k_pcg5<T, true> : (const void*)k_pcg5<T, false>;
+		p5Block = PCG5_BLOCK;
 		CUDA_TRY(cudaFuncSetAttribute(p5Fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p5Smem));
 		int perSM = 0;
-		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, p5Fn, p5Block, p5Smem));
+		if (p5Big) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_pcg5<T, true>, PCG5_BLOCK, p5Smem));
+		else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_pcg5<T, false>, PCG5_BLOCK, p5Smem));
 		if (perSM < 1) return CUBA_OK;
+		}
 		if (getenv("CUBA_PCG_VERBOSE")) fprintf(stderr, "pcg5: world %d G %d gs %d A %d needMax %d maxRows %d blkMax %d maxNeedAgg %d zhInSmem %d sliceRows %d cap %d smem %zu\n",
 			W, G, gs, A, d.needMax, d.maxRows, PP.blkMax, d.maxNeedAgg, d.zhInSmem, d.sliceRows, d.capBlocks, p5Smem);
 		if (getenv("CUBA_PCG_VERBOSE")) fprintf(stderr, "pcg5: shape %s, %d threads\n", p5Big ? "big" : p5Tuned ? "tuned" : "legacy", p5Block);
@@ -1741,33 +1761,52 @@ struct Engine : EngineBase {
 			p5CoarseAge++;
 		}
 		CUDA_TRY(cudaGetLastError());
-		Pcg5Args<T> a;
-		a.fRowPtr = fRowPtr; a.fColInd = fColInd; a.fLocal = p5Local; a.fVal = fVal; a.fHat = fHat;
-		a.ctaRow = p5CtaRow; a.needPtr = p5NeedPtr; a.needCol = p5NeedCol;
-		a.numP = numP; a.G = p5G; a.rank = p5Dist ? rank : 0; a.world = p5W;
-		a.Linv = p5Linv; a.R0 = p5R0; a.Zhat = p5Zhat; a.rc0 = p5Rc0; a.x = xp;
-		a.dims = twoLevel ? p5Dims : p5DimsBJ;
-		a.dims.capBlocks = p5Dims.capBlocks;
-		a.maxIters = maxIters;
-		const double tol = cfg.pcg_tol > 0 ? cfg.pcg_tol : (sizeof(T) == 8 ? 1e-11 : 1e-6);
-		a.tol2 = tol * tol;
-		a.status = &dScal.p->pcg;
-		a.AcInv = p5AcInv; a.naPtr = p5NaPtr; a.naList = p5NaList; a.needAgg = p5NeedAgg; a.A = A; a.gs = p5Gs;
-		for (int r = 0; r < PCG5_MAXWORLD; r++) { a.peerW[r] = nullptr; a.peerR[r] = nullptr; a.peerCtl[r] = nullptr; }
-		for (int r = 0; r < p5W; r++) {
-			unsigned long long* base = (unsigned long long*)p5PeerBase[p5Dist ? r : rank];
-			a.peerW[r] = base; a.peerR[r] = base + 2 * (p5WWords + p5PWords); a.peerCtl[r] = p5Ctl(base);
-		}
-		a.wBoard = p5Boards.p; a.pBoard = p5Boards.p + 2 * p5WWords; a.rBoard = p5Boards.p + 2 * (p5WWords + p5PWords);
-		a.cBoard = p5Boards.p + 2 * (p5WWords + p5PWords + p5RWords);
-		a.rowPeers = p5RowPeers; a.ctl = p5Ctl(p5Boards.p);
-		a.timing = nullptr;
+		// the same arguments for both shapes (cuba_pcg5.cuh / cuba_pcg5t.cuh differ only in their Pcg5Dims)
+		auto fill = [&](auto& a) {
+			using CtlPtr = decltype(a.ctl);
+			a.fRowPtr = fRowPtr; a.fColInd = fColInd; a.fLocal = p5Local; a.fVal = fVal; a.fHat = fHat;
+			a.ctaRow = p5CtaRow; a.needPtr = p5NeedPtr; a.needCol = p5NeedCol;
+			a.numP = numP; a.G = p5G; a.rank = p5Dist ? rank : 0; a.world = p5W;
+			a.Linv = p5Linv; a.R0 = p5R0; a.Zhat = p5Zhat; a.rc0 = p5Rc0; a.x = xp;
+			a.maxIters = maxIters;
+			const double tol = cfg.pcg_tol > 0 ? cfg.pcg_tol : (sizeof(T) == 8 ? 1e-11 : 1e-6);
+			a.tol2 = tol * tol;
+			a.status = &dScal.p->pcg;
+			a.AcInv = p5AcInv; a.naPtr = p5NaPtr; a.naList = p5NaList; a.needAgg = p5NeedAgg; a.A = A; a.gs = p5Gs;
+			for (int r = 0; r < PCG5_MAXWORLD; r++) { a.peerW[r] = nullptr; a.peerR[r] = nullptr; a.peerCtl[r] = nullptr; }
+			for (int r = 0; r < p5W; r++) {
+				unsigned long long* base = (unsigned long long*)p5PeerBase[p5Dist ? r : rank];
+				a.peerW[r] = base; a.peerR[r] = base + 2 * (p5WWords + p5PWords); a.peerCtl[r] = reinterpret_cast<CtlPtr>(p5Ctl(base));
+			}
+			a.wBoard = p5Boards.p; a.pBoard = p5Boards.p + 2 * p5WWords; a.rBoard = p5Boards.p + 2 * (p5WWords + p5PWords);
+			a.cBoard = p5Boards.p + 2 * (p5WWords + p5PWords + p5RWords);
+			a.rowPeers = p5RowPeers; a.ctl = reinterpret_cast<CtlPtr>(p5Ctl(p5Boards.p));
+			a.timing = nullptr;
+		};
 #ifdef CUBA_PCG_TIMING
 		CUDA_TRY(pcgTiming.alloc(8 * (size_t)p5G));
-		a.timing = pcgTiming.p;
 #endif
 		if (p5Dist) CUDA_TRY(cudaMemsetAsync(xp.p, 0, sizeof(T) * 6 * (size_t)numP, stream));     // rows of the other ranks: summed in below
-		void* args[] = { (void*)&a };
+		Pcg5Args<T> a;
+		p5t::Pcg5Args<T> at;
+		void* args[1];
+		if (p5Tuned) {
+			fill(at);
+			at.dims = twoLevel ? p5tDims : p5tDimsBJ;
+			at.dims.capBlocks = p5tDims.capBlocks;
+#ifdef CUBA_PCG_TIMING
+			at.timing = pcgTiming.p;
+#endif
+			args[0] = (void*)&at;
+		} else {
+			fill(a);
+			a.dims = twoLevel ? p5Dims : p5DimsBJ;
+			a.dims.capBlocks = p5Dims.capBlocks;
+#ifdef CUBA_PCG_TIMING
+			a.timing = pcgTiming.p;
+#endif
+			args[0] = (void*)&a;
+		}
 		CUDA_TRY(cudaLaunchCooperativeKernel(p5Fn, dim3(p5G), dim3(p5Block), args, p5Smem, stream));
 		k_pcg5_commit<<<1, 1, 0, stream>>>(p5Ctl(p5Boards.p));
 		launches += 2;

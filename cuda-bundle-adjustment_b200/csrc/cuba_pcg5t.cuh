@@ -1,44 +1,42 @@
-// cuba_pcg5.cuh -- fifth-generation PCG on the reduced pose system: the two-level preconditioner of k_pcg4 inside the
-// barrier-free exchange protocol of k_pcg3, with the block rows DISTRIBUTED OVER THE GPUs OF ONE NVLink DOMAIN.
-//
-//   mathematics   = k_pcg4: hat space A^ = L^-1 S L^-T, preconditioner M^-1 = I + Z^ (Z^T S Z)^-1 Z^^T (block-Jacobi + rigid-body
-//                   coarse correction over pose aggregates), Chronopoulos-Gear single-reduction CG, stop on the block-Jacobi
-//                   norm r^.r^ <= tol^2 r0^.r0^.  With A == 0 the coarse level is switched off (plain block-Jacobi = k_pcg3).
-//   exchange      = k_pcg3: every value another CTA needs travels as "LL" words (fp64 split in two 32-bit halves, each next to
-//                   a 32-bit tag in one 8-byte single-copy-atomic store); consumers poll, nobody fences, no grid barrier.
-//   distribution  = the system's rows are cut into Gt = world * G contiguous ranges ("virtual CTAs"); GPU g runs the G CTAs
-//                   [g*G, (g+1)*G) with their A^ blocks in registers / shared memory.  What crosses GPUs, per iteration:
-//                     * the six w entries of the rows a peer's CTAs need (halo rows): the owner stores the same LL words into
-//                       the peer's board through NVLink peer memory (cudaIpc-mapped), in the same instruction stream;
-//                     * one rank summary (gamma, delta, rho and the restricted Z^^T w of the rank's aggregates): every CTA
-//                       sums its GPU's partial board itself (one L2 hop, as k_pcg3), designated CTAs push the summary to every
-//                       peer (one NVLink hop), everybody adds the summaries in rank order -> bit-identical scalars on all GPUs,
-//                       hence identical iteration counts and exit passes without any host involvement.
-//                   No NCCL call inside the solve.  world == 1 skips the rank hop.
-//   coarse level  = c = (Z^T S Z)^-1 rc is computed ONCE per GPU and pass: every CTA holds the whole coarse residual rc (advanced by
-//                   the CG recurrences from the published Z^^T w), multiplies it with ITS few rows of the explicit inverse (shared
-//                   memory, fp32) and publishes the result on a third LL board; consumers poll the six entries of each aggregate
-//                   their columns belong to.  One more L2 hop per pass, but the work is balanced: with k_pcg4's scheme (every CTA
-//                   multiplies the rows of all its needed aggregates itself) the CTAs next to loop closures of the real ba_kitti_00
-//                   needed 18 aggregates = 108 rows x 444 columns from L2 per pass and everybody waited for them (22.6 k of 40 k
-//                   cycles per pass, profiles/r02_pcg5_phase_ticks_v1.log).
-//   tags          = tagBase + pass, tagBase advanced by every solve (device-resident Pcg5Ctl): boards are never cleared;
-//                   boards are double-buffered by pass parity and by solve parity (a peer may start the next solve while a
-//                   slow CTA here still reads the last pass of this one).
-// Replaces convertBSRToCSR + cuSOLVER csrchol (reference cuda_linear_solver.cpp:301-335) like the other PCG kernels.
+// cuba_pcg5t.cuh -- k_pcg5 (cuba_pcg5.cuh: same mathematics, same LL-word exchange, same boards and tags) in the launch shape
+// tuned for ONE GPU whose reduced system fits registers + shared memory (ba_kitti_00 class: <= 512 + cached blocks per CTA):
+//   * 512 threads with one register-resident block each (cuba_pcg5.cuh: 256 threads, two blocks): twice the warps to hide the
+//     shared-memory and L2 latencies of the short phases between the exchanges;
+//   * the coarse residual is advanced first and this CTA's rows of c = Ac^-1 rc are published BEFORE r, s, p, y are advanced, so the
+//     words cross the L2 while the CTA still has work to do;
+//   * the three scalars are summed by three warps (one each) instead of by all sixteen; the nine partial products of the
+//     (row, component) threads are added by warp butterflies instead of through a shared-memory staging array;
+//   * up to two blocks per thread in one product round (register block, then one cached block), the staging sized by what a CTA owns.
+// ba_kitti_00: 14.1 -> 11.2 us per iteration (profiles/r02_pcg5_shape_ab.log lists every step and what did not help).
+// cuba_pcg5.cuh stays byte-for-byte what every multi-GPU and large-graph measurement was made with: the same source restructured
+// to serve both shapes ran 12 % slower on the streamed (BIG) path (profiles/r02_pcg5_big_regression.log), so the shapes live in two files.
+// The engine picks this kernel for world == 1 solves whose blocks fit on chip (CUBA_PCG5_LEGACY=1 forces the other one).
 #pragma once
 
-#include "cuba_pcg4.cuh"
+#include "cuba_pcg5.cuh"
 
 namespace cuba_b200 {
+namespace p5t {
 
-constexpr int PCG5_BLOCK = 256;
-constexpr int PCG5_BPT = 2;                        // register-resident A^ blocks per thread
-constexpr int PCG5_REGBLK = PCG5_BLOCK * PCG5_BPT;
-constexpr int PCG5_CHUNK = PCG5_REGBLK;
+// Launch shapes.  LEGACY (TUNED = 0): 256 threads, two register-resident blocks per thread -- the shape every multi-GPU and every
+// large-graph (BIG) measurement was made with; kept unchanged for the row-distributed and the BIG solves.  TUNED (one GPU, the
+// whole system in registers + shared memory): 512 threads with one register block each -- twice the warps to hide the shared-memory
+// and L2 latencies of the short phases -- the coarse product published before r, s, p, y are advanced, the three scalars summed by
+// three warps instead of by all of them, the nine partial products added by warp butterflies (ba_kitti_00: 14.1 -> 11.2 us per
+// iteration, profiles/r02_pcg5_shape_ab.log).
+constexpr int PCG5_BLOCK = 256;                    // LEGACY block; bounds the rows per CTA of every plan (2 * 256 / 6)
+template <bool BIG, int TUNED>
+struct Pcg5Shape {
+	static constexpr int BLOCK = TUNED ? 512 : PCG5_BLOCK;
+	static constexpr int BPT = TUNED ? 1 : 2;          // register-resident A^ blocks per thread (none with BIG)
+	static constexpr int REGBLK = BIG ? 0 : BLOCK * BPT;
+	static constexpr int CPT = 2;                      // blocks per thread and product round
+	static constexpr int CHUNK = BLOCK * CPT;
+	static constexpr int PCH = TUNED ? 3 : 8;          // polled words in flight per thread
+};
+constexpr int PCG5_REGBLK = 512;                   // both shapes keep 512 blocks in registers
 constexpr int PCG5_REPL = 8;                       // replicas of the partial / summary boards
 constexpr int PCG5_MAXWORLD = 8;
-constexpr int PCG5_PCH = 8;                        // polled words in flight per thread
 constexpr int PCG5_TPR = 16;                       // threads per row of the coarse slice product
 
 // device-resident solve bookkeeping: read by every CTA at its start, changed only BETWEEN solves by k_pcg5_commit
@@ -49,6 +47,8 @@ struct Pcg5Dims {
 	int sliceRows; // rows of the inverse coarse matrix this CTA multiplies: ceil(nc / G)
 	int npv;      // max(G * NP, world * NR): polled partial / summary words
 	int nls;      // NR: words of a rank summary
+	int ccCap;    // slots per component of the block-product staging: the shape's CHUNK, or less when a CTA never owns that many blocks
+	int sqWords;  // doubles of the partial-product staging: 9 * maxRows * 6
 };
 
 // shared-memory carve-up, one definition for the host (size) and the device (pointers)
@@ -65,14 +65,14 @@ struct Pcg5Layout {
 		u = take((size_t)d.needMax * 6 * sizeof(T), 8);
 		p = take((size_t)d.maxRows * 6 * sizeof(T), 8);
 		y = take((size_t)d.maxRows * 6 * sizeof(T), 8);
-		cc = take((size_t)PCG5_CHUNK * 6 * sizeof(double), 8);      // block-product staging; polled w entries (double) between passes
+		cc = take((size_t)d.ccCap * 6 * sizeof(double), 8);      // block-product staging; polled w entries (double) between passes
 		rc = take((size_t)d.nc * sizeof(T), 8);
 		sc = take((size_t)d.nc * sizeof(T), 8);
 		c = take((size_t)d.maxNeedAgg * 6 * sizeof(T), 8);
 		zh = take(d.zhInSmem ? (size_t)d.needMax * 36 * sizeof(T) : 0, 8);
 		pv = take((size_t)d.npv * sizeof(double), 8);
 		ls = take((size_t)d.nls * sizeof(double), 8);
-		sq = take((size_t)9 * d.maxRows * 6 * sizeof(double), 8);   // partial inner products of the (row, component) threads
+		sq = take((size_t)d.sqWords * sizeof(double), 8);           // nine products of every (row, component) thread
 		ai = take((size_t)d.sliceRows * d.nc * sizeof(float), 16);
 		loc = take((size_t)d.capBlocks * sizeof(int), 4);
 		rowPtr = take(((size_t)d.maxRows + 1) * sizeof(int), 4);
@@ -245,11 +245,12 @@ __device__ __forceinline__ bool ll_decode(unsigned long long lo, unsigned long l
 	return true;
 }
 
-// Polls `n` LL words (slot of item i given by slotOf(i)) into dst[i]; PCG5_PCH loads of a thread are in flight together.
-// Returns false when the solve was aborted (a peer vanished: spin limit).
-template <typename SlotOf>
-__device__ __forceinline__ bool ll_poll_many(int n, SlotOf slotOf, double* dst, unsigned int tag, Pcg5Ctl* ctl)
+// Polls `n` LL words (slot of item i given by slotOf(i)) and hands every value to put(i, v); PCG5_PCH loads of a thread are in
+// flight together.  Returns false when the solve was aborted (a peer vanished: spin limit).
+template <int KB, int PCG5_PCH, typename SlotOf, typename Put>
+__device__ __forceinline__ bool ll_poll_each(int n, SlotOf slotOf, Put put, unsigned int tag, Pcg5Ctl* ctl)
 {
+	constexpr int PCG5_BLOCK = KB;                      // (shadows the legacy constant inside this function)
 	const int tid = threadIdx.x;
 	for (int base = 0; base < n; base += PCG5_BLOCK * PCG5_PCH) {
 		unsigned int pend = 0;
@@ -262,7 +263,7 @@ __device__ __forceinline__ bool ll_poll_many(int n, SlotOf slotOf, double* dst, 
 #pragma unroll
 			for (int u = 0; u < PCG5_PCH; u++) if ((pend >> u) & 1u) {
 				double v;
-				if (ll_decode(lo[u], hi[u], tag, v)) { dst[base + u * PCG5_BLOCK + tid] = v; pend &= ~(1u << u); }
+				if (ll_decode(lo[u], hi[u], tag, v)) { put(base + u * PCG5_BLOCK + tid, v); pend &= ~(1u << u); }
 			}
 			if ((spin & 1023u) == 1023u) {
 				if (*(volatile int*)&ctl->abort) return false;
@@ -272,21 +273,30 @@ __device__ __forceinline__ bool ll_poll_many(int n, SlotOf slotOf, double* dst, 
 	}
 	return true;
 }
+template <int KB, int KPCH, typename SlotOf>
+__device__ __forceinline__ bool ll_poll_many(int n, SlotOf slotOf, double* dst, unsigned int tag, Pcg5Ctl* ctl)
+{
+	return ll_poll_each<KB, KPCH>(n, slotOf, [dst](int i, double v) { dst[i] = v; }, tag, ctl);
+}
 
 // BIG: the CTA may own more than 42 rows (up to 85): every thread then serves two (row, component) pairs in the row sums
-template <typename T, bool BIG = false>
-__global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
+template <typename T, bool BIG = false, int TUNED = 0>
+__global__ void __launch_bounds__((Pcg5Shape<BIG, TUNED>::BLOCK), 1) k_pcg5(const Pcg5Args<T> a)
 {
+	static_assert(!(BIG && TUNED), "the tuned shape keeps the whole system on chip");
+	using Shape = Pcg5Shape<BIG, TUNED>;
+	// the names of the legacy constants, bound to this instantiation's shape
+	constexpr int PCG5_BLOCK = Shape::BLOCK, PCG5_BPT = Shape::BPT, PCG5_CPT = Shape::CPT, PCG5_CHUNK = Shape::CHUNK, PCG5_PCH = Shape::PCH;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const Pcg5Layout<T> lay(a.dims);
-	const int capBlocks = a.dims.capBlocks, nc = a.dims.nc;
+	const int capBlocks = a.dims.capBlocks, nc = a.dims.nc, ccCap = a.dims.ccCap;
 	T* s_blk = reinterpret_cast<T*>(smem_raw + lay.blk);            // [36][capBlocks] blocks past the registers, element-major
 	T* s_r = reinterpret_cast<T*>(smem_raw + lay.r);                // [needMax][6] residual of the needed columns
 	T* s_s = reinterpret_cast<T*>(smem_raw + lay.s);                // [needMax][6] s = w + beta s
 	T* s_u = reinterpret_cast<T*>(smem_raw + lay.u);                // [needMax][6] u = M^-1 r
 	T* s_p = reinterpret_cast<T*>(smem_raw + lay.p);                // [maxRows][6]
 	T* s_y = reinterpret_cast<T*>(smem_raw + lay.y);                // [maxRows][6]
-	T* s_cc = reinterpret_cast<T*>(smem_raw + lay.cc);              // [6][PCG5_CHUNK] block products, component-major
+	T* s_cc = reinterpret_cast<T*>(smem_raw + lay.cc);              // [6][ccCap] block products, component-major
 	double* s_w = reinterpret_cast<double*>(smem_raw + lay.cc);     // polled w entries of the needed columns (same storage, other phase)
 	T* s_rc = reinterpret_cast<T*>(smem_raw + lay.rc);              // [nc] coarse residual Z^^T r
 	T* s_sc = reinterpret_cast<T*>(smem_raw + lay.sc);              // [nc]
@@ -313,7 +323,7 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 	const int need0 = a.needPtr[cta], nneed = a.needPtr[cta + 1] - need0;
 	const int blk0 = a.fRowPtr[row0], nblkCta = a.fRowPtr[row1] - blk0;
 	// BIG: no register-resident blocks -- the registers go to the loads in flight of the streamed part (see the product loop)
-	constexpr int REGBLK = BIG ? 0 : PCG5_REGBLK;
+	constexpr int REGBLK = Shape::REGBLK;
 	const int ncached = nblkCta > REGBLK ? (nblkCta - REGBLK < capBlocks ? nblkCta - REGBLK : capBlocks) : 0;
 	const size_t n6 = 6 * (size_t)a.numP;
 	const int nover = nblkCta - REGBLK - ncached > 0 ? nblkCta - REGBLK - ncached : 0;   // blocks read from the global copy every pass
@@ -424,6 +434,22 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 #endif
 	int tpp = 1;                                         // threads per (row, component) pair of the row sums, a power of two
 	while (tpp < 8 && nrows * 6 * tpp * 2 <= PCG5_BLOCK) tpp *= 2;
+	// s, r of the needed columns, p, y of the own rows (u_k is still in s_u); alpha, beta of the current pass
+	auto advance_vectors = [&]() {
+		for (int wi = tid; wi < nneed * 6; wi += PCG5_BLOCK) {
+			const T snew = (T)s_w[wi] + (T)beta * s_s[wi];
+			const T rold = s_r[wi];
+			s_s[wi] = snew;
+			s_r[wi] = rold - (T)alpha * snew;
+			const int own = s_own[wi / 6];
+			if (own >= 0) {
+				const int o = own * 6 + (wi % 6);
+				const T p = (coarse ? s_u[wi] : rold) + (T)beta * s_p[o];
+				s_p[o] = p;
+				s_y[o] += (T)alpha * p;
+			}
+		}
+	};
 	if (nbad > 0) status = 2;
 	else {
 		// pass k = -1: u0 = M^-1 r0, w0 = A^ u0, first partials; pass k >= 0: CG iteration k.
@@ -439,16 +465,28 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 					const int nW = nneed * 6, nPl = G * NP;
 					const unsigned long long* wB = a.wBoard + 2 * (wHalf + (size_t)par * wStride);
 					const unsigned long long* pB = a.pBoard + 2 * (pHalf + (size_t)par * pStride + (size_t)rep * nPl);
-					// one destination array: s_w directly followed (logically) by s_pv -> two calls keep the indexing simple
-					bool ok = ll_poll_many(nW, [&](int i) { return wB + 2 * (size_t)s_woff[i]; }, s_w, tag, a.ctl);
-					ok = ok && ll_poll_many(nPl, [&](int i) { return pB + 2 * (size_t)i; }, s_pv, tag, a.ctl);
+					// two lists, one after the other (one mixed list, the loads of both boards in flight together, was slower: +0.6 us per
+					// iteration on ba_kitti_00 with 256 threads, +0.5 us with 512)
+					bool ok = ll_poll_many<PCG5_BLOCK, PCG5_PCH>(nW, [&](int i) { return wB + 2 * (size_t)s_woff[i]; }, s_w, tag, a.ctl);
+					ok = ok && ll_poll_many<PCG5_BLOCK, PCG5_PCH>(nPl, [&](int i) { return pB + 2 * (size_t)i; }, s_pv, tag, a.ctl);
 					if (!ok) s_abort = 1;
 				}
 				__syncthreads();
 				PCG_T(t1);
 				if (s_abort) { status = 3; break; }
 				double gnew, delta, rnew;
-				if (world == 1) {
+				if (world == 1 && TUNED) {
+					// ---- one GPU, 16 warps: three of them add one scalar each over the CTAs (every warp adding all three, as below, keeps
+					//      the shared-memory and shuffle pipes busy for ~2 000 cycles); the others meet them at the barrier ----
+					if (wid < 3) {
+						double v = 0;
+						for (int c = lane; c < G; c += 32) v += s_pv[c * NP + wid];
+						v = warp_sum(v);
+						if (lane == 0) s_ls[wid] = v;
+					}
+					__syncthreads();
+					gnew = s_ls[0]; delta = s_ls[1]; rnew = s_ls[2];
+				} else if (world == 1) {
 					// ---- one GPU: every warp adds the three scalars over the CTAs itself (same order everywhere), no barrier;
 					//      the restricted Z^^T w of an aggregate is summed by the thread that advances that coarse entry ----
 					double v0 = 0, v1 = 0, v2 = 0;
@@ -479,7 +517,7 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 						for (int q = tid; q < NR; q += PCG5_BLOCK) ll_store(dst + 2 * (size_t)q, s_ls[q], tag);
 					}
 					const unsigned long long* rB = a.rBoard + 2 * (rOff + (size_t)rep * world * NR);
-					const bool ok = ll_poll_many(world * NR, [&](int i) { return rB + 2 * (size_t)i; }, s_pv, tag, a.ctl);
+					const bool ok = ll_poll_many<PCG5_BLOCK, PCG5_PCH>(world * NR, [&](int i) { return rB + 2 * (size_t)i; }, s_pv, tag, a.ctl);
 					if (!ok) s_abort = 1;
 					__syncthreads();
 					if (s_abort) { status = 3; break; }
@@ -507,20 +545,10 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 					gamma = gnew;
 				}
 				if (k >= a.maxIters) { status = 1; break; }
-				// ---- advance s, r (needed columns), p, y (own rows; u_k is still in s_u) and the coarse residual ----
-				for (int wi = tid; wi < nneed * 6; wi += PCG5_BLOCK) {
-					const T snew = (T)s_w[wi] + (T)beta * s_s[wi];
-					const T rold = s_r[wi];
-					s_s[wi] = snew;
-					s_r[wi] = rold - (T)alpha * snew;
-					const int own = s_own[wi / 6];
-					if (own >= 0) {
-						const int o = own * 6 + (wi % 6);
-						const T p = (coarse ? s_u[wi] : rold) + (T)beta * s_p[o];
-						s_p[o] = p;
-						s_y[o] += (T)alpha * p;
-					}
-				}
+				// ---- advance s, r (needed columns), p, y (own rows; u_k is still in s_u) and the coarse residual.  TUNED: the coarse
+				//      residual first -- its product with Ac^-1 is published before r, s, p, y are advanced, so that the words
+				//      cross the L2 while this CTA still has work to do ----
+				if (!(TUNED && coarse)) advance_vectors();
 				if (coarse)
 					for (int q = tid; q < nc; q += PCG5_BLOCK) {
 						// global aggregate q/6 = rank r, local aggregate al
@@ -553,10 +581,11 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 					sacc = warp_sum(sacc);
 					if (lane < PCG5_REPL) ll_store(cB + 2 * ((size_t)lane * nc + rowi), (double)sacc, ctag);
 				}
+				if (TUNED && k >= 0) advance_vectors();
 				{
 					const unsigned long long* cR = cB + 2 * ((size_t)rep * nc);
 					double* cdst = sizeof(T) == 8 ? reinterpret_cast<double*>(s_c) : s_pv;
-					const bool ok = ll_poll_many(nagg * 6, [&](int i) { return cR + 2 * (size_t)(s_alist[i / 6] * 6 + (i % 6)); }, cdst, ctag, a.ctl);
+					const bool ok = ll_poll_many<PCG5_BLOCK, PCG5_PCH>(nagg * 6, [&](int i) { return cR + 2 * (size_t)(s_alist[i / 6] * 6 + (i % 6)); }, cdst, ctag, a.ctl);
 					if (!ok) s_abort = 1;
 				}
 				__syncthreads();
@@ -597,17 +626,18 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 			for (int cs = 0; cs < nblkCta; cs += PCG5_CHUNK) {
 				if (cs > 0) __syncthreads();
 #pragma unroll
-				for (int u = 0; u < PCG5_BPT; u++) {
+				for (int u = 0; u < PCG5_CPT; u++) {
 					const int n = cs + u * PCG5_BLOCK + tid;
 					T y[6] = { T(0), T(0), T(0), T(0), T(0), T(0) };
-					if (!BIG && cs == 0) {
-						if (myLoc[u] >= 0) {
-							const T* rj = s_v + 6 * (size_t)myLoc[u];
+					if (!BIG && u < PCG5_BPT && cs == 0) {
+						const int ur = u < PCG5_BPT ? u : 0;
+						if (myLoc[ur] >= 0) {
+							const T* rj = s_v + 6 * (size_t)myLoc[ur];
 #pragma unroll
 							for (int c = 0; c < 6; c++) {
 								const T rc = rj[c];
 #pragma unroll
-								for (int r = 0; r < 6; r++) y[r] += breg[u][c * 6 + r] * rc;
+								for (int r = 0; r < 6; r++) y[r] += breg[ur][c * 6 + r] * rc;
 							}
 						}
 					} else if (n < nblkCta) {
@@ -652,8 +682,10 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 							}
 						}
 					}
+					if (u * PCG5_BLOCK + tid < ccCap) {
 #pragma unroll
-					for (int r = 0; r < 6; r++) s_cc[r * PCG5_CHUNK + u * PCG5_BLOCK + tid] = y[r];
+						for (int r = 0; r < 6; r++) s_cc[r * ccCap + u * PCG5_BLOCK + tid] = y[r];
+					}
 				}
 				__syncthreads();
 #pragma unroll
@@ -665,7 +697,7 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 						n0 = (n0 > cs ? n0 : cs) - cs;
 						n1 = (n1 < cs + PCG5_CHUNK ? n1 : cs + PCG5_CHUNK) - cs;
 						T s0 = T(0), s1 = T(0);
-						const T* col = s_cc + comp * PCG5_CHUNK;
+						const T* col = s_cc + comp * ccCap;
 						int q = n0 + sub;
 						for (; q + tpp < n1; q += 2 * tpp) { s0 += col[q]; s1 += col[q + tpp]; }
 						if (q < n1) s0 += col[q];
@@ -676,45 +708,104 @@ __global__ void __launch_bounds__(PCG5_BLOCK, 1) k_pcg5(const Pcg5Args<T> a)
 			for (int o = 1; o < tpp; o <<= 1) wacc[0] += __shfl_xor_sync(0xffffffffu, wacc[0], o);
 			PCG_T(t6);
 			// ---- publish w (own board + the boards of the ranks that need the row), partial inner products, Z^^T w ----
-			// The nine quantities of the (row, component) threads go to shared memory; afterwards warp w adds quantity w (warp 0
-			// also the ninth) in a fixed order and its first REPL lanes publish the replicas.
-			const int nact = nrows * 6;                           // active threads: tid = pair * tpp
-			double* s_q = reinterpret_cast<double*>(smem_raw + lay.sq);   // [9][nact]; read below, rewritten only after the next pass's barriers
+#ifdef CUBA_PCG_TIMING
+			long long t7 = 0;
+#endif
+			if constexpr (TUNED == 1) {
+				// Every (row, component) thread keeps its nine products in registers; a butterfly adds them over the warp, lane 0 leaves the
+				// warp's sums in shared memory and 9 x REPL threads add the eight warps in a fixed order and publish the replicas.
+				double* s_q = reinterpret_cast<double*>(smem_raw + lay.sq);   // [warps][9]; rewritten only after the next pass's barriers
+				double q9[9];
 #pragma unroll
-			for (int pu = 0; pu < NPU; pu++) {
-				const int pair = tid / tpp + pu * PCG5_BLOCK;
-				if (!(pair < npairs && (tid % tpp) == 0 && (pu == 0 || tpp == 1))) continue;
-				const int li = pair / 6, comp = pair - 6 * li;
-				const int dl = s_diag[li];
-				const T ri = s_r[6 * (size_t)dl + comp];
-				const T ui = s_v[6 * (size_t)dl + comp];
-				const T wv1 = wacc[pu] + ui;                                   // A^_ii = I
-				const size_t slot = wHalf + (size_t)opar * wStride + 6 * (size_t)(row0 + li) + comp;
-				ll_store(a.wBoard + 2 * slot, (double)wv1, otag);
-				if (world > 1) {
-					unsigned int peers = a.rowPeers[row0 + li];
-					while (peers) {
-						const int pr = __ffs(peers) - 1;
-						peers &= peers - 1;
-						ll_store(a.peerW[pr] + 2 * slot, (double)wv1, otag);
+				for (int w = 0; w < 9; w++) q9[w] = 0.0;
+#pragma unroll
+				for (int pu = 0; pu < NPU; pu++) {
+					const int pair = tid / tpp + pu * PCG5_BLOCK;
+					if (!(pair < npairs && (tid % tpp) == 0 && (pu == 0 || tpp == 1))) continue;
+					const int li = pair / 6, comp = pair - 6 * li;
+					const int dl = s_diag[li];
+					const T ri = s_r[6 * (size_t)dl + comp];
+					const T ui = s_v[6 * (size_t)dl + comp];
+					const T wv1 = wacc[pu] + ui;                                   // A^_ii = I
+					const size_t slot = wHalf + (size_t)opar * wStride + 6 * (size_t)(row0 + li) + comp;
+					ll_store(a.wBoard + 2 * slot, (double)wv1, otag);
+					if (world > 1) {
+						unsigned int peers = a.rowPeers[row0 + li];
+						while (peers) {
+							const int pr = __ffs(peers) - 1;
+							peers &= peers - 1;
+							ll_store(a.peerW[pr] + 2 * slot, (double)wv1, otag);
+						}
+					}
+					q9[0] += (double)ri * (double)ui;
+					q9[1] += (double)wv1 * (double)ui;
+					q9[2] += (double)ri * (double)ri;
+					if (coarse) {
+						const T* Zh = a.dims.zhInSmem ? s_zh + 36 * (size_t)dl + comp : a.Zhat + 36 * (size_t)(row0 + li) + comp;
+#pragma unroll
+						for (int q = 0; q < 6; q++) q9[3 + q] += (double)(Zh[6 * q] * wv1);   // (Z^^T w)(q) = sum_comp Z^(comp,q) w(comp)
 					}
 				}
-				s_q[pair] = (double)ri * (double)ui;
-				s_q[nact + pair] = (double)wv1 * (double)ui;
-				s_q[2 * nact + pair] = (double)ri * (double)ri;
-				if (coarse) {
-					const T* Zh = a.dims.zhInSmem ? s_zh + 36 * (size_t)dl + comp : a.Zhat + 36 * (size_t)(row0 + li) + comp;
 #pragma unroll
-					for (int q = 0; q < 6; q++) s_q[(3 + q) * nact + pair] = (double)(Zh[6 * q] * wv1);   // (Z^^T w)(q) = sum_comp Z^(comp,q) w(comp)
+				for (int w = 0; w < 9; w++) if (w < NP) q9[w] = warp_sum(q9[w]);
+				if (lane == 0) {
+#pragma unroll
+					for (int w = 0; w < 9; w++) if (w < NP) s_q[wid * 9 + w] = q9[w];
 				}
-			}
-			__syncthreads();
-			PCG_T(t7);
-			for (int word = wid; word < NP; word += PCG5_BLOCK / 32) {
-				double v = 0;
-				for (int i = lane; i < nact; i += 32) v += s_q[word * nact + i];
-				v = warp_sum(v);
-				if (lane < PCG5_REPL) ll_store(a.pBoard + 2 * (pHalf + (size_t)opar * pStride + ((size_t)lane * G + lc) * NP + word), v, otag);
+				__syncthreads();
+#ifdef CUBA_PCG_TIMING
+				t7 = clock64();
+#endif
+				if (tid < NP * PCG5_REPL) {
+					const int word = tid / PCG5_REPL, rp = tid - word * PCG5_REPL;
+					double v = 0;
+#pragma unroll
+					for (int w8 = 0; w8 < PCG5_BLOCK / 32; w8++) v += s_q[w8 * 9 + word];
+					ll_store(a.pBoard + 2 * (pHalf + (size_t)opar * pStride + ((size_t)rp * G + lc) * NP + word), v, otag);
+				}
+			} else {
+				// The nine quantities of the (row, component) threads go to shared memory; afterwards warp w adds quantity w (with eight
+				// warps warp 0 also the ninth) in a fixed order and its first REPL lanes publish the replicas.
+				const int nact = nrows * 6;                           // active threads: tid = pair * tpp
+				double* s_q = reinterpret_cast<double*>(smem_raw + lay.sq);   // [9][nact]; read below, rewritten only after the next pass's barriers
+#pragma unroll
+				for (int pu = 0; pu < NPU; pu++) {
+					const int pair = tid / tpp + pu * PCG5_BLOCK;
+					if (!(pair < npairs && (tid % tpp) == 0 && (pu == 0 || tpp == 1))) continue;
+					const int li = pair / 6, comp = pair - 6 * li;
+					const int dl = s_diag[li];
+					const T ri = s_r[6 * (size_t)dl + comp];
+					const T ui = s_v[6 * (size_t)dl + comp];
+					const T wv1 = wacc[pu] + ui;                                   // A^_ii = I
+					const size_t slot = wHalf + (size_t)opar * wStride + 6 * (size_t)(row0 + li) + comp;
+					ll_store(a.wBoard + 2 * slot, (double)wv1, otag);
+					if (world > 1) {
+						unsigned int peers = a.rowPeers[row0 + li];
+						while (peers) {
+							const int pr = __ffs(peers) - 1;
+							peers &= peers - 1;
+							ll_store(a.peerW[pr] + 2 * slot, (double)wv1, otag);
+						}
+					}
+					s_q[pair] = (double)ri * (double)ui;
+					s_q[nact + pair] = (double)wv1 * (double)ui;
+					s_q[2 * nact + pair] = (double)ri * (double)ri;
+					if (coarse) {
+						const T* Zh = a.dims.zhInSmem ? s_zh + 36 * (size_t)dl + comp : a.Zhat + 36 * (size_t)(row0 + li) + comp;
+#pragma unroll
+						for (int q = 0; q < 6; q++) s_q[(3 + q) * nact + pair] = (double)(Zh[6 * q] * wv1);   // (Z^^T w)(q) = sum_comp Z^(comp,q) w(comp)
+					}
+				}
+				__syncthreads();
+#ifdef CUBA_PCG_TIMING
+				t7 = clock64();
+#endif
+				for (int word = wid; word < NP; word += PCG5_BLOCK / 32) {
+					double v = 0;
+					for (int i = lane; i < nact; i += 32) v += s_q[word * nact + i];
+					v = warp_sum(v);
+					if (lane < PCG5_REPL) ll_store(a.pBoard + 2 * (pHalf + (size_t)opar * pStride + ((size_t)lane * G + lc) * NP + word), v, otag);
+				}
 			}
 			PCG_T(t8);
 			PCG_ACC(3, t4, t5); PCG_ACC(4, t5, t6); PCG_ACC(5, t6, t7); PCG_ACC(6, t7, t8);
@@ -751,4 +842,5 @@ __global__ void k_pcg5_commit(Pcg5Ctl* ctl)
 	ctl->advance = 0;
 }
 
+}  // namespace p5t
 }  // namespace cuba_b200
