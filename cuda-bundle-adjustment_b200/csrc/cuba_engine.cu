@@ -1578,7 +1578,7 @@ struct Engine : EngineBase {
 		// the tuned shape (cuba_pcg5t.cuh): a solve on one GPU whose blocks fit registers + shared memory
 		p5Tuned = false;
 		if (W == 1 && !getenv("CUBA_PCG5_LEGACY")) {
-			using TS = p5t::Pcg5Shape<false, 1>;
+			using TS = p5t::Pcg5Shape;
 			p5t::Pcg5Dims t{};
 			t.needMax = PP.needMax; t.maxRows = PP.maxRows; t.nc = nc; t.maxNeedAgg = CP.maxNeedAgg;
 			t.npv = d.npv; t.nls = NR; t.sliceRows = d.sliceRows;
@@ -1594,7 +1594,7 @@ struct Engine : EngineBase {
 				p5tDims = t;
 				p5tDimsBJ = t; p5tDimsBJ.nc = 0; p5tDimsBJ.maxNeedAgg = 0; p5tDimsBJ.zhInSmem = 0; p5tDimsBJ.sliceRows = 0; p5tDimsBJ.nls = 3; p5tDimsBJ.npv = std::max(G * 3, W * 3);
 				const size_t smemT = std::max(p5t::Pcg5Layout<T>(p5tDims).total, p5t::Pcg5Layout<T>(p5tDimsBJ).total);
-				const void* fn = (const void*)p5t::k_pcg5<T, false, 1>;
+				const void* fn = (const void*)p5t::k_pcg5t<T>;
 				int perSM = 0;
 				if (smemT <= (size_t)smemMax - 1024 && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemT) == cudaSuccess &&
 					cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, fn, TS::BLOCK, smemT) == cudaSuccess && perSM >= 1) {

@@ -18,29 +18,15 @@
 namespace cuba_b200 {
 namespace p5t {
 
-// Launch shapes.  LEGACY (TUNED = 0): 256 threads, two register-resident blocks per thread -- the shape every multi-GPU and every
-// large-graph (BIG) measurement was made with; kept unchanged for the row-distributed and the BIG solves.  TUNED (one GPU, the
-// whole system in registers + shared memory): 512 threads with one register block each -- twice the warps to hide the shared-memory
-// and L2 latencies of the short phases -- the coarse product published before r, s, p, y are advanced, the three scalars summed by
-// three warps instead of by all of them, the nine partial products added by warp butterflies (ba_kitti_00: 14.1 -> 11.2 us per
-// iteration, profiles/r02_pcg5_shape_ab.log).
-constexpr int PCG5_BLOCK = 256;                    // LEGACY block; bounds the rows per CTA of every plan (2 * 256 / 6)
-template <bool BIG, int TUNED>
+// the launch shape
 struct Pcg5Shape {
-	static constexpr int BLOCK = TUNED ? 512 : PCG5_BLOCK;
-	static constexpr int BPT = TUNED ? 1 : 2;          // register-resident A^ blocks per thread (none with BIG)
-	static constexpr int REGBLK = BIG ? 0 : BLOCK * BPT;
-	static constexpr int CPT = 2;                      // blocks per thread and product round
+	static constexpr int BLOCK = 512;
+	static constexpr int BPT = 1;                      // register-resident A^ blocks per thread
+	static constexpr int REGBLK = BLOCK * BPT;         // 512, as in cuba_pcg5.cuh (PCG5_REGBLK)
+	static constexpr int CPT = 2;                      // blocks per thread and product round: the register block, then one cached block
 	static constexpr int CHUNK = BLOCK * CPT;
-	static constexpr int PCH = TUNED ? 3 : 8;          // polled words in flight per thread
+	static constexpr int PCH = 3;                      // polled words in flight per thread
 };
-constexpr int PCG5_REGBLK = 512;                   // both shapes keep 512 blocks in registers
-constexpr int PCG5_REPL = 8;                       // replicas of the partial / summary boards
-constexpr int PCG5_MAXWORLD = 8;
-constexpr int PCG5_TPR = 16;                       // threads per row of the coarse slice product
-
-// device-resident solve bookkeeping: read by every CTA at its start, changed only BETWEEN solves by k_pcg5_commit
-struct Pcg5Ctl { unsigned int tagBase; unsigned int solve; int abort; int nbad; unsigned int advance; int pad[3]; };
 
 struct Pcg5Dims {
 	int capBlocks, needMax, maxRows, nc, maxNeedAgg, zhInSmem;
@@ -117,133 +103,6 @@ struct Pcg5Args {
 	long long* timing;               // [G][8] per-phase clock64 sums (only with -DCUBA_PCG_TIMING)
 };
 
-// chol6_factor_and_inverse of cuba_pcg4.cuh with every loop unrolled: L and Li live in registers instead of local memory
-// (k_pcg5_prep_rows ran 53 us for 1 321 rows with the rolled version, profiles/r02_launches_k00_bench.csv).  Same operations
-// in the same order.
-template <typename T>
-__device__ __forceinline__ bool chol6_factor_and_inverse_u(const T* A, T* L, T* Li)
-{
-#pragma unroll
-	for (int i = 0; i < 36; i++) { L[i] = T(0); Li[i] = T(0); }
-	bool ok = true;
-#pragma unroll
-	for (int j = 0; j < 6; j++) {
-		T d = A[j * 6 + j];
-#pragma unroll
-		for (int k = 0; k < 6; k++) if (k < j) d -= L[k * 6 + j] * L[k * 6 + j];
-		if (!(d > T(0))) ok = false;
-		d = t_sqrt(ok ? d : T(1));
-		L[j * 6 + j] = d;
-		const T id = 1 / d;
-#pragma unroll
-		for (int i = 0; i < 6; i++) {
-			if (i <= j) continue;
-			T s = A[j * 6 + i];
-#pragma unroll
-			for (int k = 0; k < 6; k++) if (k < j) s -= L[k * 6 + i] * L[k * 6 + j];
-			L[j * 6 + i] = s * id;
-		}
-	}
-#pragma unroll
-	for (int j = 0; j < 6; j++) {
-		Li[j * 6 + j] = 1 / L[j * 6 + j];
-#pragma unroll
-		for (int i = 0; i < 6; i++) {
-			if (i <= j) continue;
-			T s = T(0);
-#pragma unroll
-			for (int k = 0; k < 6; k++) if (k >= j && k < i) s -= L[k * 6 + i] * Li[j * 6 + k];
-			Li[j * 6 + i] = s / L[i * 6 + i];
-		}
-	}
-	return ok;
-}
-
-// ---- preparation: factor every diagonal block, b^ = L^-1 b, Z^ = L^T Z, per-row share of rc0 = Z^^T b^ ----------------
-template <typename T>
-struct Pcg5PrepArgs {
-	const int* fRowPtr; const int* fColInd; const T* fVal; const T* b; const T* Zx;
-	int numP, A; const int* aggRow;
-	T* Linv; T* R0; T* Zhat; T* rcRow; T* rc0; Pcg5Ctl* ctl;
-};
-
-template <typename T>
-__global__ void k_pcg5_prep_rows(const Pcg5PrepArgs<T> a)
-{
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= a.numP) return;
-	// the diagonal block of row i: the columns of a row are ascending -> binary search (a linear walk is ~60 dependent loads)
-	int d = -1;
-	{
-		int lo = a.fRowPtr[i], hi = a.fRowPtr[i + 1] - 1;
-		while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.fColInd[mid] < i) lo = mid + 1; else hi = mid; }
-		if (lo <= hi && a.fColInd[lo] == i) d = lo;
-	}
-	T L[36], Li[36];
-	T Ad[36];
-#pragma unroll
-	for (int e = 0; e < 36; e++) Ad[e] = d >= 0 ? a.fVal[36 * (size_t)d + e] : T(0);
-	const bool ok = d >= 0 && chol6_factor_and_inverse_u(Ad, L, Li);
-	if (!ok) {
-		atomicAdd(&a.ctl->nbad, 1);
-#pragma unroll
-		for (int e = 0; e < 36; e++) { Li[e] = (e % 7) == 0 ? T(1) : T(0); L[e] = Li[e]; }
-	}
-#pragma unroll
-	for (int e = 0; e < 36; e++) a.Linv[36 * (size_t)i + e] = Li[e];
-	T bh[6], bi[6];
-#pragma unroll
-	for (int c = 0; c < 6; c++) bi[c] = a.b[6 * (size_t)i + c];
-#pragma unroll
-	for (int r = 0; r < 6; r++) {
-		T s = T(0);
-#pragma unroll
-		for (int c = 0; c < 6; c++) if (c <= r) s += Li[c * 6 + r] * bi[c];
-		bh[r] = s;
-		a.R0[6 * (size_t)i + r] = s;
-	}
-	if (a.A > 0) {
-		const T* Z = a.Zx + 36 * (size_t)i;
-#pragma unroll
-		for (int q = 0; q < 6; q++) {
-			T zq[6];
-#pragma unroll
-			for (int k = 0; k < 6; k++) zq[k] = Z[q * 6 + k];
-			T rcq = T(0);
-#pragma unroll
-			for (int r = 0; r < 6; r++) {
-				T s = T(0);
-#pragma unroll
-				for (int k = 0; k < 6; k++) if (k >= r) s += L[r * 6 + k] * zq[k];       // Z^(r,q) = sum_{k>=r} L(k,r) Z(k,q)
-				a.Zhat[36 * (size_t)i + q * 6 + r] = s;
-				rcq += s * bh[r];
-			}
-			a.rcRow[6 * (size_t)i + q] = rcq;
-		}
-	}
-}
-// rc0 of every aggregate: rows in ascending order (fixed order -> identical on every rank)
-template <typename T>
-__global__ void k_pcg5_prep_rc(const Pcg5PrepArgs<T> a)
-{
-	const int e = blockIdx.x * blockDim.x + threadIdx.x;
-	if (e >= 6 * a.A) return;
-	const int ag = e / 6, q = e - 6 * ag;
-	T s = T(0);
-	for (int i = a.aggRow[ag]; i < a.aggRow[ag + 1]; i++) s += a.rcRow[6 * (size_t)i + q];
-	a.rc0[e] = s;
-}
-
-__device__ __forceinline__ void ll_load_raw(const unsigned long long* slot, unsigned long long& lo, unsigned long long& hi)
-{
-	asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(slot));
-}
-__device__ __forceinline__ bool ll_decode(unsigned long long lo, unsigned long long hi, unsigned int tag, double& v)
-{
-	if ((unsigned int)(lo >> 32) != tag || (unsigned int)(hi >> 32) != tag) return false;
-	v = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
-	return true;
-}
 
 // Polls `n` LL words (slot of item i given by slotOf(i)) and hands every value to put(i, v); PCG5_PCH loads of a thread are in
 // flight together.  Returns false when the solve was aborted (a peer vanished: spin limit).
@@ -279,13 +138,11 @@ __device__ __forceinline__ bool ll_poll_many(int n, SlotOf slotOf, double* dst, 
 	return ll_poll_each<KB, KPCH>(n, slotOf, [dst](int i, double v) { dst[i] = v; }, tag, ctl);
 }
 
-// BIG: the CTA may own more than 42 rows (up to 85): every thread then serves two (row, component) pairs in the row sums
-template <typename T, bool BIG = false, int TUNED = 0>
-__global__ void __launch_bounds__((Pcg5Shape<BIG, TUNED>::BLOCK), 1) k_pcg5(const Pcg5Args<T> a)
+template <typename T>
+__global__ void __launch_bounds__(Pcg5Shape::BLOCK, 1) k_pcg5t(const Pcg5Args<T> a)
 {
-	static_assert(!(BIG && TUNED), "the tuned shape keeps the whole system on chip");
-	using Shape = Pcg5Shape<BIG, TUNED>;
-	// the names of the legacy constants, bound to this instantiation's shape
+	using Shape = Pcg5Shape;
+	// the names of cuba_pcg5.cuh's constants, bound to this shape
 	constexpr int PCG5_BLOCK = Shape::BLOCK, PCG5_BPT = Shape::BPT, PCG5_CPT = Shape::CPT, PCG5_CHUNK = Shape::CHUNK, PCG5_PCH = Shape::PCH;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const Pcg5Layout<T> lay(a.dims);
@@ -322,7 +179,6 @@ __global__ void __launch_bounds__((Pcg5Shape<BIG, TUNED>::BLOCK), 1) k_pcg5(cons
 	const int row0 = a.ctaRow[cta], row1 = a.ctaRow[cta + 1], nrows = row1 - row0;
 	const int need0 = a.needPtr[cta], nneed = a.needPtr[cta + 1] - need0;
 	const int blk0 = a.fRowPtr[row0], nblkCta = a.fRowPtr[row1] - blk0;
-	// BIG: no register-resident blocks -- the registers go to the loads in flight of the streamed part (see the product loop)
 	constexpr int REGBLK = Shape::REGBLK;
 	const int ncached = nblkCta > REGBLK ? (nblkCta - REGBLK < capBlocks ? nblkCta - REGBLK : capBlocks) : 0;
 	const size_t n6 = 6 * (size_t)a.numP;
@@ -397,7 +253,7 @@ __global__ void __launch_bounds__((Pcg5Shape<BIG, TUNED>::BLOCK), 1) k_pcg5(cons
 #pragma unroll
 		for (int u = 0; u < PCG5_BPT; u++) {
 			const int n = u * PCG5_BLOCK + tid;
-			if (!BIG && n < nblkCta) {
+			if (n < nblkCta) {
 				T out[36];
 				transform(n, out);
 #pragma unroll
@@ -413,10 +269,9 @@ __global__ void __launch_bounds__((Pcg5Shape<BIG, TUNED>::BLOCK), 1) k_pcg5(cons
 				for (int e = 0; e < 36; e++) s_blk[(size_t)e * capBlocks + m] = out[e];
 				s_loc[m] = a.fLocal[blk0 + n];
 			} else {
-				// past the shared-memory cache: the global copy.  BIG: block-major (a thread streams its 288 contiguous bytes with
-				// eighteen 16-byte loads in flight); else element-major inside this CTA's slice (coalesced 8-byte loads)
-				if (BIG) { for (int e = 0; e < 36; e++) a.fHat[36 * (size_t)(blk0 + n) + e] = out[e]; }
-				else { for (int e = 0; e < 36; e++) a.fHat[overBase + (size_t)e * nover + (m - ncached)] = out[e]; }
+				// past the shared-memory cache (the engine sizes this shape so that it does not happen): the global copy, element-major
+				// inside this CTA's slice
+				for (int e = 0; e < 36; e++) a.fHat[overBase + (size_t)e * nover + (m - ncached)] = out[e];
 			}
 		}
 	}
@@ -475,9 +330,9 @@ __global__ void __launch_bounds__((Pcg5Shape<BIG, TUNED>::BLOCK), 1) k_pcg5(cons
 				PCG_T(t1);
 				if (s_abort) { status = 3; break; }
 				double gnew, delta, rnew;
-				if (world == 1 && TUNED) {
-					// ---- one GPU, 16 warps: three of them add one scalar each over the CTAs (every warp adding all three, as below, keeps
-					//      the shared-memory and shuffle pipes busy for ~2 000 cycles); the others meet them at the barrier ----
+				if (world == 1) {
+					// ---- one GPU, 16 warps: three of them add one scalar each over the CTAs (every warp adding all three, as k_pcg5 does,
+					//      keeps the shared-memory and shuffle pipes busy for ~2 000 cycles); the others meet them at the barrier ----
 					if (wid < 3) {
 						double v = 0;
 						for (int c = lane; c < G; c += 32) v += s_pv[c * NP + wid];
@@ -486,12 +341,6 @@ __global__ void __launch_bounds__((Pcg5Shape<BIG, TUNED>::BLOCK), 1) k_pcg5(cons
 					}
 					__syncthreads();
 					gnew = s_ls[0]; delta = s_ls[1]; rnew = s_ls[2];
-				} else if (world == 1) {
-					// ---- one GPU: every warp adds the three scalars over the CTAs itself (same order everywhere), no barrier;
-					//      the restricted Z^^T w of an aggregate is summed by the thread that advances that coarse entry ----
-					double v0 = 0, v1 = 0, v2 = 0;
-					for (int c = lane; c < G; c += 32) { v0 += s_pv[c * NP]; v1 += s_pv[c * NP + 1]; v2 += s_pv[c * NP + 2]; }
-					gnew = warp_sum(v0); delta = warp_sum(v1); rnew = warp_sum(v2);
 				} else {
 				// ---- this GPU's summary: gamma, delta, rho over its CTAs (one warp each), Z^^T w per local aggregate ----
 				if (wid < 3) {
@@ -545,10 +394,10 @@ __global__ void __launch_bounds__((Pcg5Shape<BIG, TUNED>::BLOCK), 1) k_pcg5(cons
 					gamma = gnew;
 				}
 				if (k >= a.maxIters) { status = 1; break; }
-				// ---- advance s, r (needed columns), p, y (own rows; u_k is still in s_u) and the coarse residual.  TUNED: the coarse
+				// ---- advance s, r (needed columns), p, y (own rows; u_k is still in s_u) and the coarse residual: the coarse
 				//      residual first -- its product with Ac^-1 is published before r, s, p, y are advanced, so that the words
 				//      cross the L2 while this CTA still has work to do ----
-				if (!(TUNED && coarse)) advance_vectors();
+				if (!coarse) advance_vectors();
 				if (coarse)
 					for (int q = tid; q < nc; q += PCG5_BLOCK) {
 						// global aggregate q/6 = rank r, local aggregate al
@@ -581,7 +430,7 @@ __global__ void __launch_bounds__((Pcg5Shape<BIG, TUNED>::BLOCK), 1) k_pcg5(cons
 					sacc = warp_sum(sacc);
 					if (lane < PCG5_REPL) ll_store(cB + 2 * ((size_t)lane * nc + rowi), (double)sacc, ctag);
 				}
-				if (TUNED && k >= 0) advance_vectors();
+				if (k >= 0) advance_vectors();
 				{
 					const unsigned long long* cR = cB + 2 * ((size_t)rep * nc);
 					double* cdst = sizeof(T) == 8 ? reinterpret_cast<double*>(s_c) : s_pv;
@@ -618,7 +467,7 @@ __global__ void __launch_bounds__((Pcg5Shape<BIG, TUNED>::BLOCK), 1) k_pcg5(cons
 			const unsigned int otag = tagBase + (unsigned int)(k + 2);
 			const int opar = (k + 2) & 1;
 			// (row, component) pairs of this thread: pair tid / tpp, and -- only when the CTA owns more than 42 rows (tpp == 1) -- pair tid + BLOCK
-			constexpr int NPU = BIG ? 2 : 1;
+			constexpr int NPU = 1;                                // (row, component) pairs per thread: nrows * 6 <= BLOCK
 			T wacc[NPU];
 #pragma unroll
 			for (int pu = 0; pu < NPU; pu++) wacc[pu] = T(0);
@@ -629,7 +478,7 @@ __global__ void __launch_bounds__((Pcg5Shape<BIG, TUNED>::BLOCK), 1) k_pcg5(cons
 				for (int u = 0; u < PCG5_CPT; u++) {
 					const int n = cs + u * PCG5_BLOCK + tid;
 					T y[6] = { T(0), T(0), T(0), T(0), T(0), T(0) };
-					if (!BIG && u < PCG5_BPT && cs == 0) {
+					if (u < PCG5_BPT && cs == 0) {
 						const int ur = u < PCG5_BPT ? u : 0;
 						if (myLoc[ur] >= 0) {
 							const T* rj = s_v + 6 * (size_t)myLoc[ur];
@@ -654,22 +503,6 @@ __global__ void __launch_bounds__((Pcg5Shape<BIG, TUNED>::BLOCK), 1) k_pcg5(cons
 									const T rc = rj[c];
 #pragma unroll
 									for (int r = 0; r < 6; r++) y[r] += B[(c * 6 + r) * st] * rc;
-								}
-							} else if (BIG) {
-								// streamed block: all 288 bytes requested before the first use (measured: requesting the blocks of both
-								// chunk slots at once, 144 registers of loads in flight, is slower -- spills and L1 thrash: 123 vs 92 us)
-								const T* B = a.fHat + 36 * (size_t)(blk0 + n);
-								T bv[36];
-#pragma unroll
-								for (int x = 0; x < 36; x += 2) {      // plain (coherent) vector loads: this CTA wrote the block earlier in this launch
-									const typename V2<T>::type v2 = *reinterpret_cast<const typename V2<T>::type*>(B + x);
-									bv[x] = v2.x; bv[x + 1] = v2.y;
-								}
-#pragma unroll
-								for (int c = 0; c < 6; c++) {
-									const T rc = rj[c];
-#pragma unroll
-									for (int r = 0; r < 6; r++) y[r] += bv[c * 6 + r] * rc;
 								}
 							} else {
 								const T* B = a.fHat + overBase + (m - ncached);
@@ -711,101 +544,56 @@ __global__ void __launch_bounds__((Pcg5Shape<BIG, TUNED>::BLOCK), 1) k_pcg5(cons
 #ifdef CUBA_PCG_TIMING
 			long long t7 = 0;
 #endif
-			if constexpr (TUNED == 1) {
-				// Every (row, component) thread keeps its nine products in registers; a butterfly adds them over the warp, lane 0 leaves the
-				// warp's sums in shared memory and 9 x REPL threads add the eight warps in a fixed order and publish the replicas.
-				double* s_q = reinterpret_cast<double*>(smem_raw + lay.sq);   // [warps][9]; rewritten only after the next pass's barriers
-				double q9[9];
+			// Every (row, component) thread keeps its nine products in registers; a butterfly adds them over the warp, lane 0 leaves the
+			// warp's sums in shared memory and 9 x REPL threads add the eight warps in a fixed order and publish the replicas.
+			double* s_q = reinterpret_cast<double*>(smem_raw + lay.sq);   // [warps][9]; rewritten only after the next pass's barriers
+			double q9[9];
 #pragma unroll
-				for (int w = 0; w < 9; w++) q9[w] = 0.0;
+			for (int w = 0; w < 9; w++) q9[w] = 0.0;
 #pragma unroll
-				for (int pu = 0; pu < NPU; pu++) {
-					const int pair = tid / tpp + pu * PCG5_BLOCK;
-					if (!(pair < npairs && (tid % tpp) == 0 && (pu == 0 || tpp == 1))) continue;
-					const int li = pair / 6, comp = pair - 6 * li;
-					const int dl = s_diag[li];
-					const T ri = s_r[6 * (size_t)dl + comp];
-					const T ui = s_v[6 * (size_t)dl + comp];
-					const T wv1 = wacc[pu] + ui;                                   // A^_ii = I
-					const size_t slot = wHalf + (size_t)opar * wStride + 6 * (size_t)(row0 + li) + comp;
-					ll_store(a.wBoard + 2 * slot, (double)wv1, otag);
-					if (world > 1) {
-						unsigned int peers = a.rowPeers[row0 + li];
-						while (peers) {
-							const int pr = __ffs(peers) - 1;
-							peers &= peers - 1;
-							ll_store(a.peerW[pr] + 2 * slot, (double)wv1, otag);
-						}
-					}
-					q9[0] += (double)ri * (double)ui;
-					q9[1] += (double)wv1 * (double)ui;
-					q9[2] += (double)ri * (double)ri;
-					if (coarse) {
-						const T* Zh = a.dims.zhInSmem ? s_zh + 36 * (size_t)dl + comp : a.Zhat + 36 * (size_t)(row0 + li) + comp;
-#pragma unroll
-						for (int q = 0; q < 6; q++) q9[3 + q] += (double)(Zh[6 * q] * wv1);   // (Z^^T w)(q) = sum_comp Z^(comp,q) w(comp)
+			for (int pu = 0; pu < NPU; pu++) {
+				const int pair = tid / tpp + pu * PCG5_BLOCK;
+				if (!(pair < npairs && (tid % tpp) == 0 && (pu == 0 || tpp == 1))) continue;
+				const int li = pair / 6, comp = pair - 6 * li;
+				const int dl = s_diag[li];
+				const T ri = s_r[6 * (size_t)dl + comp];
+				const T ui = s_v[6 * (size_t)dl + comp];
+				const T wv1 = wacc[pu] + ui;                                   // A^_ii = I
+				const size_t slot = wHalf + (size_t)opar * wStride + 6 * (size_t)(row0 + li) + comp;
+				ll_store(a.wBoard + 2 * slot, (double)wv1, otag);
+				if (world > 1) {
+					unsigned int peers = a.rowPeers[row0 + li];
+					while (peers) {
+						const int pr = __ffs(peers) - 1;
+						peers &= peers - 1;
+						ll_store(a.peerW[pr] + 2 * slot, (double)wv1, otag);
 					}
 				}
+				q9[0] += (double)ri * (double)ui;
+				q9[1] += (double)wv1 * (double)ui;
+				q9[2] += (double)ri * (double)ri;
+				if (coarse) {
+					const T* Zh = a.dims.zhInSmem ? s_zh + 36 * (size_t)dl + comp : a.Zhat + 36 * (size_t)(row0 + li) + comp;
 #pragma unroll
-				for (int w = 0; w < 9; w++) if (w < NP) q9[w] = warp_sum(q9[w]);
-				if (lane == 0) {
-#pragma unroll
-					for (int w = 0; w < 9; w++) if (w < NP) s_q[wid * 9 + w] = q9[w];
+					for (int q = 0; q < 6; q++) q9[3 + q] += (double)(Zh[6 * q] * wv1);   // (Z^^T w)(q) = sum_comp Z^(comp,q) w(comp)
 				}
-				__syncthreads();
+			}
+#pragma unroll
+			for (int w = 0; w < 9; w++) if (w < NP) q9[w] = warp_sum(q9[w]);
+			if (lane == 0) {
+#pragma unroll
+				for (int w = 0; w < 9; w++) if (w < NP) s_q[wid * 9 + w] = q9[w];
+			}
+			__syncthreads();
 #ifdef CUBA_PCG_TIMING
-				t7 = clock64();
+			t7 = clock64();
 #endif
-				if (tid < NP * PCG5_REPL) {
-					const int word = tid / PCG5_REPL, rp = tid - word * PCG5_REPL;
-					double v = 0;
+			if (tid < NP * PCG5_REPL) {
+				const int word = tid / PCG5_REPL, rp = tid - word * PCG5_REPL;
+				double v = 0;
 #pragma unroll
-					for (int w8 = 0; w8 < PCG5_BLOCK / 32; w8++) v += s_q[w8 * 9 + word];
-					ll_store(a.pBoard + 2 * (pHalf + (size_t)opar * pStride + ((size_t)rp * G + lc) * NP + word), v, otag);
-				}
-			} else {
-				// The nine quantities of the (row, component) threads go to shared memory; afterwards warp w adds quantity w (with eight
-				// warps warp 0 also the ninth) in a fixed order and its first REPL lanes publish the replicas.
-				const int nact = nrows * 6;                           // active threads: tid = pair * tpp
-				double* s_q = reinterpret_cast<double*>(smem_raw + lay.sq);   // [9][nact]; read below, rewritten only after the next pass's barriers
-#pragma unroll
-				for (int pu = 0; pu < NPU; pu++) {
-					const int pair = tid / tpp + pu * PCG5_BLOCK;
-					if (!(pair < npairs && (tid % tpp) == 0 && (pu == 0 || tpp == 1))) continue;
-					const int li = pair / 6, comp = pair - 6 * li;
-					const int dl = s_diag[li];
-					const T ri = s_r[6 * (size_t)dl + comp];
-					const T ui = s_v[6 * (size_t)dl + comp];
-					const T wv1 = wacc[pu] + ui;                                   // A^_ii = I
-					const size_t slot = wHalf + (size_t)opar * wStride + 6 * (size_t)(row0 + li) + comp;
-					ll_store(a.wBoard + 2 * slot, (double)wv1, otag);
-					if (world > 1) {
-						unsigned int peers = a.rowPeers[row0 + li];
-						while (peers) {
-							const int pr = __ffs(peers) - 1;
-							peers &= peers - 1;
-							ll_store(a.peerW[pr] + 2 * slot, (double)wv1, otag);
-						}
-					}
-					s_q[pair] = (double)ri * (double)ui;
-					s_q[nact + pair] = (double)wv1 * (double)ui;
-					s_q[2 * nact + pair] = (double)ri * (double)ri;
-					if (coarse) {
-						const T* Zh = a.dims.zhInSmem ? s_zh + 36 * (size_t)dl + comp : a.Zhat + 36 * (size_t)(row0 + li) + comp;
-#pragma unroll
-						for (int q = 0; q < 6; q++) s_q[(3 + q) * nact + pair] = (double)(Zh[6 * q] * wv1);   // (Z^^T w)(q) = sum_comp Z^(comp,q) w(comp)
-					}
-				}
-				__syncthreads();
-#ifdef CUBA_PCG_TIMING
-				t7 = clock64();
-#endif
-				for (int word = wid; word < NP; word += PCG5_BLOCK / 32) {
-					double v = 0;
-					for (int i = lane; i < nact; i += 32) v += s_q[word * nact + i];
-					v = warp_sum(v);
-					if (lane < PCG5_REPL) ll_store(a.pBoard + 2 * (pHalf + (size_t)opar * pStride + ((size_t)lane * G + lc) * NP + word), v, otag);
-				}
+				for (int w8 = 0; w8 < PCG5_BLOCK / 32; w8++) v += s_q[w8 * 9 + word];
+				ll_store(a.pBoard + 2 * (pHalf + (size_t)opar * pStride + ((size_t)rp * G + lc) * NP + word), v, otag);
 			}
 			PCG_T(t8);
 			PCG_ACC(3, t4, t5); PCG_ACC(4, t5, t6); PCG_ACC(5, t6, t7); PCG_ACC(6, t7, t8);
@@ -833,14 +621,6 @@ __global__ void __launch_bounds__((Pcg5Shape<BIG, TUNED>::BLOCK), 1) k_pcg5(cons
 	}
 }
 
-// between solves: move the tag base past every tag the finished solve used, flip the solve parity, clear the breakdown counter
-__global__ void k_pcg5_commit(Pcg5Ctl* ctl)
-{
-	ctl->tagBase += ctl->advance;
-	ctl->solve += 1;
-	ctl->nbad = 0;
-	ctl->advance = 0;
-}
 
 }  // namespace p5t
 }  // namespace cuba_b200

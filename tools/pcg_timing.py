@@ -22,7 +22,8 @@ VARIANT = int(os.environ.get("PCG_VARIANT", "0"))
 names = ["poll", "sync_after_poll", "scalars", "update+sync", "spmv", "reduce+sync", "publish"] if VARIANT not in (3, 5, 6) else \
     ["loads+scalars", "rc+owners+gather", "coarse slices", "u", "spmv+restrict", "reduce+publish", "grid barrier"]
 if VARIANT in (5, 6):   # k_pcg5
-    names = ["poll w + partials", "local sums (+rank hop) + scalars", "advance rc (BJ: r,s,p,y)", "coarse rows, advance r,s,p,y, poll c, u", "spmv + row sums", "publish w + butterfly sums", "publish partials"]
+    # one-GPU on-chip solves run the tuned shape (cuba_pcg5t.cuh), CUBA_PCG5_LEGACY=1 / large systems the legacy one (cuba_pcg5.cuh)
+    names = ["poll w + partials", "local sums (+rank hop) + scalars", "advance rc (legacy: + r,s,p,y)", "coarse rows (tuned: + advance r,s,p,y), poll c, u", "spmv + row sums", "publish w + partial products", "publish partials"]
 for workload in sys.argv[1:] or ["kitti00_shaped"]:
     path = os.path.join(ROOT, "oracle", "_ref", "fixtures", workload + ".cubagraph")
     g = pkg.graphio.read_graph(path) if workload.startswith("ba_") else pkg.synth.make_config(workload)
