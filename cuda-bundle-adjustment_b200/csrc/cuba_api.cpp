@@ -300,10 +300,7 @@ public:
 		if (!uploaded_) {
 			// the reference builds its structure inside the first optimize() iteration (cpp:804-805)
 			cuba_problem p;
-			p.Pall = static_cast<int32_t>(vP_.size()); p.numP = numP_; p.Lall = static_cast<int32_t>(vL_.size()); p.numL = numL_;
-			p.q = q_.data(); p.t = t_.data(); p.cam = cam_.data(); p.Xw = Xw_.data();
-			p.E2 = static_cast<int32_t>(om2_.size()); p.idx2 = idx2_.data(); p.meas2 = meas2_.data(); p.omega2 = om2_.data();
-			p.E3 = static_cast<int32_t>(om3_.size()); p.idx3 = idx3_.data(); p.meas3 = meas3_.data(); p.omega3 = om3_.data();
+			flatProblem(p);
 			check(cuba_engine_set_problem(engine_, &p));
 			uploaded_ = true;
 		}
@@ -334,6 +331,17 @@ public:
 		profile_.clear();
 		for (int i = 0; i < CUBA_PROF_NUM; i++) profile_[names[i]] = sec[i];
 		profile_[names[0]] += initSeconds_;
+	}
+
+	// the flat arrays of the last initialize() (also behind cuba_debug_dropin_problem)
+	bool flatProblem(cuba_problem& p) const
+	{
+		if (!initialized_) return false;
+		p.Pall = static_cast<int32_t>(vP_.size()); p.numP = numP_; p.Lall = static_cast<int32_t>(vL_.size()); p.numL = numL_;
+		p.q = q_.data(); p.t = t_.data(); p.cam = cam_.data(); p.Xw = Xw_.data();
+		p.E2 = static_cast<int32_t>(om2_.size()); p.idx2 = idx2_.data(); p.meas2 = meas2_.data(); p.omega2 = om2_.data();
+		p.E3 = static_cast<int32_t>(om3_.size()); p.idx3 = idx3_.data(); p.meas3 = meas3_.data(); p.omega3 = om3_.data();
+		return true;
 	}
 
 	void clear() override
@@ -439,6 +447,18 @@ private:
 } // namespace
 
 CudaBundleAdjustment::Ptr CudaBundleAdjustment::create() { return Ptr(new Impl()); }
+
+// include/cuba_b200.h: cuba_debug_dropin_problem
+static bool dropin_problem(CudaBundleAdjustment* obj, cuba_problem* out)
+{
+	const Impl* impl = dynamic_cast<const Impl*>(obj);
+	return impl && out && impl->flatProblem(*out);
+}
 CudaBundleAdjustment::~CudaBundleAdjustment() {}
 
 } // namespace cuba
+
+extern "C" int cuba_debug_dropin_problem(void* dropin, cuba_problem* out)
+{
+	return cuba::dropin_problem(static_cast<cuba::CudaBundleAdjustment*>(dropin), out) ? CUBA_OK : CUBA_ERR_STATE;
+}

@@ -226,6 +226,10 @@ int cuba_debug_pcg_partition(const cuba_problem* p, int nCtas, int maxAgg, int32
  * CTAs, aggregates aligned with the ranks, halo masks.  info[8] = ok (0: system too small for this kernel), G, gs, A, needMax,
  * maxRows, maxNeedAgg, number of halo rows.  No device needed. */
 int cuba_debug_pcg5_plan(const cuba_problem* p, int world, int numSMs, int maxAgg, int32_t* info);
+/* The flat arrays the drop-in class (cuba::CudaBundleAdjustment, csrc/cuba_api.cpp) built in its last initialize(): what optimize()
+ * hands to cuba_engine_set_problem.  `dropin` is the object's address; the pointers stay valid until the next initialize().
+ * Needs no GPU (tests of the graph container: tombstones, re-added edges, fixed vertices, vertices without edges). */
+int cuba_debug_dropin_problem(void* dropin, cuba_problem* out);
 
 /* ---- micro-benchmark hooks for bench.py / profiles (device-resident data, CUDA-event timed) ---- */
 /* Runs the named stage `reps` times back to back and returns the average device milliseconds per
