@@ -112,12 +112,14 @@ public:
 	void addMonocularEdge(MonoEdge* e) override
 	{
 		if (!member_.insert(e).second) return;
+		edgeVersion_++;
 		mono_.push_back(e);
 		e->vertexP->edges.insert(e); e->vertexL->edges.insert(e);
 	}
 	void addStereoEdge(StereoEdge* e) override
 	{
 		if (!member_.insert(e).second) return;
+		edgeVersion_++;
 		stereo_.push_back(e);
 		e->vertexP->edges.insert(e); e->vertexL->edges.insert(e);
 	}
@@ -149,6 +151,7 @@ public:
 		if (auto p = e->poseVertex()) p->edges.erase(e);
 		if (auto l = e->landmarkVertex()) l->edges.erase(e);
 		if (!member_.erase(e)) return;
+		edgeVersion_++;
 		tombstones_[e]++;
 		(e->dim() == 2 ? deadMono_ : deadStereo_)++;
 	}
@@ -176,6 +179,9 @@ public:
 			orderDirty_ = false;
 		}
 		// index assignment: ascending id, free vertices first, fixed ones appended, vertices without edges skipped
+		// (if neither the numbering nor the edge lists moved since the last initialize(), the edge pass below only refreshes values)
+		prevP_.swap(vP_);
+		const int prevNumP = numP_, prevNumL = numL_;
 		vP_.clear();
 		vP_.reserve(orderP_.size());
 		size_t nFixedP = 0, nFixedL = 0;
@@ -202,20 +208,27 @@ public:
 			for (unsigned t = 0; t < nt; t++) { cntFree[t + 1] += cntFree[t]; cntFixed[t + 1] += cntFixed[t]; }
 			numL_ = static_cast<int>(cntFree[nt]);
 			nFixedL = cntFixed[nt];
+			sameNumbering_ = vL_.size() == cntFree[nt] + cntFixed[nt] && numL_ == prevNumL;
 			vL_.resize(cntFree[nt] + cntFixed[nt]);
 			Xw_.resize(3 * vL_.size());
+			std::vector<unsigned char> moved(nt, 0);
 			parallel_slices(nl, nt, [&](unsigned tix, size_t b, size_t e) {
 				size_t wf = cntFree[tix], wx = cntFree[nt] + cntFixed[tix];
+				unsigned char mv = 0;
 				for (size_t i = b; i < e; i++) {
 					if (i + 8 < e) __builtin_prefetch(orderL_[i + 8], 1);
 					if (!cls_[i]) continue;
 					LandmarkVertex* v = orderL_[i];
 					const size_t w = cls_[i] == 1 ? wf++ : wx++;
+					mv |= vL_[w] != v;
 					v->iL = static_cast<int>(w); vL_[w] = v;
 					for (int k = 0; k < 3; k++) Xw_[3 * w + k] = v->Xw.data()[k];
 				}
+				moved[tix] = mv;
 			});
+			for (unsigned char mv : moved) if (mv) sameNumbering_ = false;
 		}
+		sameNumbering_ = sameNumbering_ && numP_ == prevNumP && vP_ == prevP_;
 
 		q_.resize(4 * vP_.size()); t_.resize(3 * vP_.size()); cam_.resize(5 * vP_.size());
 		for (size_t i = 0; i < vP_.size(); i++) {
@@ -230,10 +243,34 @@ public:
 		// turned up (they are dropped, cpp:210-211) the arrays are closed up afterwards
 		idx2_.resize(2 * mono_.size()); meas2_.resize(2 * mono_.size()); om2_.resize(mono_.size());
 		idx3_.resize(2 * stereo_.size()); meas3_.resize(3 * stereo_.size()); om3_.resize(stereo_.size());
-		auto am = takeList(mono_.size());
-		auto as = takeList(stereo_.size());
 		const size_t n2 = mono_.size(), n3 = stereo_.size(), total = n2 + n3;
 		const unsigned nthreads = host_threads(total, 65536);
+		if (flatValid_ && sameNumbering_ && flatVersion_ == edgeVersion_ && om2_.size() == n2 && om3_.size() == n3) {
+			// same edges in the same order between the same indices, none dropped: the index pairs and the position -> edge lists of
+			// the last initialize() still hold; the caller may have edited measurements / information in place
+			parallel_slices(total, nthreads, [&](unsigned, size_t b, size_t e) {
+				for (size_t k = b; k < e; k++) {
+					if (k + 16 < e) __builtin_prefetch(k + 16 < n2 ? static_cast<const void*>(mono_[k + 16]) : static_cast<const void*>(stereo_[k + 16 - n2]));
+					if (k < n2) {
+						const MonoEdge* ed = mono_[k];
+						meas2_[2 * k] = ed->measurement.data()[0]; meas2_[2 * k + 1] = ed->measurement.data()[1];
+						om2_[k] = ed->information;
+					} else {
+						const size_t j = k - n2;
+						const StereoEdge* ed = stereo_[j];
+						for (int c = 0; c < 3; c++) meas3_[3 * j + c] = ed->measurement.data()[c];
+						om3_[j] = ed->information;
+					}
+				}
+			});
+			stats_.clear();
+			uploaded_ = false;
+			initSeconds_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+			initialized_ = true;
+			return;
+		}
+		auto am = takeList(mono_.size());
+		auto as = takeList(stereo_.size());
 		std::vector<size_t> dropped(nthreads, 0);
 		parallel_slices(total, nthreads, [&](unsigned tix, size_t b, size_t e) {
 			// two prefetch distances: the edge object 16 ahead, its landmark (read through the edge) 8 ahead
@@ -285,6 +322,7 @@ public:
 			as->resize(w); idx3_.resize(2 * w); meas3_.resize(3 * w); om3_.resize(w);
 		}
 		activeMono_ = am; activeStereo_ = as;
+		flatValid_ = ndrop == 0; flatVersion_ = edgeVersion_;
 		stats_.clear();
 		uploaded_ = false;
 		initSeconds_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -348,6 +386,7 @@ public:
 	{
 		poses_.clear(); landmarks_.clear(); mono_.clear(); stereo_.clear(); member_.clear(); tombstones_.clear();
 		deadMono_ = deadStereo_ = 0; orderDirty_ = true;
+		edgeVersion_++; flatValid_ = false;
 		stats_.clear(); initialized_ = false; uploaded_ = false;
 	}
 
@@ -426,8 +465,10 @@ private:
 	size_t deadMono_ = 0, deadStereo_ = 0;
 	Kernel kernels_[2];
 
-	std::vector<PoseVertex*> vP_;
+	std::vector<PoseVertex*> vP_, prevP_;
 	std::vector<LandmarkVertex*> vL_;
+	size_t edgeVersion_ = 0, flatVersion_ = 0;   // edits of the edge lists / the version the flat edge arrays were built from
+	bool flatValid_ = false, sameNumbering_ = false;
 	std::shared_ptr<const std::vector<const BaseEdge*>> activeMono_, activeStereo_, chiMono_, chiStereo_;
 	std::vector<std::shared_ptr<std::vector<const BaseEdge*>>> listPool_;
 	std::vector<unsigned char> cls_;
