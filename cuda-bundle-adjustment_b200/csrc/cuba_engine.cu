@@ -1260,7 +1260,7 @@ struct Engine : EngineBase {
 		int G = std::max((numP + 7) / 8, (int)((matBytes + budget - 1) / std::max<size_t>(budget, 1)));
 		G = std::max(1, std::min(G, std::min(numSMs, numP)));
 		// row partition, need lists, block-local column positions: cuba_structure.cpp (CPU-tested)
-		PcgPartition PP;
+		PcgPartition& PP = hostPP;                     // kept: k_pcg5's plan starts from the same partition when its CTA count is the same
 		build_pcg_partition(numP, S.nfull, S.fRowPtr, S.fColInd, G, PP);
 		const std::vector<int>& rows = PP.rows; const std::vector<int>& nptr = PP.nptr; const std::vector<int>& ncol = PP.ncol; const std::vector<int>& local = PP.local;
 		const int needMax = PP.needMax, blkMax = PP.blkMax, maxRows = PP.maxRows;
@@ -1455,6 +1455,7 @@ struct Engine : EngineBase {
 	void* p5PeerBase[PCG5_MAXWORLD] = { nullptr };   // cudaIpc mappings of the peers' boards (own entry: the local allocation)
 	void* p5MappedFor = nullptr;                   // local allocation the mappings were exchanged for
 	size_t p5WWords = 0, p5PWords = 0, p5RWords = 0, p5CWords = 0;
+	PcgPartition hostPP;                           // host copy of k_pcg3's row partition of the current system (setup_pcg2)
 	Pcg5Dims p5Dims{}, p5DimsBJ{};
 	size_t p5Smem = 0;
 	int p5G = 0, p5W = 1, p5A = 0, p5Gs = 1;
@@ -1563,7 +1564,7 @@ struct Engine : EngineBase {
 		// row sums), rank-aligned aggregates, halo masks: cuba_structure.cpp (CPU-tested through cuba_debug_pcg5_plan)
 		const int maxAgg = (cfg.reserved[6] > 0 && cfg.reserved[6] < PCG5_MAXAGG) ? cfg.reserved[6] : PCG5_MAXAGG;
 		Pcg5Plan plan;
-		build_pcg5_plan(numP, S.nfull, S.fRowPtr, S.fColInd, W, numSMs, maxAgg, 2 * PCG5_BLOCK / 6, plan);
+		build_pcg5_plan(numP, S.nfull, S.fRowPtr, S.fColInd, W, numSMs, maxAgg, 2 * PCG5_BLOCK / 6, plan, &hostPP);
 		if (!plan.ok) return CUBA_OK;
 		const int G = plan.G, gs = plan.gs, A = plan.A;
 		const PcgPartition& PP = plan.P; const CoarsePartition& CP = plan.C;

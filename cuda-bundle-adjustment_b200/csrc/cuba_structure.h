@@ -110,8 +110,9 @@ struct Pcg5Plan {
 	CoarsePartition C;
 	std::vector<unsigned char> rowPeers;
 };
+// `same`: a partition of the same system the caller already has (k_pcg3's); copied instead of rebuilt when its CTA count fits.
 void build_pcg5_plan(int numP, int nfull, const std::vector<int>& fRowPtr, const std::vector<int>& fColInd, int world, int numSMs, int maxAgg,
-	int maxRowsPerCta, Pcg5Plan& plan);
+	int maxRowsPerCta, Pcg5Plan& plan, const PcgPartition* same = nullptr);
 // invariants of a plan (nullptr when everything holds)
 const char* check_pcg5_plan(int numP, int nfull, const std::vector<int>& fRowPtr, const std::vector<int>& fColInd, const Pcg5Plan& plan);
 
